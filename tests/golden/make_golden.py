@@ -1,0 +1,190 @@
+"""Generate golden vectors by running the UNMODIFIED reference in the build container.
+
+    python tests/golden/make_golden.py            # needs /root/reference (absent on the GPU box)
+
+The reference modules `src/clip/eval/metrics.py` and `fusion.py` import with numpy only;
+`src/retrieval.py` is imported with four stubs (its import logs in to the HF hub and needs
+`mistralai` / `SPARQLWrapper`) and `RetrievalEngine.__new__` so that the
+network-bound constructor never runs.  Outputs: `tests/golden/*.npz|json`, committed.
+Inputs are produced by `knowledge_enhanced_multimodal_retrieval_b200.synth` and stored as
+bf16 bit patterns so the fixtures do not depend on the generator staying unchanged.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("KEMR_REFERENCE", "/root/reference")
+
+from knowledge_enhanced_multimodal_retrieval_b200 import synth  # noqa: E402
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    from src.clip.eval import metrics as rmetrics, fusion as rfusion
+    import huggingface_hub
+    huggingface_hub.login = lambda *a, **k: None
+    huggingface_hub.hf_hub_download = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("offline"))
+    for name, attrs in (("mistralai", ("Mistral",)), ("SPARQLWrapper", ("SPARQLWrapper", "JSON")),
+                        ("dotenv", ())):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                m = types.ModuleType(name)
+                for a in attrs:
+                    setattr(m, a, object)
+                if name == "dotenv":
+                    m.load_dotenv = lambda *a, **k: None
+                sys.modules[name] = m
+    import src.retrieval as rretrieval
+    return rmetrics, rfusion, rretrieval
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def f64dict(d):
+    return {k: float(v) for k, v in d.items()}
+
+
+def main():
+    rmetrics, rfusion, rretrieval = import_reference()
+    out_json = {}
+
+    # ------------------------------------------------------------------ metrics, small
+    s = synth.make_retrieval_set(Q=96, M=160, D=64, seed=11, fused=True, lam=0.6, with_kg=True)
+    q, img, tgt = s.query, s.image, s.target
+    m = {}
+    m["retrieval_metrics_T2I"] = f64dict(rmetrics.compute_retrieval_metrics(q, img, prefix="T2I"))
+    m["retrieval_metrics_noprefix_k"] = f64dict(
+        rmetrics.compute_retrieval_metrics(q, tgt, k_values=[1, 3, 7]))
+    m["final_05_05"] = f64dict(quiet(rmetrics.compute_retrieval_metrics_final, q, tgt, img))
+    m["final_01_09"] = f64dict(quiet(rmetrics.compute_retrieval_metrics_final, q, tgt, img,
+                                     prefix="F", t2i_weight=0.1, t2t_weight=0.9))
+    # the "all" variants need square inputs (I2T scores image i against target i)
+    sq = synth.make_retrieval_set(Q=128, M=128, D=64, seed=12, fused=True, lam=0.5)
+    m["all"] = f64dict(rmetrics.compute_all_retrieval_metrics(sq.query, sq.target, sq.image))
+    m["all_T2I_T2T_mrr_only"] = f64dict(rmetrics.compute_all_retrieval_metrics(
+        sq.query, sq.target, sq.image, tasks=["T2I", "T2T"], compute_recall=False))
+    m["training"] = f64dict(rmetrics.compute_training_metrics(sq.query, sq.target, sq.image))
+    sim = (q @ img.T).astype(np.float32)
+    m["recall_at_k_matrix"] = f64dict(rmetrics.compute_recall_at_k(sim))
+    m["mrr_matrix"] = f64dict(rmetrics.compute_mrr_and_mean_rank(sim))
+    m["metrics_fusion_matrix"] = f64dict(rmetrics.compute_retrieval_metrics_fusion(sim, prefix="X"))
+    m["evaluate_retrieval"] = f64dict(quiet(rfusion.evaluate_retrieval, sim))
+    out_json["metrics_small"] = m
+
+    # ------------------------------------------------------------------ dense KG fusion, small
+    fus = {}
+    args = (sim, s.kg_results, s.query_uuids, s.uuids)
+    fus["weighted_default"] = rfusion.weighted_fusion(*args)
+    fus["weighted_09_01"] = rfusion.weighted_fusion(*args, alpha=0.9, sparql_weight=1 - 0.9)
+    fus["weighted_renorm"] = quiet(rfusion.weighted_fusion, *args, alpha=0.6, sparql_weight=0.6)
+    fus["additive_default"] = rfusion.additive_bonus_fusion(*args)
+    fus["additive_013"] = rfusion.additive_bonus_fusion(*args, delta=0.13)
+    fus["adaptive_default"] = rfusion.adaptive_additive_fusion(*args)
+    fus["adaptive_custom"] = rfusion.adaptive_additive_fusion(
+        *args, delta=0.3, size_thresholds={2: 0.9, 10: 0.4, 25: 0.05})
+    fus["dispatch_weighted"] = rfusion.fuse_clip_and_text2sparql(
+        *args, fusion_strategy="weighted", fusion_params={"alpha": 0.4, "sparql_weight": 0.6})
+    fus["dispatch_additive"] = rfusion.fuse_clip_and_text2sparql(*args, fusion_strategy="additive")
+    fus["dispatch_adaptive"] = rfusion.fuse_clip_and_text2sparql(
+        *args, fusion_strategy="adaptive", fusion_params={"delta": 0.25})
+    fm = {}
+    for name, mat in fus.items():
+        assert mat.dtype == np.float32, (name, mat.dtype)
+        fm[name] = f64dict(quiet(rfusion.evaluate_retrieval, mat))
+    out_json["fusion_small_metrics"] = fm
+    np.savez_compressed(
+        os.path.join(HERE, "small_set.npz"),
+        query_bits=synth.f32_to_bf16_bits(q), image_bits=synth.f32_to_bf16_bits(img),
+        target_bits=synth.f32_to_bf16_bits(tgt), sim=sim,
+        sq_query_bits=synth.f32_to_bf16_bits(sq.query), sq_image_bits=synth.f32_to_bf16_bits(sq.image),
+        sq_target_bits=synth.f32_to_bf16_bits(sq.target),
+        **{f"fusion_{k}": v for k, v in fus.items()})
+    with open(os.path.join(HERE, "small_set_kg.json"), "w") as f:
+        json.dump({"kg_results": s.kg_results, "query_uuids": s.query_uuids, "uuids": s.uuids}, f)
+
+    # ------------------------------------------------------------------ metrics, mid size (seed-regenerated)
+    mid = synth.make_retrieval_set(Q=1500, M=1500, D=128, seed=23, fused=True, lam=0.4, with_kg=True)
+    mm = {"checksum": [float(mid.query.astype(np.float64).sum()), float(mid.image.astype(np.float64).sum()),
+                       float(mid.target.astype(np.float64).sum())]}
+    mm["all"] = f64dict(rmetrics.compute_all_retrieval_metrics(mid.query, mid.target, mid.image))
+    for wi, wt in ((0.5, 0.5), (0.1, 0.9)):
+        mm[f"final_{wi}_{wt}"] = f64dict(quiet(rmetrics.compute_retrieval_metrics_final,
+                                               mid.query, mid.target, mid.image,
+                                               t2i_weight=wi, t2t_weight=wt))
+        fusedsim = (wi * (mid.query @ mid.image.T)) + (wt * (mid.query @ mid.target.T))
+        for alpha in (0.9, 0.5, 0.1):            # evaluator.py:176-190 sweep (subset)
+            fw = rfusion.fuse_clip_and_text2sparql(
+                fusedsim, mid.kg_results, mid.query_uuids, mid.uuids, "weighted",
+                {"alpha": alpha, "sparql_weight": 1 - alpha})
+            mm[f"sweep_{wi}_{wt}_alpha{alpha}"] = f64dict(quiet(rfusion.evaluate_retrieval, fw))
+    out_json["metrics_mid"] = mm
+    # a set whose targets sit deep in the score bulk: fp32 near-ties next to the target exist,
+    # so the reference's own numbers depend on its BLAS; kept to test that any deviation of
+    # the canonical contract is confined to those audited rows
+    nt = synth.make_retrieval_set(Q=1500, M=1500, D=128, seed=21, fused=True, lam=0.25)
+    out_json["metrics_mid_nearties"] = {
+        "final_0.5_0.5": f64dict(quiet(rmetrics.compute_retrieval_metrics_final, nt.query, nt.target, nt.image))}
+
+    # ------------------------------------------------------------------ serving-engine list fusion
+    eng = rretrieval.RetrievalEngine.__new__(rretrieval.RetrievalEngine)
+    rng = np.random.default_rng(5)
+    cases = []
+    for n in (0, 1, 7, 40):
+        clip = [{"uuid": f"a{j}", "score": float(np.float32(rng.uniform(-0.2, 0.9)))} for j in range(n)]
+        clip.sort(key=lambda d: -d["score"])
+        if n >= 7:                                  # exact and rounding-induced ties
+            clip[3]["score"] = clip[2]["score"]
+            clip[5]["score"] = clip[4]["score"] - 1e-6
+        sparql = [f"a{j}" for j in rng.integers(0, max(n, 1), size=n // 3)] + ["zz-not-in-clip"]
+        for alpha, beta in ((0.8, 0.2), (0.5, 0.5), (1.0, 0.0)):
+            fused = eng._fuse_clip_sparql_linear(clip, sparql, alpha=alpha, beta=beta)
+            cases.append({"clip": clip, "sparql": sparql, "alpha": alpha, "beta": beta, "out": fused})
+
+    class FakeClip:
+        def __init__(self, res):
+            self.res = res
+
+        def retrieval(self, query, alpha=0.5):
+            return self.res
+
+    class FakeT2S:
+        def __init__(self, res):
+            self.res = res
+
+        def retrieval(self, query):
+            return self.res
+
+    eng.clip_retriever = FakeClip(cases[-1]["clip"])
+    eng.t2s_retriever = FakeT2S(cases[-1]["sparql"])
+    engine_calls = {
+        "retrieve_text_default": eng.retrieve_text("q"),
+        "retrieve_text_thr": eng.retrieve_text("q", alpha=0.6, beta=0.4, threshold=0.3),
+        "noknowledge_default": eng.retrieve_text_noknowledge("q"),
+        "noknowledge_thr": eng.retrieve_text_noknowledge("q", threshold=0.25),
+    }
+    out_json["engine"] = {"fuse_cases": cases, "calls": engine_calls,
+                          "call_inputs": {"clip": cases[-1]["clip"], "sparql": cases[-1]["sparql"]}}
+
+    import numpy
+    out_json["provenance"] = {"numpy": numpy.__version__, "reference": REF,
+                              "note": "outputs of the unmodified reference functions"}
+    with open(os.path.join(HERE, "golden.json"), "w") as f:
+        json.dump(out_json, f, indent=1, sort_keys=True)
+    print("wrote", os.path.join(HERE, "golden.json"))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+"""CPU: the numpy oracle reproduces every golden vector produced by the unmodified reference."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from knowledge_enhanced_multimodal_retrieval_b200 import synth
+
+
+def same(d_got, d_want):
+    assert set(d_got) == set(d_want)
+    for k in d_want:
+        assert float(d_got[k]) == d_want[k], (k, float(d_got[k]), d_want[k])
+
+
+def test_ref_metrics_small(golden, small_set):
+    g = golden["metrics_small"]
+    q, img, tgt, sim = (small_set[k] for k in ("query", "image", "target", "sim"))
+    same(O.ref_retrieval_metrics(q, img, prefix="T2I"), g["retrieval_metrics_T2I"])
+    same(O.ref_retrieval_metrics(q, tgt, k_values=[1, 3, 7]), g["retrieval_metrics_noprefix_k"])
+    same(O.ref_retrieval_metrics_final(q, tgt, img), g["final_05_05"])
+    same(O.ref_retrieval_metrics_final(q, tgt, img, prefix="F", t2i_weight=0.1, t2t_weight=0.9),
+         g["final_01_09"])
+    sq = [small_set[k] for k in ("sq_query", "sq_target", "sq_image")]
+    same(O.ref_all_retrieval_metrics(*sq), g["all"])
+    same(O.ref_all_retrieval_metrics(*sq, tasks=["T2I", "T2T"], compute_recall=False),
+         g["all_T2I_T2T_mrr_only"])
+    same(O.ref_all_retrieval_metrics(*sq, compute_recall=False), g["training"])
+    same(O.ref_recall_at_k(sim), g["recall_at_k_matrix"])
+    same(O.ref_mrr_and_mean_rank(sim), g["mrr_matrix"])
+    same(O.ref_metrics_from_matrix(sim, prefix="X"), g["metrics_fusion_matrix"])
+    same(O.ref_metrics_from_matrix(sim), g["evaluate_retrieval"])
+
+
+def test_ref_fusion_small_bit_exact(golden, small_set):
+    sim = small_set["sim"]
+    a = (sim, small_set["kg_results"], small_set["query_uuids"], small_set["uuids"])
+    got = {
+        "weighted_default": O.ref_weighted_fusion(*a),
+        "weighted_09_01": O.ref_weighted_fusion(*a, alpha=0.9, sparql_weight=1 - 0.9),
+        "weighted_renorm": O.ref_weighted_fusion(*a, alpha=0.6, sparql_weight=0.6),
+        "additive_default": O.ref_additive_bonus_fusion(*a),
+        "additive_013": O.ref_additive_bonus_fusion(*a, delta=0.13),
+        "adaptive_default": O.ref_adaptive_additive_fusion(*a),
+        "adaptive_custom": O.ref_adaptive_additive_fusion(*a, delta=0.3,
+                                                          size_thresholds={2: 0.9, 10: 0.4, 25: 0.05}),
+        "dispatch_weighted": O.ref_fuse_clip_and_text2sparql(*a, fusion_strategy="weighted",
+                                                             fusion_params={"alpha": 0.4, "sparql_weight": 0.6}),
+        "dispatch_additive": O.ref_fuse_clip_and_text2sparql(*a, fusion_strategy="additive"),
+        "dispatch_adaptive": O.ref_fuse_clip_and_text2sparql(*a, fusion_strategy="adaptive",
+                                                             fusion_params={"delta": 0.25}),
+    }
+    for name, mat in got.items():
+        want = small_set["fusion_" + name]
+        assert mat.dtype == np.float32 and mat.shape == want.shape
+        assert np.array_equal(mat.view(np.uint32), want.view(np.uint32)), name
+        same(O.ref_metrics_from_matrix(mat), golden["fusion_small_metrics"][name])
+    with pytest.raises(ValueError):
+        O.ref_fuse_clip_and_text2sparql(*a, fusion_strategy="nope")
+    assert sim is a[0] and np.array_equal(sim, small_set["sim"])   # inputs never mutated
+
+
+def test_ref_engine_list_fusion(golden):
+    for c in golden["engine"]["fuse_cases"]:
+        assert O.ref_fuse_clip_sparql_linear(c["clip"], c["sparql"], c["alpha"], c["beta"]) == c["out"]
+    ci = golden["engine"]["call_inputs"]
+    calls = golden["engine"]["calls"]
+    fused = O.ref_fuse_clip_sparql_linear(ci["clip"], ci["sparql"], 0.8, 0.2)
+    assert O.ref_threshold_filter(fused, 0) == calls["retrieve_text_default"]
+    fused = O.ref_fuse_clip_sparql_linear(ci["clip"], ci["sparql"], 0.6, 0.4)
+    assert O.ref_threshold_filter(fused, 0.3) == calls["retrieve_text_thr"]
+    assert O.ref_threshold_filter(ci["clip"], 0) == calls["noknowledge_default"]
+    assert O.ref_threshold_filter(ci["clip"], 0.25) == calls["noknowledge_thr"]
+
+
+def test_ref_and_canonical_mid(golden):
+    """Mid-size set regenerated from its seed: ref layer == golden; canonical layer == golden
+    (no near-tie flips a rank for this seed)."""
+    g = golden["metrics_mid"]
+    s = synth.make_retrieval_set(Q=1500, M=1500, D=128, seed=23, fused=True, lam=0.4, with_kg=True)
+    chk = [float(x.astype(np.float64).sum()) for x in (s.query, s.image, s.target)]
+    assert chk == g["checksum"], "synthetic generator drifted from the committed fixtures"
+    same(O.ref_all_retrieval_metrics(s.query, s.target, s.image), g["all"])
+    si = O.canon_dot64(s.query, s.image)
+    st = O.canon_dot64(s.query, s.target)
+    r, c, _ = O.kg_hits_to_pairs(s.kg_results, s.query_uuids, s.uuids)
+    for wi, wt in ((0.5, 0.5), (0.1, 0.9)):
+        same(O.ref_retrieval_metrics_final(s.query, s.target, s.image, t2i_weight=wi, t2t_weight=wt),
+             g[f"final_{wi}_{wt}"])
+        clip = O.canon_fused64(si, st, wi, wt)
+        same(O.metrics_from_ranks(O.canon_rank(clip, s.target_idx)), g[f"final_{wi}_{wt}"])
+        for alpha in (0.9, 0.5, 0.1):
+            bonus = O.canon_bonus_matrix(s.Q, s.M, r, c, 1 - alpha, dedupe=True)
+            fused = O.canon_fused64(si, st, wi, wt, alpha=alpha, bonus=bonus)
+            same(O.metrics_from_ranks(O.canon_rank(fused, s.target_idx)),
+                 g[f"sweep_{wi}_{wt}_alpha{alpha}"])
+
+
+def test_canonical_order_is_what_it_says():
+    rng = np.random.default_rng(0)
+    q = synth.round_to_bf16(rng.standard_normal((3, 80), dtype=np.float32))
+    g = synth.round_to_bf16(rng.standard_normal((5, 80), dtype=np.float32))
+    got = O.canon_dot64(q, g)
+    for i in range(3):
+        for j in range(5):
+            part = [0.0] * 32
+            for d in range(80):
+                part[d % 32] += float(q[i, d]) * float(g[j, d])
+            n = 32
+            while n > 1:
+                n //= 2
+                part = [part[l] + part[l + n] for l in range(n)]
+            assert got[i, j] == part[0]
+    assert np.allclose(got, q.astype(np.float64) @ g.astype(np.float64).T, rtol=0, atol=1e-12)
+
+
+def test_canon_topk_and_rank_ties_nan():
+    s = np.array([[0.5, 0.9, 0.9, np.nan, 0.1], [np.nan, 0.2, 0.2, 0.2, np.nan]])
+    idx, val = O.canon_topk(s, 3)
+    assert idx.tolist() == [[1, 2, 0], [1, 2, 3]]
+    assert O.canon_rank(s, np.array([2, 4])).tolist() == [2, 5]
+    assert O.canon_rank(s, np.array([3, 0])).tolist() == [5, 4]
+
+
+def test_canonical_vs_reference_confined_to_near_ties(golden):
+    """Where the fp32 reference and the binary64 contract disagree, it is only on rows the
+    near-tie audit flags (the reference's own result there depends on its BLAS build)."""
+    g = golden["metrics_mid_nearties"]["final_0.5_0.5"]
+    s = synth.make_retrieval_set(Q=1500, M=1500, D=128, seed=21, fused=True, lam=0.25)
+    clip = O.canon_fused64(O.canon_dot64(s.query, s.image), O.canon_dot64(s.query, s.target), 0.5, 0.5)
+    _, risky_rows = O.near_tie_audit(clip, s.target_idx, 20)
+    got = O.metrics_from_ranks(O.canon_rank(clip, s.target_idx))
+    assert 0 < risky_rows <= 32
+    assert abs(float(got["Mean_Rank"]) - g["Mean_Rank"]) * s.Q <= risky_rows + 1e-6
+    for k in (1, 5, 10, 20):
+        assert abs(float(got[f"R@{k}"]) - g[f"R@{k}"]) * s.Q / 100.0 <= risky_rows + 1e-6
