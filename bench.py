@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the retrieval-scoring hot path (BASELINE.json metric: queries/sec, top-k=10).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c1|big]
+
+One "step" = one pass of the hot path over one batch of synthetic queries: similarity scan of
+both galleries + weighted T2I/T2T fusion + top-k selection + canonical re-scoring.  Default
+workload = BASELINE.json configs[1] ("c2": 1000 queries x 43 000 gallery x 768-d, fused
+T2I+T2T, top-10).  With N > 1 (torchrun) every rank holds a replica of the 43k gallery (it is
+132 MB) and scans its own 1000-query shard of the global batch; results are all-gathered
+(NCCL) so every rank ends with the whole batch's top-k -- weak scaling over queries.
+
+Keys of the JSON line follow the driver's contract; see DESIGN.md §Measurement.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: Q, M, D, fused, k, kg
+    "c1": dict(Q=4300, M=43000, D=512, fused=False, k=10, seed=0),
+    "c2": dict(Q=1000, M=43000, D=768, fused=True, k=10, seed=1),
+    "c3": dict(Q=1, M=43000, D=768, fused=True, k=10, seed=1),
+    "b64": dict(Q=64, M=2_000_000, D=768, fused=False, k=10, seed=5, device_synth=True),
+    "b4096": dict(Q=4096, M=1_250_000, D=768, fused=False, k=100, seed=4, device_synth=True),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def reference_step(q, img, tgt, wi, wt, k):
+    """The reference's own CPU scoring path for this workload, restated in oracle/oracle.py:
+    fp32 BLAS similarity (metrics.py:102,145-148), weighted sum, full-row argsort (metrics.py:34)."""
+    from oracle import oracle as O
+    sim = O.ref_fused_similarity(q, tgt, img, wi, wt) if tgt is not None else O.ref_similarity(q, img)
+    order = np.argsort(-sim, axis=1)          # the reference sorts the entire row (metrics.py:34)
+    return order[:, :k]
+
+
+def cpu_sample(cfg, max_q):
+    from knowledge_enhanced_multimodal_retrieval_b200 import synth
+    Q = min(cfg["Q"], max_q)
+    M = min(cfg["M"], 43000)
+    s = synth.make_retrieval_set(Q=Q, M=M, D=cfg["D"], seed=cfg["seed"], fused=cfg["fused"], lam=0.1,
+                                 diagonal=False)
+    return s, Q, M
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    s, Q, M = cpu_sample(cfg, 1000)
+    scale = (cfg["M"] / M)                      # rows beyond the sample are extrapolated linearly
+    for _ in range(max(1, args.warmup if args.warmup < 2 else 1)):
+        reference_step(s.query, s.image, s.target, 0.5, 0.5, cfg["k"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        reference_step(s.query, s.image, s.target, 0.5, 0.5, cfg["k"])
+    dt = (time.perf_counter() - t0) * scale
+    qps = Q * args.steps / dt
+    cores = os.cpu_count()
+    sample = (f"{Q} queries x {M} gallery rows x {cfg['D']}-d per step, numpy sgemm + weighted sum + full-row "
+              f"argsort (reference path){'' if scale == 1 else f', time scaled x{scale:.1f} to the full gallery'}")
+    line = {"impl": "reference", "metric": "queries_per_sec_top%d" % cfg["k"], "value": qps, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, cfg, 1),
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
+                             "blas_threads": torch.get_num_threads()},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, cfg, world):
+    return {"workload": f"{args.workload}: {cfg['Q']} queries/GPU x {cfg['M']} gallery x {cfg['D']}-d, "
+                        f"{'fused T2I+T2T (0.5/0.5)' if cfg['fused'] else 'single gallery'}, top-{cfg['k']}",
+            "queries_per_step": cfg["Q"] * world, "gallery_rows": cfg["M"], "dim": cfg["D"],
+            "galleries": 2 if cfg["fused"] else 1, "k": cfg["k"],
+            "parallelism": "single GPU" if world == 1 else f"query-sharded x{world}, gallery replicated, "
+                                                           "NCCL all-gather of top-k",
+            "l2": "L2 flushed (512 MiB memset) before every timed step"}
+
+
+# ----------------------------------------------------------------------------- our arm (GPU)
+def run_ours(args, cfg):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from knowledge_enhanced_multimodal_retrieval_b200 import _lib, engine, index, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    lib = _lib.load()
+    pk = peaks()
+    Q, M, D, k = cfg["Q"], cfg["M"], cfg["D"], cfg["k"]
+    G = 2 if cfg["fused"] else 1
+    wi, wt = (0.5, 0.5) if cfg["fused"] else (1.0, 0.0)
+
+    # ---- data: same gallery on every rank, per-rank query shard
+    if cfg.get("device_synth"):
+        img = engine.synth_rows(M, D, cfg["seed"])
+        tgt = engine.synth_rows(M, D, cfg["seed"] + 1) if cfg["fused"] else None
+        qsrc = img[torch.randint(0, M, (Q,), generator=torch.Generator().manual_seed(7 + rank)).cuda()]
+        q_host = (qsrc.float() + 0.3 * torch.randn(Q, D, device="cuda", generator=torch.Generator("cuda").manual_seed(rank))
+                  / D ** 0.5)
+        q_host = torch.nn.functional.normalize(q_host, dim=1).cpu().numpy()
+        host_sets = None
+    else:
+        s = synth.make_retrieval_set(Q=Q, M=M, D=D, seed=cfg["seed"], fused=cfg["fused"], lam=0.1, diagonal=False)
+        if rank:
+            s.query = synth.make_queries((s.image, s.target) if cfg["fused"] else (s.image,),
+                                         s.target_idx, 0.1, cfg["seed"] + 100 + rank)
+        img, tgt = engine.quantize(s.image), (engine.quantize(s.target) if cfg["fused"] else None)
+        q_host = s.query
+        host_sets = s
+    q = engine.quantize(q_host)
+    k_sel = engine.default_k_sel(k)
+    ws = engine.workspace_for(Q, M, D, k_sel)
+    score = torch.empty((Q, k), dtype=torch.float64, device="cuda")
+    idx = torch.empty((Q, k), dtype=torch.int64, device="cuda")
+    flags = torch.empty((Q,), dtype=torch.int32, device="cuda")
+    packed = torch.empty((Q, 2 * k), dtype=torch.float64, device="cuda")
+    gathered = torch.empty((world * Q, 2 * k), dtype=torch.float64, device="cuda") if world > 1 else None
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def step():
+        engine.scan_topk_raw(q, img, tgt, wi, wt, 1.0, None, k, k_sel, engine.DEFAULT_EPS, 0, score, idx, flags, ws)
+        if world > 1:
+            packed[:, :k] = score
+            packed[:, k:] = idx.view(torch.float64)           # bit-cast, exact
+            dist.all_gather_into_tensor(gathered, packed)
+
+    ev_scan = torch.cuda.Event(enable_timing=True)
+    for _ in range(max(3, args.warmup)):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: K steps, device-timed, L2 flushed before each step
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for m_ in mids:
+        m_.record()                      # materialise the underlying cudaEvent_t
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        lib.kemr_set_scan_done_event(C.c_void_p(mids[i].cuda_event))
+        step()
+        ends[i].record()
+    lib.kemr_set_scan_done_event(None)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    step_ms = [s_.elapsed_time(e_) for s_, e_ in zip(starts, ends)]
+    scan_ms = [s_.elapsed_time(m_) for s_, m_ in zip(starts, mids)]
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    n_uncert = int((flags & 1).sum().item())
+
+    # ---- end to end through the C-ABI host-buffer call (gallery resident, queries/results on the host)
+    hi = index.HostIndex(synth.f32_to_bf16_bits(host_sets.image) if host_sets else img.view(torch.int16).cpu().numpy().view(np.uint16),
+                         None if not cfg["fused"] else (synth.f32_to_bf16_bits(host_sets.target) if host_sets
+                                                        else tgt.view(torch.int16).cpu().numpy().view(np.uint16)),
+                         max_queries=Q, max_k=k)
+    out = (np.empty((Q, k), np.int64), np.empty((Q, k), np.float64), np.empty((Q,), np.int32))
+    qh = np.ascontiguousarray(q_host, dtype=np.float32)
+    for _ in range(3):
+        hi.search(qh, k=k, t2i_weight=wi, t2t_weight=wt, out=out)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hi.search(qh, k=k, t2i_weight=wi, t2t_weight=wt, out=out)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert np.array_equal(out[0], idx.cpu().numpy()), "host-buffer path disagrees with the device path"
+    hi.close()
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        info = engine.device_info()
+        scan_t = statistics.mean(scan_ms) * 1e-3
+        flops = 2.0 * Q * G * M * D
+        bytes_ = float(G) * M * D * 2
+        ridge = pk["tensor_burst"] * 1e12 / (pk["hbm"] * 1e9)
+        if Q >= ridge:
+            roof = {"bound": "tensor", "achieved": flops / scan_t / 1e12, "peak": pk["tensor_burst"], "unit": "TFLOP/s"}
+        else:
+            roof = {"bound": "hbm", "achieved": bytes_ / scan_t / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["traffic"] = None
+        roof["peak_source"] = pk["source"]
+        roof["kernel"] = "scan (first kernel of kemr_scan_topk)"
+        roof["kernel_ms"] = scan_t * 1e3
+        roof["kernel_share_of_step"] = sum(scan_ms) / sum(step_ms)
+        qps = world * Q * args.steps / (total_ms * 1e-3)
+        line = {"metric": "queries_per_sec_top%d" % k, "value": qps, "unit": "queries/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload_config(args, cfg, world),
+                "e2e": {"value": world * Q * args.steps / e2e_s, "unit": "queries/s",
+                        "h2d_bytes_per_step": int(Q * D * 4), "d2h_bytes_per_step": int(Q * k * 16 + Q * 4),
+                        "api": "kemr_index_search_host (HostIndex.search): fp32 host queries in, top-k host arrays out; "
+                               "gallery resident in HBM", "ms_per_step": e2e_s / args.steps * 1e3},
+                "gpu_launches": 2 * args.steps, "roofline": roof, "clocks": clocks,
+                "uncertified_queries": n_uncert, "sm_count": info["sm_count"],
+                "scan_path": "tcgen05" if (info["has_tcgen05"] and Q >= 5) else "warp-dot"}
+        # CPU baseline beside it: bounded sample of the same workload on the host cores
+        if world == 1 and not args.no_cpu_baseline:
+            s2, Q2, M2 = cpu_sample(cfg, 1000)
+            reference_step(s2.query, s2.image, s2.target, 0.5, 0.5, k)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                reference_step(s2.query, s2.image, s2.target, 0.5, 0.5, k)
+            dt = (time.perf_counter() - t0) / reps * (M / M2)
+            line["cpu_baseline"] = {"value": Q2 / dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{Q2} queries x {M2} rows x {D}-d, numpy sgemm + weighted sum + full-row "
+                                              f"argsort, {reps} reps" + ("" if M2 == M else f", scaled x{M / M2:.1f}")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,182 @@
+/*
+ * kemr.h -- C ABI of the B200-native retrieval-scoring engine (libkemr.so).
+ *
+ * The reference (REEVALUATE/knowledge_enhanced_multimodal_retrieval) is pure Python and has no
+ * FFI of its own; its boundary for this path is a set of Python callables.
+ * Every entry point below names the reference call site(s) whose arithmetic it replaces
+ * (paths relative to the reference root).  The Python host layer in
+ * knowledge_enhanced_multimodal_retrieval_b200/{metrics,fusion,retrieval}.py mirrors those callables
+ * 1-for-1 and reaches this library through ctypes (see INTEGRATION.md for the stub a
+ * maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - unless a parameter says "host", pointers are DEVICE pointers on the current device;
+ *   - embeddings are bf16 bit patterns (uint16_t), row-major [rows, D], D % 8 == 0, D <= 1024,
+ *     rows 16-byte aligned;
+ *   - calls are enqueued on `stream` and do not synchronise (except the *_host calls);
+ *   - every call returns KEMR_OK or an error code; kemr_last_error() describes the last failure
+ *     of the calling thread;
+ *   - gallery row indices inside one call are LOCAL to the shard passed in (0..M-1); `idx_base`
+ *     is added when results are written, so shards of a row-partitioned gallery emit global ids.
+ *
+ * Scoring contract (the "canonical" score, identical to oracle/oracle.py canon_*):
+ *     S_a(q,j)  = sum_d q[d]*gal_a[j][d]   accumulated in binary64 in the fixed 32-lane order
+ *     clip(q,j) = fl(fl(w_a*S_a) + fl(w_b*S_b))          (gal_b == NULL: clip = fl(w_a*S_a))
+ *     final(q,j)= fl(fl(alpha*clip) + bonus(q,j))        (bonus from the KG-hit CSR, else +0)
+ *   ordering: final descending, ties by lowest gallery index.
+ * The fast scan kernels compute clip in fp32 to SELECT candidates; every returned index/score and
+ * every rank is then decided on canonical binary64 scores, and each query carries a certificate
+ * bit saying the selection margin was provably wide enough (given |fp32 - canonical| <= eps).
+ */
+#ifndef KEMR_H_
+#define KEMR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KEMR_ABI_VERSION 1
+
+enum {
+  KEMR_OK = 0,
+  KEMR_ERR_ARG = 1,          /* bad argument (shape, alignment, NULL) */
+  KEMR_ERR_CUDA = 2,         /* CUDA runtime / driver error */
+  KEMR_ERR_WORKSPACE = 3,    /* workspace too small */
+  KEMR_ERR_UNSUPPORTED = 4   /* not available on this device / build */
+};
+
+/* scan kernel selection */
+enum {
+  KEMR_PATH_AUTO = 0,
+  KEMR_PATH_WARP = 1,        /* coalesced, vectorised HBM-streaming warp-dot kernel (small batches) */
+  KEMR_PATH_MMA = 2          /* TMA-fed tcgen05/TMEM tensor-core kernel (sm_100a) */
+};
+
+/* per-query flag bits written by kemr_scan_topk / kemr_rank_count */
+#define KEMR_FLAG_UNCERTIFIED 1   /* selection margin not provably sufficient: retry with larger k_sel/eps */
+#define KEMR_FLAG_OVERFLOW 2      /* ambiguous-candidate list overflowed the workspace: retry with a larger one */
+
+typedef void* kemr_stream_t;      /* cudaStream_t */
+
+const char* kemr_last_error(void);
+int kemr_abi_version(void);
+/* sm count, compute capability, and whether the tcgen05 path can run here */
+int kemr_device_info(int* sm_count, int* cc_major, int* cc_minor, int* has_tcgen05);
+
+/* measurement hook: record `cuda_event` (a cudaEvent_t, or NULL to disable) right after the scan
+ * kernel inside the following kemr_scan_topk / kemr_rank_count calls of this thread. */
+int kemr_set_scan_done_event(void* cuda_event);
+
+/* ---- embedding boundary: fp32 rows -> optional x/||x|| -> bf16 (round-to-nearest-even).
+ * Replaces: evaluator.py:120-135 (normalise) + the implicit fp32 storage of the reference. */
+int kemr_quantize_rows(const float* src, uint16_t* dst, int64_t rows, int D, int normalize,
+                       kemr_stream_t stream);
+
+/* ---- deterministic synthetic gallery, generated on the device (counter-based, keyed by
+ * seed and GLOBAL row index row_base+r so any shard can be regenerated anywhere). */
+int kemr_synth_rows(uint16_t* dst, int64_t rows, int D, uint64_t seed, int64_t row_base,
+                    kemr_stream_t stream);
+
+/* ---- workspace sizing for kemr_scan_topk / kemr_rank_count / kemr_score_matrix */
+size_t kemr_workspace_bytes(int Q, int64_t M, int D, int k_sel, int64_t max_hits_per_query);
+
+/* ---- similarity scan + weighted fusion + KG boost + top-k, score matrix never written.
+ * Replaces: metrics.py:102,145-148 (sgemm + weighted sum), fusion.py:83 (alpha*S + w*I),
+ *           metrics.py:34 (argsort, of which only the first k columns are used),
+ *           and the remote CLIPRetriever.search scan (clip_retrieval.py:39-40).
+ *   hit_rowptr/hit_col/hit_bonus: optional CSR of KG hits per query (unique local columns per
+ *   query, bonus already aggregated); NULL = no boost.  alpha must be > 0.
+ *   k_sel >= k: candidates kept by the fp32 scan (k + margin), <= 128.
+ *   out_idx[q][i] = idx_base + local row, -1 past the end of a short gallery. */
+int kemr_scan_topk(const uint16_t* q, int Q,
+                   const uint16_t* gal_a, const uint16_t* gal_b, int64_t M, int D,
+                   double w_a, double w_b, double alpha,
+                   const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
+                   int64_t max_hits_per_query,
+                   int k, int k_sel, double eps, int64_t idx_base,
+                   double* out_score64, float* out_score32, int64_t* out_idx, int32_t* out_flags,
+                   void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream);
+
+/* ---- canonical final score of arbitrary (query, local row) pairs (target scores, spot checks).
+ *   pair_bonus may be NULL. */
+int kemr_score_pairs(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
+                     double w_a, double w_b, double alpha,
+                     const int32_t* pair_q, const int64_t* pair_row, const double* pair_bonus,
+                     int64_t n_pairs, double* out_score64, kemr_stream_t stream);
+
+/* ---- number of rows of this shard ranked strictly ahead of each query's target:
+ *   count[q] = #{ j : final(q,j) > t[q]  or  (final(q,j) == t[q] and idx_base+j < t_gidx[q]) }
+ * so that rank = 1 + sum over shards.  Replaces the two full-row argsorts of
+ * metrics.py:34,62 + :41,68 (position of the target) without materialising or sorting anything.
+ *   t_score64 / t_gidx: canonical final score and GLOBAL index of each query's target. */
+int kemr_rank_count(const uint16_t* q, int Q,
+                    const uint16_t* gal_a, const uint16_t* gal_b, int64_t M, int D,
+                    double w_a, double w_b, double alpha,
+                    const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
+                    const double* t_score64, const int64_t* t_gidx, double eps, int64_t idx_base,
+                    int64_t* out_count, int32_t* out_flags,
+                    void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream);
+
+/* ---- dense fp32 fused similarity matrix out[q*ld + j] = fl32(w_a*S_a + w_b*S_b) as the scan
+ * kernels compute it (compatibility with callers that want the matrix: metrics.py:102,145-148). */
+int kemr_score_matrix(const uint16_t* q, int Q,
+                      const uint16_t* gal_a, const uint16_t* gal_b, int64_t M, int D,
+                      float w_a, float w_b, float* out, int64_t ld,
+                      void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream);
+
+/* ---- matrix-taking compatibility entry points (metrics.py:13-44, :47-76, :165-185;
+ * fusion.py:6-20): stable-descending rank of column target_col[q] in row q, NaN last. */
+int kemr_matrix_rank(const float* S, int Q, int64_t M, int64_t ld, const int64_t* target_col,
+                     int64_t* out_rank, kemr_stream_t stream);
+/* top-k columns per row by (value desc, column asc); k <= 128 */
+int kemr_matrix_topk(const float* S, int Q, int64_t M, int64_t ld, int k,
+                     int64_t* out_idx, float* out_val, kemr_stream_t stream);
+
+/* ---- dense KG fusion in fp32, bit-identical to numpy (fusion.py:83, :119-130, :180-204):
+ *   out = scale_first ? fl32(fl32(alpha32*S) + 0) : S ;  then for every CSR entry of row q, in
+ *   order:  out[q][hit_col] = fl32(out[q][hit_col] + hit_add).   out may not alias S. */
+int kemr_matrix_fuse(const float* S, float* out, int Q, int64_t M, int64_t ld,
+                     int scale_first, float alpha32,
+                     const int64_t* hit_rowptr, const int32_t* hit_col, const float* hit_add,
+                     kemr_stream_t stream);
+
+/* ---- fused Recall@K / MRR / Mean-Rank reduction over 1-based ranks (metrics.py:41-42,70-71).
+ *   out_hits[i] = #{rank <= k_values[i]};  out_stats[0] = sum(rank) (exact integer as double),
+ *   out_stats[1] = sum(1/rank) in numpy's pairwise order, so that
+ *   MRR = out_stats[1]/Q*100 is bit-identical to np.mean(1.0/pos)*100. */
+int kemr_metrics_reduce(const int64_t* ranks, int Q, const int32_t* k_values, int n_k,
+                        int64_t* out_hits, double* out_stats, kemr_stream_t stream);
+/* host twin of the reduction above (no GPU needed; used to pin the summation order on CPU) */
+int kemr_metrics_reduce_host(const int64_t* ranks_host, int Q, const int32_t* k_values_host, int n_k,
+                             int64_t* out_hits_host, double* out_stats_host);
+
+/* ---- merge of R per-shard top-k lists after the all-gather:
+ *   in_score64/in_idx: [R][Q][k]; output top-k by (score desc, idx asc); idx < 0 = empty slot. */
+int kemr_merge_topk(const double* in_score64, const int64_t* in_idx, int R, int Q, int k,
+                    double* out_score64, int64_t* out_idx, kemr_stream_t stream);
+
+/* ---- resident gallery handle with HOST-buffer search: the serving-side drop-in for
+ * CLIPRetriever.search (clip_retrieval.py:39-40 -> retrieval.py:80,98).  The handle owns its
+ * device copies of the galleries, a workspace, pinned staging buffers and a stream.
+ *   gal_*_host: bf16 bit patterns [M, D] in host memory (gal_b_host may be NULL). */
+typedef struct kemr_index kemr_index_t;
+int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal_b_host, int64_t M, int D,
+                      int max_queries, int max_k, kemr_index_t** out);
+int kemr_index_destroy(kemr_index_t* index);
+/* queries: fp32 [Q, D] host (quantised to bf16 on the device; set normalize=1 to L2-normalise).
+ * Copies in, scans, copies the k results out and synchronises.  hits_* host CSR or NULL. */
+int kemr_index_search_host(kemr_index_t* index, const float* q_host, int Q, int normalize,
+                           double w_a, double w_b, double alpha,
+                           const int64_t* hit_rowptr_host, const int32_t* hit_col_host,
+                           const double* hit_bonus_host,
+                           int k, int64_t* out_idx_host, double* out_score64_host,
+                           int32_t* out_flags_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KEMR_H_ */

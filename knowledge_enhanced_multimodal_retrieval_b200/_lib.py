@@ -1,0 +1,87 @@
+"""ctypes binding of libkemr.so (include/kemr.h).  There is no fallback: if the CUDA library
+is missing or a call fails, an exception is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkemr.so")
+
+KEMR_OK = 0
+PATH_AUTO, PATH_WARP, PATH_MMA = 0, 1, 2
+FLAG_UNCERTIFIED, FLAG_OVERFLOW = 1, 2
+ABI_VERSION = 1
+
+EXPORTS = (
+    "kemr_last_error", "kemr_abi_version", "kemr_device_info", "kemr_quantize_rows", "kemr_synth_rows",
+    "kemr_workspace_bytes", "kemr_scan_topk", "kemr_score_pairs", "kemr_rank_count", "kemr_score_matrix",
+    "kemr_matrix_rank", "kemr_matrix_topk", "kemr_matrix_fuse", "kemr_metrics_reduce",
+    "kemr_metrics_reduce_host", "kemr_merge_topk", "kemr_index_create", "kemr_index_destroy",
+    "kemr_index_search_host", "kemr_set_scan_done_event",
+)
+
+
+class KemrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def _declare(lib):
+    p, i32, i64, u64, f32, f64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_double, C.c_size_t
+    lib.kemr_last_error.restype = C.c_char_p
+    lib.kemr_last_error.argtypes = []
+    lib.kemr_abi_version.restype = i32
+    lib.kemr_abi_version.argtypes = []
+    lib.kemr_device_info.argtypes = [C.POINTER(i32)] * 4
+    lib.kemr_quantize_rows.argtypes = [p, p, i64, i32, i32, p]
+    lib.kemr_synth_rows.argtypes = [p, i64, i32, u64, i64, p]
+    lib.kemr_workspace_bytes.restype = sz
+    lib.kemr_workspace_bytes.argtypes = [i32, i64, i32, i32, i64]
+    lib.kemr_scan_topk.argtypes = [p, i32, p, p, i64, i32, f64, f64, f64, p, p, p, i64, i32, i32, f64, i64,
+                                   p, p, p, p, p, sz, i32, p]
+    lib.kemr_score_pairs.argtypes = [p, p, p, i32, f64, f64, f64, p, p, p, i64, p, p]
+    lib.kemr_rank_count.argtypes = [p, i32, p, p, i64, i32, f64, f64, f64, p, p, p, p, p, f64, i64,
+                                    p, p, p, sz, i32, p]
+    lib.kemr_score_matrix.argtypes = [p, i32, p, p, i64, i32, f32, f32, p, i64, p, sz, i32, p]
+    lib.kemr_matrix_rank.argtypes = [p, i32, i64, i64, p, p, p]
+    lib.kemr_matrix_topk.argtypes = [p, i32, i64, i64, i32, p, p, p]
+    lib.kemr_matrix_fuse.argtypes = [p, p, i32, i64, i64, i32, f32, p, p, p, p]
+    lib.kemr_metrics_reduce.argtypes = [p, i32, p, i32, p, p, p]
+    lib.kemr_metrics_reduce_host.argtypes = [p, i32, p, i32, p, p]
+    lib.kemr_merge_topk.argtypes = [p, p, i32, i32, i32, p, p, p]
+    lib.kemr_index_create.argtypes = [p, p, i64, i32, i32, i32, C.POINTER(p)]
+    lib.kemr_index_destroy.argtypes = [p]
+    lib.kemr_set_scan_done_event.argtypes = [p]
+    lib.kemr_index_search_host.argtypes = [p, p, i32, i32, f64, f64, f64, p, p, p, i32, p, p, p]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("kemr_last_error", "kemr_workspace_bytes", "kemr_abi_version"):
+            fn.restype = i32
+
+
+def load():
+    """Load libkemr.so (built in-tree by `__graft_entry__.build()` / csrc/Makefile)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KemrError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C knowledge_enhanced_multimodal_retrieval_b200/csrc`). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        missing = [n for n in EXPORTS if not hasattr(lib, n)]
+        if missing:
+            raise KemrError(f"libkemr.so lacks symbols declared in include/kemr.h: {missing}")
+        _declare(lib)
+        if lib.kemr_abi_version() != ABI_VERSION:
+            raise KemrError("libkemr.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != KEMR_OK:
+        msg = load().kemr_last_error().decode("utf-8", "replace")
+        raise KemrError(f"libkemr error {rc}: {msg}")

@@ -1,0 +1,121 @@
+// Shared device/host helpers for libkemr (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace kemr {
+
+constexpr int kWarp = 32;
+constexpr int kMaxKSel = 128;          // candidates kept per query by the fp32 scan
+constexpr int kMaxD = 1024;
+
+// ----------------------------------------------------------------------------- bf16 helpers
+__device__ __forceinline__ float bf16_lo(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+__device__ __forceinline__ float bf16_to_f32(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+
+__device__ __forceinline__ uint16_t f32_to_bf16_rne(float x) {
+  uint32_t u = __float_as_uint(x);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x0040u);   // quiet NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// streaming 16-byte load that does not pollute L1
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// ----------------------------------------------------------------------------- ordering keys
+// A candidate is a 64-bit key: high word = order-preserving image of the fp32 score, low word =
+// ~row, so that "larger key" == "higher score, then lower row index".  0 is the empty slot.
+__host__ __device__ __forceinline__ uint32_t order_f32(float f) {
+  uint32_t u;
+#ifdef __CUDA_ARCH__
+  u = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; u = c.u;
+#endif
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 1u;          // NaN: below -inf, above "empty"
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float unorder_f32(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  if (k == 1u) u = 0x7fc00000u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
+  return ((uint64_t)order_f32(score) << 32) | (uint64_t)(~row);
+}
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return ~(uint32_t)k; }
+__host__ __device__ __forceinline__ float key_score(uint64_t k) { return unorder_f32((uint32_t)(k >> 32)); }
+
+// ----------------------------------------------------------------------------- warp primitives
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Canonical binary64 dot product of two bf16 rows, computed by one full warp; every lane
+// returns the result.  Lane l accumulates d = l, l+32, ... in increasing d (products of two
+// bf16 are exact in binary64), then the 32 partials fold 16,8,4,2,1 -- exactly
+// oracle/oracle.py::canon_dot64.
+__device__ __forceinline__ double canon_dot_warp(const uint16_t* __restrict__ a,
+                                                 const uint16_t* __restrict__ b, int D, int lane) {
+  double acc = 0.0;
+  for (int d = lane; d < D; d += 32)
+    acc = fma((double)bf16_to_f32(a[d]), (double)bf16_to_f32(b[d]), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, o));
+  return __shfl_sync(0xffffffffu, acc, 0);
+}
+
+// final = fl(fl(alpha * fl(fl(w_a*S_a) + fl(w_b*S_b))) + bonus); no contraction allowed.
+__device__ __forceinline__ double canon_fuse(double sa, double sb, bool two, double wa, double wb,
+                                             double alpha, double bonus, bool has_bonus) {
+  double clip = __dmul_rn(wa, sa);
+  if (two) clip = __dadd_rn(clip, __dmul_rn(wb, sb));
+  double f = __dmul_rn(alpha, clip);
+  if (has_bonus) f = __dadd_rn(f, bonus);
+  return f;
+}
+
+// "a ranks ahead of b": higher score first, then lower index; NaN after everything.
+__device__ __forceinline__ bool ahead64(double sa, int64_t ia, double sb, int64_t ib) {
+  const bool na = isnan(sa), nb = isnan(sb);
+  if (na || nb) return (!na && nb) || (na && nb && ia < ib);
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+// Insert key x into a descending sorted list L[0..K) held in shared memory, cooperatively by one
+// warp.  Precondition: x > L[K-1] (caller checked the threshold).  K <= 128.
+__device__ __forceinline__ void warp_list_insert(uint64_t* L, int K, uint64_t x, int lane) {
+  uint64_t nv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = lane + 32 * i;
+    if (p < K) {
+      const uint64_t cur = L[p];
+      const uint64_t prev = p > 0 ? L[p - 1] : ~0ull;
+      nv[i] = cur > x ? cur : (prev > x ? x : prev);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = lane + 32 * i;
+    if (p < K) L[p] = nv[i];
+  }
+  __syncwarp();
+}
+
+}  // namespace kemr

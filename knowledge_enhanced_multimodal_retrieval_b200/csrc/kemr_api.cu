@@ -1,0 +1,548 @@
+// libkemr.so -- C ABI (include/kemr.h) over the sm_100a kernels.  Host logic only: argument
+// checks, workspace carving, kernel selection and launches.  Nothing here synchronises the
+// device except the kemr_index_*_host calls.
+#include "../../include/kemr.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "common.cuh"
+#include "scan_warp.cuh"
+#include "select.cuh"
+#include "matrix_ops.cuh"
+#include "scan_mma.cuh"
+
+using namespace kemr;
+
+// ----------------------------------------------------------------------------- errors
+static thread_local std::string g_last_error;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(KEMR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),   \
+                  __FILE__, __LINE__);                                                      \
+  } while (0)
+#define LAUNCH_CHECK(what)                                                                  \
+  do {                                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(KEMR_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" const char* kemr_last_error(void) { return g_last_error.c_str(); }
+
+// measurement hook: when set, the event is recorded right after the scan kernel of the next
+// kemr_scan_topk / kemr_rank_count calls of this thread (lets bench.py time the scan kernel alone)
+static thread_local cudaEvent_t g_scan_done_event = nullptr;
+extern "C" int kemr_set_scan_done_event(void* cuda_event) {
+  g_scan_done_event = reinterpret_cast<cudaEvent_t>(cuda_event);
+  return KEMR_OK;
+}
+extern "C" int kemr_abi_version(void) { return KEMR_ABI_VERSION; }
+
+struct DevInfo { int ok = 0, dev = -1, sms = 0, major = 0, minor = 0; };
+static int dev_info(DevInfo* out) {
+  static thread_local DevInfo cache;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (!cache.ok || cache.dev != dev) {
+    cache.dev = dev;
+    CUDA_TRY(cudaDeviceGetAttribute(&cache.sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&cache.major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&cache.minor, cudaDevAttrComputeCapabilityMinor, dev));
+    cache.ok = 1;
+  }
+  *out = cache;
+  return KEMR_OK;
+}
+
+extern "C" int kemr_device_info(int* sm_count, int* cc_major, int* cc_minor, int* has_tcgen05) {
+  DevInfo d;
+  int rc = dev_info(&d);
+  if (rc) return rc;
+  if (sm_count) *sm_count = d.sms;
+  if (cc_major) *cc_major = d.major;
+  if (cc_minor) *cc_minor = d.minor;
+  if (has_tcgen05) *has_tcgen05 = (d.major == 10 && mma_built()) ? 1 : 0;
+  return KEMR_OK;
+}
+
+static inline cudaStream_t S(kemr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ----------------------------------------------------------------------------- simple kernels
+extern "C" int kemr_quantize_rows(const float* src, uint16_t* dst, int64_t rows, int D, int normalize,
+                                  kemr_stream_t stream) {
+  if (!src || !dst || rows < 0 || D <= 0) return fail(KEMR_ERR_ARG, "quantize_rows: bad argument");
+  if (rows == 0) return KEMR_OK;
+  const int threads = 256;
+  const int64_t blocks = std::min<int64_t>((rows + 7) / 8, 148 * 16);
+  quantize_rows_kernel<<<(unsigned)blocks, threads, 0, S(stream)>>>(src, dst, rows, D, normalize);
+  LAUNCH_CHECK("quantize_rows_kernel");
+  return KEMR_OK;
+}
+
+extern "C" int kemr_synth_rows(uint16_t* dst, int64_t rows, int D, uint64_t seed, int64_t row_base,
+                               kemr_stream_t stream) {
+  if (!dst || rows < 0 || D <= 0) return fail(KEMR_ERR_ARG, "synth_rows: bad argument");
+  if (rows == 0) return KEMR_OK;
+  const int64_t blocks = std::min<int64_t>((rows + 7) / 8, 148 * 16);
+  synth_rows_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(dst, rows, D, seed, row_base);
+  LAUNCH_CHECK("synth_rows_kernel");
+  return KEMR_OK;
+}
+
+// ----------------------------------------------------------------------------- scan planning
+struct ScanPlan {
+  int path;        // KEMR_PATH_WARP / KEMR_PATH_MMA
+  int QB, CH;      // warp path
+  int P;           // parts (lists per query)
+  int groups;      // warp path: query groups (grid.y)
+  MmaPlan mma;     // mma path
+};
+
+static int check_common(const void* q, int Q, const void* ga, int64_t M, int D) {
+  if (!q || !ga) return fail(KEMR_ERR_ARG, "null embedding pointer");
+  if (Q <= 0 || M <= 0) return fail(KEMR_ERR_ARG, "Q and M must be positive (Q=%d, M=%lld)", Q, (long long)M);
+  if (M >= (1ll << 31)) return fail(KEMR_ERR_ARG, "a shard holds at most 2^31-1 rows");
+  if (D <= 0 || D % 8 != 0 || D > kMaxD) return fail(KEMR_ERR_ARG, "D must be a multiple of 8, <= %d (D=%d)", kMaxD, D);
+  if (((uintptr_t)q | (uintptr_t)ga) & 15) return fail(KEMR_ERR_ARG, "embedding pointers must be 16-byte aligned");
+  return KEMR_OK;
+}
+
+static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, const DevInfo& dv, ScanPlan* pl) {
+  pl->path = path;
+  if (path == KEMR_PATH_AUTO) {
+    // tensor-core kernel when there is a batch to amortise its prologue; warp-dot for the
+    // latency-bound tiny batches
+    pl->path = (dv.major == 10 && Q >= 5 && mma_supported(D, K)) ? KEMR_PATH_MMA : KEMR_PATH_WARP;
+  }
+  if (pl->path == KEMR_PATH_MMA) {
+    if (dv.major != 10) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path needs compute capability 10.x (have %d.%d)", dv.major, dv.minor);
+    if (!mma_supported(D, K)) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path: unsupported D=%d / k_sel=%d", D, K);
+    int rc = mma_make_plan(Q, M, D, G, K, mode, dv.sms, &pl->mma);
+    if (rc) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path: cannot plan this shape");
+    pl->P = pl->mma.parts;
+    return KEMR_OK;
+  }
+  pl->QB = Q == 1 ? 1 : 2;
+  pl->CH = (D + 255) / 256;
+  pl->groups = (Q + pl->QB - 1) / pl->QB;
+  int want = 2 * dv.sms;
+  int P = std::max(1, (want + pl->groups - 1) / pl->groups);
+  P = (int)std::min<int64_t>(P, std::max<int64_t>(1, (M + 15) / 16));
+  pl->P = P;
+  return KEMR_OK;
+}
+
+static size_t parts_bytes(int P, int Q, int K) { return align_up((size_t)P * Q * K * sizeof(uint64_t)); }
+
+extern "C" size_t kemr_workspace_bytes(int Q, int64_t M, int D, int k_sel, int64_t max_hits_per_query) {
+  (void)max_hits_per_query;
+  DevInfo dv;
+  int sms = 148;
+  if (dev_info(&dv) == KEMR_OK && dv.sms > 0) sms = dv.sms;
+  const int P = 2 * sms + 8;                    // upper bound of any plan's part count
+  const int K = std::max(1, std::min(k_sel, kMaxKSel));
+  const int Qp = (Q + 127) / 128 * 128;
+  size_t topk = parts_bytes(P, Qp, K);
+  size_t count = align_up((size_t)Q * 8) + align_up((size_t)Q * 8) + align_up((size_t)P * Qp * 4) + 256 +
+                 align_up(((size_t)1 << 20) * 8 + (size_t)Q * 256 * 8);
+  (void)M; (void)D;
+  return std::max(topk, count) + 4096;
+}
+
+template <int QB, int CH>
+static void launch_warp(const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  scan_warp_kernel<QB, CH><<<grid, kWarpScanThreads, smem, st>>>(a);
+}
+static int launch_warp_scan(const ScanArgs& a, const ScanPlan& pl, cudaStream_t st) {
+  dim3 grid(pl.P, pl.groups);
+  const size_t smem = a.mode == kModeTopk ? (size_t)kWarpScanWarps * pl.QB * a.K * 8 : 0;
+  if (pl.groups > 65535) return fail(KEMR_ERR_UNSUPPORTED, "warp path: too many query groups (%d)", pl.groups);
+#define KEMR_CASE(qb, ch) if (pl.QB == qb && pl.CH == ch) { launch_warp<qb, ch>(a, grid, smem, st); }
+  KEMR_CASE(1, 1) KEMR_CASE(1, 2) KEMR_CASE(1, 3) KEMR_CASE(1, 4)
+  KEMR_CASE(2, 1) KEMR_CASE(2, 2) KEMR_CASE(2, 3) KEMR_CASE(2, 4)
+#undef KEMR_CASE
+  LAUNCH_CHECK("scan_warp_kernel");
+  return KEMR_OK;
+}
+
+// ----------------------------------------------------------------------------- scan + top-k
+extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
+                              int64_t M, int D, double w_a, double w_b, double alpha,
+                              const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
+                              int64_t max_hits_per_query, int k, int k_sel, double eps, int64_t idx_base,
+                              double* out_score64, float* out_score32, int64_t* out_idx, int32_t* out_flags,
+                              void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream) {
+  int rc = check_common(q, Q, gal_a, M, D);
+  if (rc) return rc;
+  if (k <= 0 || k_sel < k || k_sel > kMaxKSel) return fail(KEMR_ERR_ARG, "need 0 < k <= k_sel <= %d (k=%d, k_sel=%d)", kMaxKSel, k, k_sel);
+  if (!(alpha > 0.0)) return fail(KEMR_ERR_ARG, "alpha must be > 0 for the sparse KG-boost path (alpha=%g)", alpha);
+  if (!out_score64 || !out_idx || !out_flags) return fail(KEMR_ERR_ARG, "null output pointer");
+  if (hit_rowptr && (!hit_col || !hit_bonus)) return fail(KEMR_ERR_ARG, "hit CSR needs col and bonus arrays");
+  if (!hit_rowptr) max_hits_per_query = 0;
+  if (max_hits_per_query < 0 || max_hits_per_query > 4096) return fail(KEMR_ERR_ARG, "max_hits_per_query must be in [0, 4096]");
+  DevInfo dv;
+  if ((rc = dev_info(&dv))) return rc;
+  const int G = gal_b ? 2 : 1;
+  ScanPlan pl;
+  if ((rc = make_plan(Q, M, D, G, k_sel, kModeTopk, path, dv, &pl))) return rc;
+  const int Qrows = pl.path == KEMR_PATH_MMA ? pl.mma.q_pad : Q;
+  const size_t need = parts_bytes(pl.P, Qrows, k_sel);
+  if (!workspace || workspace_bytes < need) return fail(KEMR_ERR_WORKSPACE, "scan_topk needs %zu workspace bytes, got %zu", need, workspace_bytes);
+  cudaStream_t st = S(stream);
+  uint64_t* part_keys = reinterpret_cast<uint64_t*>(workspace);
+
+  ScanArgs a{};
+  a.q = q; a.Q = Q; a.gal[0] = gal_a; a.gal[1] = gal_b; a.G = G; a.M = M; a.D = D;
+  a.w[0] = (float)w_a; a.w[1] = (float)w_b; a.mode = kModeTopk; a.K = k_sel; a.part_keys = part_keys;
+  if (pl.path == KEMR_PATH_MMA) {
+    CUDA_TRY(cudaMemsetAsync(part_keys, 0, need, st));
+    if ((rc = mma_launch(a, pl.mma, st))) return fail(KEMR_ERR_CUDA, "tcgen05 scan launch failed: %s", mma_last_error());
+  } else {
+    if ((rc = launch_warp_scan(a, pl, st))) return rc;
+  }
+  if (g_scan_done_event) CUDA_TRY(cudaEventRecord(g_scan_done_event, st));
+
+  SelectArgs s{};
+  s.part_keys = part_keys; s.P = pl.P; s.Q = Qrows; s.K = k_sel;
+  s.q = q; s.gal[0] = gal_a; s.gal[1] = gal_b; s.G = G; s.D = D; s.M = M;
+  s.w[0] = w_a; s.w[1] = w_b; s.alpha = alpha;
+  s.hit_rowptr = hit_rowptr; s.hit_col = hit_col; s.hit_bonus = hit_bonus;
+  s.k = k; s.eps = eps; s.idx_base = idx_base;
+  s.out_score64 = out_score64; s.out_score32 = out_score32; s.out_idx = out_idx; s.out_flags = out_flags;
+  s.max_cand = k_sel + (int)max_hits_per_query;
+  const size_t smem = select_smem_bytes(k_sel, s.max_cand);
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  select_rescore_kernel<<<Q, kSelectThreads, smem, st>>>(s);
+  LAUNCH_CHECK("select_rescore_kernel");
+  return KEMR_OK;
+}
+
+extern "C" int kemr_score_pairs(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
+                                double w_a, double w_b, double alpha, const int32_t* pair_q,
+                                const int64_t* pair_row, const double* pair_bonus, int64_t n_pairs,
+                                double* out_score64, kemr_stream_t stream) {
+  if (!q || !gal_a || !pair_q || !pair_row || !out_score64) return fail(KEMR_ERR_ARG, "score_pairs: null pointer");
+  if (D <= 0 || D > kMaxD) return fail(KEMR_ERR_ARG, "score_pairs: bad D");
+  if (n_pairs <= 0) return KEMR_OK;
+  const int64_t blocks = std::min<int64_t>((n_pairs + 7) / 8, 148 * 8);
+  score_pairs_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(q, gal_a, gal_b, D, w_a, w_b, alpha, pair_q,
+                                                              pair_row, pair_bonus, n_pairs, out_score64);
+  LAUNCH_CHECK("score_pairs_kernel");
+  return KEMR_OK;
+}
+
+// ----------------------------------------------------------------------------- rank counting
+extern "C" int kemr_rank_count(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
+                               int64_t M, int D, double w_a, double w_b, double alpha,
+                               const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
+                               const double* t_score64, const int64_t* t_gidx, double eps, int64_t idx_base,
+                               int64_t* out_count, int32_t* out_flags, void* workspace,
+                               size_t workspace_bytes, int path, kemr_stream_t stream) {
+  int rc = check_common(q, Q, gal_a, M, D);
+  if (rc) return rc;
+  if (!(alpha > 0.0)) return fail(KEMR_ERR_ARG, "alpha must be > 0 (alpha=%g)", alpha);
+  if (!t_score64 || !t_gidx || !out_count || !out_flags) return fail(KEMR_ERR_ARG, "rank_count: null pointer");
+  if (hit_rowptr && (!hit_col || !hit_bonus)) return fail(KEMR_ERR_ARG, "hit CSR needs col and bonus arrays");
+  DevInfo dv;
+  if ((rc = dev_info(&dv))) return rc;
+  const int G = gal_b ? 2 : 1;
+  ScanPlan pl;
+  if ((rc = make_plan(Q, M, D, G, 16, kModeCount, path, dv, &pl))) return rc;
+  const int Qrows = pl.path == KEMR_PATH_MMA ? pl.mma.q_pad : Q;
+
+  // carve: band_lo | band_hi | part_count | amb_counter | amb_q | amb_row
+  unsigned char* p = reinterpret_cast<unsigned char*>(workspace);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  const size_t o_lo = take((size_t)Qrows * 4), o_hi = take((size_t)Qrows * 4);
+  const size_t o_pc = take((size_t)pl.P * Qrows * 4), o_ctr = take(256);
+  if (!workspace || workspace_bytes < off + 2 * 4096) return fail(KEMR_ERR_WORKSPACE, "rank_count needs at least %zu workspace bytes, got %zu", off + 2 * 4096, workspace_bytes);
+  const size_t left = workspace_bytes - off;
+  const unsigned int amb_cap = (unsigned int)std::min<size_t>((left - 512) / 8, 0x7fffffffu);
+  const size_t o_aq = take((size_t)amb_cap * 4), o_ar = off;
+  float* band_lo = reinterpret_cast<float*>(p + o_lo);
+  float* band_hi = reinterpret_cast<float*>(p + o_hi);
+  int32_t* part_count = reinterpret_cast<int32_t*>(p + o_pc);
+  unsigned int* amb_counter = reinterpret_cast<unsigned int*>(p + o_ctr);
+  uint32_t* amb_q = reinterpret_cast<uint32_t*>(p + o_aq);
+  uint32_t* amb_row = reinterpret_cast<uint32_t*>(p + o_ar);
+  cudaStream_t st = S(stream);
+
+  CUDA_TRY(cudaMemsetAsync(amb_counter, 0, 256, st));
+  if (Qrows > Q) {   // padded query rows of the tensor path never count
+    CUDA_TRY(cudaMemsetAsync(band_lo, 0x7f, (size_t)Qrows * 4, st));   // ~3.4e38
+    CUDA_TRY(cudaMemsetAsync(band_hi, 0x7f, (size_t)Qrows * 4, st));
+  }
+  rank_band_kernel<<<(Q + 255) / 256, 256, 0, st>>>(t_score64, alpha, eps, Q, band_lo, band_hi);
+  LAUNCH_CHECK("rank_band_kernel");
+
+  ScanArgs a{};
+  a.q = q; a.Q = Q; a.gal[0] = gal_a; a.gal[1] = gal_b; a.G = G; a.M = M; a.D = D;
+  a.w[0] = (float)w_a; a.w[1] = (float)w_b; a.mode = kModeCount; a.K = 16;
+  a.band_lo = band_lo; a.band_hi = band_hi; a.part_count = part_count;
+  a.amb_q = amb_q; a.amb_row = amb_row; a.amb_counter = amb_counter; a.amb_cap = amb_cap;
+  if (pl.path == KEMR_PATH_MMA) {
+    CUDA_TRY(cudaMemsetAsync(part_count, 0, (size_t)pl.P * Qrows * 4, st));
+    if ((rc = mma_launch(a, pl.mma, st))) return fail(KEMR_ERR_CUDA, "tcgen05 scan launch failed: %s", mma_last_error());
+  } else {
+    if ((rc = launch_warp_scan(a, pl, st))) return rc;
+  }
+  if (g_scan_done_event) CUDA_TRY(cudaEventRecord(g_scan_done_event, st));
+
+  unsigned long long* count = reinterpret_cast<unsigned long long*>(out_count);
+  rank_sum_parts_kernel<<<(Q + 255) / 256, 256, 0, st>>>(part_count, pl.P, Qrows, amb_counter, amb_cap, count, out_flags);
+  LAUNCH_CHECK("rank_sum_parts_kernel");
+  RankFixArgs f{};
+  f.q = q; f.gal[0] = gal_a; f.gal[1] = gal_b; f.G = G; f.D = D; f.w[0] = w_a; f.w[1] = w_b; f.alpha = alpha;
+  f.t = t_score64; f.t_gidx = t_gidx; f.idx_base = idx_base; f.count = count;
+  rank_amb_kernel<<<dv.sms * 4, 256, 0, st>>>(f, amb_q, amb_row, amb_counter, amb_cap);
+  LAUNCH_CHECK("rank_amb_kernel");
+  if (hit_rowptr) {
+    rank_hits_kernel<<<std::min(Q, dv.sms * 8), 128, 0, st>>>(f, Q, M, hit_rowptr, hit_col, hit_bonus);
+    LAUNCH_CHECK("rank_hits_kernel");
+  }
+  return KEMR_OK;
+}
+
+// ----------------------------------------------------------------------------- dense score matrix
+extern "C" int kemr_score_matrix(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
+                                 int64_t M, int D, float w_a, float w_b, float* out, int64_t ld,
+                                 void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream) {
+  (void)workspace; (void)workspace_bytes;
+  int rc = check_common(q, Q, gal_a, M, D);
+  if (rc) return rc;
+  if (!out || ld < M) return fail(KEMR_ERR_ARG, "score_matrix: bad output");
+  DevInfo dv;
+  if ((rc = dev_info(&dv))) return rc;
+  const int G = gal_b ? 2 : 1;
+  ScanPlan pl;
+  if ((rc = make_plan(Q, M, D, G, 16, kModeDense, path, dv, &pl))) return rc;
+  ScanArgs a{};
+  a.q = q; a.Q = Q; a.gal[0] = gal_a; a.gal[1] = gal_b; a.G = G; a.M = M; a.D = D;
+  a.w[0] = w_a; a.w[1] = w_b; a.mode = kModeDense; a.K = 16; a.dense = out; a.ld = ld;
+  if (pl.path == KEMR_PATH_MMA) {
+    if ((rc = mma_launch(a, pl.mma, S(stream)))) return fail(KEMR_ERR_CUDA, "tcgen05 scan launch failed: %s", mma_last_error());
+    return KEMR_OK;
+  }
+  return launch_warp_scan(a, pl, S(stream));
+}
+
+// ----------------------------------------------------------------------------- matrix compat
+extern "C" int kemr_matrix_rank(const float* Smat, int Q, int64_t M, int64_t ld, const int64_t* target_col,
+                                int64_t* out_rank, kemr_stream_t stream) {
+  if (!Smat || !target_col || !out_rank || Q <= 0 || M <= 0 || ld < M) return fail(KEMR_ERR_ARG, "matrix_rank: bad argument");
+  matrix_rank_kernel<<<Q, 256, 0, S(stream)>>>(Smat, Q, M, ld, target_col, out_rank);
+  LAUNCH_CHECK("matrix_rank_kernel");
+  return KEMR_OK;
+}
+
+extern "C" int kemr_matrix_topk(const float* Smat, int Q, int64_t M, int64_t ld, int k, int64_t* out_idx,
+                                float* out_val, kemr_stream_t stream) {
+  if (!Smat || !out_idx || !out_val || Q <= 0 || M <= 0 || ld < M) return fail(KEMR_ERR_ARG, "matrix_topk: bad argument");
+  if (k <= 0 || k > kMaxKSel) return fail(KEMR_ERR_ARG, "matrix_topk: k must be in [1, %d]", kMaxKSel);
+  if (M >= (1ll << 32) - 1) return fail(KEMR_ERR_ARG, "matrix_topk: too many columns");
+  matrix_topk_kernel<<<Q, 256, (size_t)8 * k * 8, S(stream)>>>(Smat, Q, M, ld, k, out_idx, out_val);
+  LAUNCH_CHECK("matrix_topk_kernel");
+  return KEMR_OK;
+}
+
+extern "C" int kemr_matrix_fuse(const float* Smat, float* out, int Q, int64_t M, int64_t ld, int scale_first,
+                                float alpha32, const int64_t* hit_rowptr, const int32_t* hit_col,
+                                const float* hit_add, kemr_stream_t stream) {
+  if (!Smat || !out || Smat == out || Q <= 0 || M <= 0 || ld < M) return fail(KEMR_ERR_ARG, "matrix_fuse: bad argument");
+  const int64_t total = (int64_t)Q * M;
+  const int64_t blocks = std::min<int64_t>((total + 255) / 256, 148 * 16);
+  matrix_scale_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(Smat, out, Q, M, ld, scale_first, alpha32);
+  LAUNCH_CHECK("matrix_scale_kernel");
+  if (hit_rowptr) {
+    if (!hit_col || !hit_add) return fail(KEMR_ERR_ARG, "matrix_fuse: hit CSR needs col and add arrays");
+    matrix_hits_kernel<<<(Q + 127) / 128, 128, 0, S(stream)>>>(out, Q, M, ld, hit_rowptr, hit_col, hit_add);
+    LAUNCH_CHECK("matrix_hits_kernel");
+  }
+  return KEMR_OK;
+}
+
+// ----------------------------------------------------------------------------- metrics reduction
+struct MetricsScratch { double* sums = nullptr; int64_t* off = nullptr; int64_t* n = nullptr; int dev = -1; };
+static int metrics_scratch(MetricsScratch** out) {
+  static thread_local MetricsScratch sc;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (!sc.sums || sc.dev != dev) {
+    CUDA_TRY(cudaMalloc(&sc.sums, (size_t)kMaxLeaves * 8));
+    CUDA_TRY(cudaMalloc(&sc.off, (size_t)kMaxLeaves * 8));
+    CUDA_TRY(cudaMalloc(&sc.n, (size_t)kMaxLeaves * 8));
+    sc.dev = dev;
+  }
+  *out = &sc;
+  return KEMR_OK;
+}
+
+extern "C" int kemr_metrics_reduce(const int64_t* ranks, int Q, const int32_t* k_values, int n_k,
+                                   int64_t* out_hits, double* out_stats, kemr_stream_t stream) {
+  if (!ranks || Q <= 0 || n_k < 0 || n_k > 32 || !out_stats || (n_k && (!k_values || !out_hits)))
+    return fail(KEMR_ERR_ARG, "metrics_reduce: bad argument");
+  if ((int64_t)Q > (int64_t)kMaxLeaves * 64) return fail(KEMR_ERR_ARG, "metrics_reduce: Q too large");
+  MetricsScratch* sc;
+  int rc = metrics_scratch(&sc);
+  if (rc) return rc;
+  metrics_reduce_kernel<<<1, kMetricsThreads, 0, S(stream)>>>(ranks, Q, k_values, n_k, out_hits, out_stats,
+                                                              sc->sums, sc->off, sc->n);
+  LAUNCH_CHECK("metrics_reduce_kernel");
+  return KEMR_OK;
+}
+
+extern "C" int kemr_metrics_reduce_host(const int64_t* ranks, int Q, const int32_t* k_values, int n_k,
+                                        int64_t* out_hits, double* out_stats) {
+  if (!ranks || Q <= 0 || n_k < 0 || n_k > 32 || !out_stats || (n_k && (!k_values || !out_hits)))
+    return fail(KEMR_ERR_ARG, "metrics_reduce_host: bad argument");
+  unsigned long long sum = 0;
+  for (int j = 0; j < n_k; ++j) out_hits[j] = 0;
+  for (int i = 0; i < Q; ++i) {
+    sum += (unsigned long long)ranks[i];
+    for (int j = 0; j < n_k; ++j) out_hits[j] += ranks[i] <= k_values[j];
+  }
+  out_stats[0] = (double)sum;
+  out_stats[1] = 0.0 + pairwise_tree(Q, [&](int64_t off, int64_t n) { return pairwise_leaf(ranks, off, n); });
+  return KEMR_OK;
+}
+
+extern "C" int kemr_merge_topk(const double* in_score64, const int64_t* in_idx, int R, int Q, int k,
+                               double* out_score64, int64_t* out_idx, kemr_stream_t stream) {
+  if (!in_score64 || !in_idx || !out_score64 || !out_idx || R <= 0 || Q <= 0 || k <= 0)
+    return fail(KEMR_ERR_ARG, "merge_topk: bad argument");
+  const size_t smem = (size_t)R * k * 16;
+  if (smem > 200 * 1024) return fail(KEMR_ERR_ARG, "merge_topk: R*k too large (%d*%d)", R, k);
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_topk_kernel<<<Q, 256, smem, S(stream)>>>(in_score64, in_idx, R, Q, k, out_score64, out_idx);
+  LAUNCH_CHECK("merge_topk_kernel");
+  return KEMR_OK;
+}
+
+// ----------------------------------------------------------------------------- resident index, host-buffer search
+struct kemr_index {
+  uint16_t* gal[2] = {nullptr, nullptr};
+  int64_t M = 0;
+  int D = 0, max_q = 0, max_k = 0;
+  cudaStream_t stream = nullptr;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // device staging
+  float* d_qf32 = nullptr; uint16_t* d_q = nullptr;
+  double* d_score = nullptr; int64_t* d_idx = nullptr; int32_t* d_flags = nullptr;
+  int64_t* d_rowptr = nullptr; int32_t* d_col = nullptr; double* d_bonus = nullptr; int64_t hit_cap = 0;
+  // pinned staging
+  float* h_q = nullptr; double* h_score = nullptr; int64_t* h_idx = nullptr; int32_t* h_flags = nullptr;
+  int64_t* h_rowptr = nullptr; int32_t* h_col = nullptr; double* h_bonus = nullptr;
+};
+
+extern "C" int kemr_index_destroy(kemr_index_t* ix) {
+  if (!ix) return KEMR_OK;
+  if (ix->stream) cudaStreamSynchronize(ix->stream);
+  cudaFree(ix->gal[0]); cudaFree(ix->gal[1]); cudaFree(ix->ws);
+  cudaFree(ix->d_qf32); cudaFree(ix->d_q); cudaFree(ix->d_score); cudaFree(ix->d_idx); cudaFree(ix->d_flags);
+  cudaFree(ix->d_rowptr); cudaFree(ix->d_col); cudaFree(ix->d_bonus);
+  cudaFreeHost(ix->h_q); cudaFreeHost(ix->h_score); cudaFreeHost(ix->h_idx); cudaFreeHost(ix->h_flags);
+  cudaFreeHost(ix->h_rowptr); cudaFreeHost(ix->h_col); cudaFreeHost(ix->h_bonus);
+  if (ix->stream) cudaStreamDestroy(ix->stream);
+  delete ix;
+  return KEMR_OK;
+}
+
+extern "C" int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal_b_host, int64_t M, int D,
+                                 int max_queries, int max_k, kemr_index_t** out) {
+  if (!gal_a_host || !out || M <= 0 || D <= 0 || D % 8 || D > kMaxD || max_queries <= 0 || max_k <= 0 || max_k > kMaxKSel - 8)
+    return fail(KEMR_ERR_ARG, "index_create: bad argument");
+  kemr_index* ix = new kemr_index();
+  ix->M = M; ix->D = D; ix->max_q = max_queries; ix->max_k = max_k; ix->hit_cap = (int64_t)max_queries * 256;
+  const size_t gbytes = (size_t)M * D * 2;
+  const int ksel = std::min(kMaxKSel, max_k + std::max(8, max_k / 4));
+  ix->ws_bytes = kemr_workspace_bytes(max_queries, M, D, ksel, 256);
+#define IX_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { kemr_index_destroy(ix); \
+    return fail(KEMR_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } } while (0)
+  IX_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+  IX_TRY(cudaMalloc(&ix->gal[0], gbytes));
+  IX_TRY(cudaMemcpyAsync(ix->gal[0], gal_a_host, gbytes, cudaMemcpyHostToDevice, ix->stream));
+  if (gal_b_host) {
+    IX_TRY(cudaMalloc(&ix->gal[1], gbytes));
+    IX_TRY(cudaMemcpyAsync(ix->gal[1], gal_b_host, gbytes, cudaMemcpyHostToDevice, ix->stream));
+  }
+  IX_TRY(cudaMalloc(&ix->ws, ix->ws_bytes));
+  const size_t nq = (size_t)max_queries;
+  IX_TRY(cudaMalloc(&ix->d_qf32, nq * D * 4)); IX_TRY(cudaMalloc(&ix->d_q, nq * D * 2));
+  IX_TRY(cudaMalloc(&ix->d_score, nq * max_k * 8)); IX_TRY(cudaMalloc(&ix->d_idx, nq * max_k * 8));
+  IX_TRY(cudaMalloc(&ix->d_flags, nq * 4));
+  IX_TRY(cudaMalloc(&ix->d_rowptr, (nq + 1) * 8)); IX_TRY(cudaMalloc(&ix->d_col, (size_t)ix->hit_cap * 4));
+  IX_TRY(cudaMalloc(&ix->d_bonus, (size_t)ix->hit_cap * 8));
+  IX_TRY(cudaMallocHost(&ix->h_q, nq * D * 4)); IX_TRY(cudaMallocHost(&ix->h_score, nq * max_k * 8));
+  IX_TRY(cudaMallocHost(&ix->h_idx, nq * max_k * 8)); IX_TRY(cudaMallocHost(&ix->h_flags, nq * 4));
+  IX_TRY(cudaMallocHost(&ix->h_rowptr, (nq + 1) * 8)); IX_TRY(cudaMallocHost(&ix->h_col, (size_t)ix->hit_cap * 4));
+  IX_TRY(cudaMallocHost(&ix->h_bonus, (size_t)ix->hit_cap * 8));
+  IX_TRY(cudaStreamSynchronize(ix->stream));
+#undef IX_TRY
+  *out = ix;
+  return KEMR_OK;
+}
+
+extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int Q, int normalize,
+                                      double w_a, double w_b, double alpha, const int64_t* hit_rowptr_host,
+                                      const int32_t* hit_col_host, const double* hit_bonus_host, int k,
+                                      int64_t* out_idx_host, double* out_score64_host, int32_t* out_flags_host) {
+  if (!ix || !q_host || !out_idx_host || !out_score64_host) return fail(KEMR_ERR_ARG, "index_search_host: null pointer");
+  if (Q <= 0 || Q > ix->max_q || k <= 0 || k > ix->max_k) return fail(KEMR_ERR_ARG, "index_search_host: Q or k beyond the handle's limits");
+  cudaStream_t st = ix->stream;
+  const size_t qbytes = (size_t)Q * ix->D * 4;
+  memcpy(ix->h_q, q_host, qbytes);
+  CUDA_TRY(cudaMemcpyAsync(ix->d_qf32, ix->h_q, qbytes, cudaMemcpyHostToDevice, st));
+  int64_t max_hits = 0;
+  const int64_t* d_rowptr = nullptr;
+  if (hit_rowptr_host) {
+    const int64_t nnz = hit_rowptr_host[Q];
+    if (nnz > ix->hit_cap) return fail(KEMR_ERR_ARG, "index_search_host: too many KG hits (%lld > %lld)", (long long)nnz, (long long)ix->hit_cap);
+    for (int i = 0; i < Q; ++i) max_hits = std::max(max_hits, hit_rowptr_host[i + 1] - hit_rowptr_host[i]);
+    memcpy(ix->h_rowptr, hit_rowptr_host, (size_t)(Q + 1) * 8);
+    memcpy(ix->h_col, hit_col_host, (size_t)nnz * 4);
+    memcpy(ix->h_bonus, hit_bonus_host, (size_t)nnz * 8);
+    CUDA_TRY(cudaMemcpyAsync(ix->d_rowptr, ix->h_rowptr, (size_t)(Q + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nnz) {
+      CUDA_TRY(cudaMemcpyAsync(ix->d_col, ix->h_col, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(ix->d_bonus, ix->h_bonus, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+    }
+    d_rowptr = ix->d_rowptr;
+  }
+  int rc = kemr_quantize_rows(ix->d_qf32, ix->d_q, Q, ix->D, normalize, st);
+  if (rc) return rc;
+  const int ksel = std::min(kMaxKSel, k + std::max(8, k / 4));
+  rc = kemr_scan_topk(ix->d_q, Q, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, alpha, d_rowptr, ix->d_col,
+                      ix->d_bonus, max_hits, k, ksel, 2e-5, 0, ix->d_score, nullptr, ix->d_idx, ix->d_flags,
+                      ix->ws, ix->ws_bytes, KEMR_PATH_AUTO, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ix->h_idx, ix->d_idx, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(ix->h_score, ix->d_score, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(ix->h_flags, ix->d_flags, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(out_idx_host, ix->h_idx, (size_t)Q * k * 8);
+  memcpy(out_score64_host, ix->h_score, (size_t)Q * k * 8);
+  if (out_flags_host) memcpy(out_flags_host, ix->h_flags, (size_t)Q * 4);
+  return KEMR_OK;
+}

@@ -1,0 +1,240 @@
+// Matrix-taking compatibility kernels, the embedding boundary, the synthetic generator and the
+// fused Recall@K / MRR / Mean-Rank reduction.  All HBM-bound streaming kernels.
+#pragma once
+#include "common.cuh"
+
+namespace kemr {
+
+// ------------------------------------------------------------------ fp32 rows -> bf16
+// Replaces the normalise step of evaluator.py:120-135 plus the quantisation into the store.
+__global__ void quantize_rows_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst,
+                                     int64_t rows, int D, int normalize) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = wid; r < rows; r += nw) {
+    const float* s = src + (size_t)r * D;
+    float scale = 1.f;
+    if (normalize) {
+      float ss = 0.f;
+      for (int d = lane; d < D; d += 32) { const float v = s[d]; ss = fmaf(v, v, ss); }
+      ss = warp_sum(ss);
+      scale = 1.f / sqrtf(ss);
+    }
+    uint16_t* o = dst + (size_t)r * D;
+    for (int d = lane; d < D; d += 32) {
+      const float v = normalize ? s[d] * scale : s[d];
+      o[d] = f32_to_bf16_rne(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ synthetic gallery rows
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {          // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+__device__ __forceinline__ float synth_normal(uint64_t seed, int64_t grow, int d) {
+  const uint64_t h = mix64(mix64(seed ^ 0x9e3779b97f4a7c15ull) + (uint64_t)grow * 0x100000001b3ull + (uint64_t)d);
+  const float u1 = ((float)(uint32_t)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
+  const float u2 = ((float)(uint32_t)((h >> 16) & 0xffffff) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+__global__ void synth_rows_kernel(uint16_t* __restrict__ dst, int64_t rows, int D, uint64_t seed,
+                                  int64_t row_base) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = wid; r < rows; r += nw) {
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float v = synth_normal(seed, row_base + r, d); ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float scale = 1.f / sqrtf(ss);
+    uint16_t* o = dst + (size_t)r * D;
+    for (int d = lane; d < D; d += 32) o[d] = f32_to_bf16_rne(synth_normal(seed, row_base + r, d) * scale);
+  }
+}
+
+// ------------------------------------------------------------------ rank of a column in a given matrix
+// metrics.py:34,62,68 on a caller-supplied matrix: stable descending order, NaN last.
+__global__ void __launch_bounds__(256) matrix_rank_kernel(const float* __restrict__ S, int Q, int64_t M,
+                                                         int64_t ld, const int64_t* __restrict__ tcol,
+                                                         int64_t* __restrict__ out_rank) {
+  const int qi = blockIdx.x;
+  const float* row = S + (size_t)qi * ld;
+  const int64_t tc = tcol[qi];
+  const float t = row[tc];
+  const bool tnan = isnan(t);
+  unsigned long long cnt = 0;
+  for (int64_t j = threadIdx.x; j < M; j += blockDim.x) {
+    const float v = row[j];
+    const bool vnan = isnan(v);
+    bool ahead;
+    if (tnan) ahead = !vnan || (j < tc);
+    else ahead = (v > t) || (v == t && j < tc);
+    cnt += ahead ? 1ull : 0ull;
+  }
+  __shared__ unsigned long long s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) out_rank[qi] = (int64_t)s_cnt + 1;
+}
+
+// top-k columns of each row of a given matrix by (value desc, column asc)
+__global__ void __launch_bounds__(256) matrix_topk_kernel(const float* __restrict__ S, int Q, int64_t M,
+                                                         int64_t ld, int k, int64_t* __restrict__ out_idx,
+                                                         float* __restrict__ out_val) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw);        // [8][k]
+  const int qi = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* row = S + (size_t)qi * ld;
+  uint64_t* mine = lists + (size_t)warp * k;
+  for (int i = lane; i < k; i += 32) mine[i] = 0;
+  __syncwarp();
+  uint64_t thr = 0;
+  for (int64_t j0 = (int64_t)warp * 32; j0 < M; j0 += 8 * 32) {
+    const int64_t j = j0 + lane;
+    uint64_t key = 0;
+    if (j < M) key = make_key(row[j], (uint32_t)j);
+    unsigned m = __ballot_sync(0xffffffffu, key > thr);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint64_t x = __shfl_sync(0xffffffffu, key, src);
+      if (x > thr) { warp_list_insert(mine, k, x, lane); thr = mine[k - 1]; }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    thr = mine[k - 1];
+    for (int w2 = 1; w2 < 8; ++w2) {
+      const uint64_t* other = lists + (size_t)w2 * k;
+      for (int i = 0; i < k; ++i) {
+        const uint64_t x = other[i];
+        if (x <= thr) break;
+        warp_list_insert(mine, k, x, lane);
+        thr = mine[k - 1];
+      }
+    }
+    for (int i = lane; i < k; i += 32) {
+      const uint64_t x = mine[i];
+      out_idx[(size_t)qi * k + i] = x ? (int64_t)key_row(x) : -1;
+      out_val[(size_t)qi * k + i] = x ? row[key_row(x)] : -INFINITY;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dense KG fusion (bit-identical to numpy fp32)
+__global__ void matrix_scale_kernel(const float* __restrict__ S, float* __restrict__ out, int Q, int64_t M,
+                                    int64_t ld, int scale_first, float alpha32) {
+  const int64_t total = (int64_t)Q * M;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / M, c = i - r * M;
+    const float v = S[(size_t)r * ld + c];
+    // fusion.py:83  alpha*S + w*I  ->  non-hit entries see "+ 0.0"
+    out[(size_t)r * ld + c] = scale_first ? __fadd_rn(__fmul_rn(alpha32, v), 0.0f) : v;
+  }
+}
+// one thread per query row applies that row's hits in list order (duplicates add again,
+// fusion.py:130), each add rounded to fp32 like numpy's in-place `+=` on a float32 array
+__global__ void matrix_hits_kernel(float* __restrict__ out, int Q, int64_t M, int64_t ld,
+                                   const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                   const float* __restrict__ add) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= Q) return;
+  for (int64_t h = rowptr[qi]; h < rowptr[qi + 1]; ++h) {
+    const int64_t c = col[h];
+    if (c < 0 || c >= M) continue;
+    float* p = out + (size_t)qi * ld + c;
+    *p = __fadd_rn(*p, add[h]);
+  }
+}
+
+// ------------------------------------------------------------------ metrics reduction
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, *_pairwise_sum) over
+// a[i] = 1.0 / rank[i]; reproduced so that MRR is bit-identical to np.mean(1.0/pos)*100.
+__host__ __device__ inline double recip_rank(const int64_t* r, int64_t i) { return 1.0 / (double)r[i]; }
+
+__host__ __device__ inline double pairwise_leaf(const int64_t* r, int64_t off, int64_t n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int64_t i = 0; i < n; ++i) res += recip_rank(r, off + i);
+    return res;
+  }
+  double acc[8];
+  for (int j = 0; j < 8; ++j) acc[j] = recip_rank(r, off + j);
+  int64_t i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) acc[j] += recip_rank(r, off + i + j);
+  double res = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  for (; i < n; ++i) res += recip_rank(r, off + i);
+  return res;
+}
+
+// explicit-stack traversal of numpy's split rule; leaf sums come from `leaf(off, n)`
+template <class LeafFn>
+__host__ __device__ inline double pairwise_tree(int64_t n_total, LeafFn leaf) {
+  // post-order evaluation with a small stack: state 0 = visit, 1 = left done, 2 = right done
+  struct Frame { int64_t off, n; double left; int state; };
+  Frame st[64];
+  int sp = 0;
+  st[0] = Frame{0, n_total, 0.0, 0};
+  double ret = 0.0;
+  while (sp >= 0) {
+    Frame& f = st[sp];
+    if (f.n <= 128) { ret = leaf(f.off, f.n); --sp; continue; }
+    int64_t n2 = f.n / 2; n2 -= n2 % 8;
+    if (f.state == 0) { f.state = 1; st[sp + 1] = Frame{f.off, n2, 0.0, 0}; ++sp; }
+    else if (f.state == 1) { f.left = ret; f.state = 2; st[sp + 1] = Frame{f.off + n2, f.n - n2, 0.0, 0}; ++sp; }
+    else { ret = f.left + ret; --sp; }
+  }
+  return ret;
+}
+
+constexpr int kMetricsThreads = 1024;
+constexpr int kMaxLeaves = 8192;          // leaves hold 65..128 ranks each -> Q up to ~500k
+
+__global__ void __launch_bounds__(kMetricsThreads) metrics_reduce_kernel(
+    const int64_t* __restrict__ ranks, int Q, const int32_t* __restrict__ kv, int nk,
+    int64_t* __restrict__ out_hits, double* __restrict__ out_stats, double* __restrict__ leaf_sums,
+    int64_t* __restrict__ leaf_off, int64_t* __restrict__ leaf_n) {
+  __shared__ unsigned long long s_hits[32];
+  __shared__ unsigned long long s_sum;
+  __shared__ int s_nleaf;
+  if (threadIdx.x < 32) s_hits[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    s_sum = 0;
+    // enumerate leaves in traversal order
+    int nl = 0;
+    pairwise_tree(Q, [&](int64_t off, int64_t n) { leaf_off[nl] = off; leaf_n[nl] = n; ++nl; return 0.0; });
+    s_nleaf = nl;
+  }
+  __syncthreads();
+  unsigned long long hits[32];
+  for (int i = 0; i < nk; ++i) hits[i] = 0;
+  unsigned long long sum = 0;
+  for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+    const int64_t r = ranks[i];
+    sum += (unsigned long long)r;
+    for (int j = 0; j < nk; ++j) hits[j] += (r <= kv[j]) ? 1ull : 0ull;
+  }
+  atomicAdd(&s_sum, sum);
+  for (int j = 0; j < nk; ++j) if (hits[j]) atomicAdd(&s_hits[j], hits[j]);
+  for (int l = threadIdx.x; l < s_nleaf; l += blockDim.x) leaf_sums[l] = pairwise_leaf(ranks, leaf_off[l], leaf_n[l]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int cursor = 0;
+    const double rr = 0.0 + pairwise_tree(Q, [&](int64_t, int64_t) { return leaf_sums[cursor++]; });
+    out_stats[0] = (double)s_sum;
+    out_stats[1] = rr;
+    for (int j = 0; j < nk; ++j) out_hits[j] = (int64_t)s_hits[j];
+  }
+}
+
+}  // namespace kemr

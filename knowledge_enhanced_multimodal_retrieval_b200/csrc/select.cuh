@@ -1,0 +1,303 @@
+// Candidate selection, canonical binary64 re-scoring and rank finalisation.
+//
+// The scan kernels (scan_warp.cuh, scan_mma.cuh) only SELECT: per query they leave P sorted
+// lists of K fp32-scored candidates.  The kernels here decide every returned index, score and
+// rank on canonical binary64 scores (common.cuh::canon_dot_warp), merge the sparse KG-hit side
+// path, and emit the per-query certificate.
+#pragma once
+#include "common.cuh"
+
+namespace kemr {
+
+struct SelectArgs {
+  const uint64_t* part_keys;   // [P][Q][K]
+  int P, Q, K;
+  const uint16_t* q;
+  const uint16_t* gal[2];
+  int G, D;
+  int64_t M;
+  double w[2];
+  double alpha;
+  const int64_t* hit_rowptr;   // [Q+1] or null
+  const int32_t* hit_col;
+  const double* hit_bonus;
+  int k;
+  double eps;
+  int64_t idx_base;
+  double* out_score64;         // [Q][k]
+  float* out_score32;          // [Q][k] or null
+  int64_t* out_idx;            // [Q][k]
+  int32_t* out_flags;          // [Q]
+  int max_cand;                // K + max hits per query
+};
+
+constexpr int kSelectThreads = 256;
+constexpr int kSelectWarps = kSelectThreads / 32;
+
+// dynamic smem: lists[kSelectWarps][K] u64 | cand_score[max_cand] f64 | cand_bonus[max_cand] f64 |
+//               cand_row[max_cand] i32 | cand_has[max_cand] u8
+inline size_t select_smem_bytes(int K, int max_cand) {
+  size_t b = (size_t)kSelectWarps * K * 8 + (size_t)max_cand * (8 + 8 + 4);
+  b += (size_t)max_cand;          // has-bonus flags
+  return (b + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = a.K;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw);
+  double* cand_score = reinterpret_cast<double*>(lists + (size_t)kSelectWarps * K);
+  double* cand_bonus = cand_score + a.max_cand;
+  int32_t* cand_row = reinterpret_cast<int32_t*>(cand_bonus + a.max_cand);
+  unsigned char* cand_has = reinterpret_cast<unsigned char*>(cand_row + a.max_cand);
+  __shared__ int s_nsel, s_extra;
+
+  const int qi = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // ---- A. per-warp selection over the parts, then fold into warp 0's list
+  uint64_t* mine = lists + (size_t)warp * K;
+  for (int i = lane; i < K; i += 32) mine[i] = 0;
+  __syncwarp();
+  uint64_t thr = 0;
+  for (int p = warp; p < a.P; p += kSelectWarps) {
+    const uint64_t* src = a.part_keys + ((size_t)p * a.Q + qi) * K;
+    for (int i = 0; i < K; ++i) {
+      const uint64_t x = src[i];
+      if (x <= thr) break;                      // lists are sorted: nothing further can enter
+      warp_list_insert(mine, K, x, lane);
+      thr = mine[K - 1];
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    thr = mine[K - 1];
+    for (int w2 = 1; w2 < kSelectWarps; ++w2) {
+      const uint64_t* other = lists + (size_t)w2 * K;
+      for (int i = 0; i < K; ++i) {
+        const uint64_t x = other[i];
+        if (x <= thr) break;
+        warp_list_insert(mine, K, x, lane);
+        thr = mine[K - 1];
+      }
+    }
+    int n = 0;
+    for (int i = lane; i < K; i += 32) n += (mine[i] != 0);
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) { s_nsel = n; s_extra = 0; }
+  }
+  __syncthreads();
+  const int nsel = s_nsel;
+  const uint64_t* sel = lists;                  // warp 0's list
+
+  // ---- B. candidate table = scan candidates U KG hits
+  for (int i = threadIdx.x; i < nsel; i += blockDim.x) {
+    cand_row[i] = (int32_t)key_row(sel[i]);
+    cand_bonus[i] = 0.0;
+    cand_has[i] = 0;
+  }
+  __syncthreads();
+  if (a.hit_rowptr) {
+    const int64_t h0 = a.hit_rowptr[qi], h1 = a.hit_rowptr[qi + 1];
+    for (int64_t h = h0 + threadIdx.x; h < h1; h += blockDim.x) {
+      const int32_t col = a.hit_col[h];
+      if (col < 0 || (int64_t)col >= a.M) continue;
+      int found = -1;
+      for (int i = 0; i < nsel; ++i) if (cand_row[i] == col) { found = i; break; }
+      if (found < 0) {
+        found = nsel + atomicAdd(&s_extra, 1);
+        if (found >= a.max_cand) continue;      // cannot happen when max_hits_per_query is honest
+        cand_row[found] = col;
+      }
+      cand_bonus[found] = a.hit_bonus[h];
+      cand_has[found] = 1;
+    }
+  }
+  __syncthreads();
+  const int n = min(nsel + s_extra, a.max_cand);
+
+  // ---- C. canonical re-scoring, one warp per candidate
+  const uint16_t* qrow = a.q + (size_t)qi * a.D;
+  for (int c = warp; c < n; c += kSelectWarps) {
+    const size_t off = (size_t)cand_row[c] * a.D;
+    const double sa = canon_dot_warp(qrow, a.gal[0] + off, a.D, lane);
+    const double sb = a.G > 1 ? canon_dot_warp(qrow, a.gal[1] + off, a.D, lane) : 0.0;
+    if (lane == 0)
+      cand_score[c] = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, cand_bonus[c], cand_has[c] != 0);
+  }
+  __syncthreads();
+
+  // ---- D. order by (score desc, row asc) by counting; write the first k
+  __shared__ double s_kth;
+  if (threadIdx.x == 0) s_kth = -INFINITY;
+  __syncthreads();
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    const double sc = cand_score[c];
+    const int32_t rc = cand_row[c];
+    int r = 0;
+    for (int j = 0; j < n; ++j) r += ahead64(cand_score[j], cand_row[j], sc, rc) ? 1 : 0;
+    if (r < a.k) {
+      const size_t o = (size_t)qi * a.k + r;
+      a.out_score64[o] = sc;
+      if (a.out_score32) a.out_score32[o] = (float)sc;
+      a.out_idx[o] = a.idx_base + rc;
+      if (r == a.k - 1) s_kth = sc;
+    }
+  }
+  for (int r = n + threadIdx.x; r < a.k; r += blockDim.x) {
+    const size_t o = (size_t)qi * a.k + r;
+    a.out_score64[o] = -INFINITY;
+    if (a.out_score32) a.out_score32[o] = -INFINITY;
+    a.out_idx[o] = -1;
+  }
+  __syncthreads();
+
+  // ---- E. certificate: nothing the scan rejected can reach the k-th canonical score
+  if (threadIdx.x == 0) {
+    int flag = 0;
+    if (nsel == K) {                            // list full -> rows were rejected
+      const double bound = (double)key_score(sel[K - 1]) + a.eps * (1.0 + 1.0 / 64.0);
+      const double reach = a.alpha * bound + 1e-300;
+      if (!(n >= a.k && s_kth > reach)) flag = 1;
+    }
+    a.out_flags[qi] = flag;
+  }
+}
+
+// ------------------------------------------------------------------ canonical pair scores
+__global__ void score_pairs_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ ga,
+                                   const uint16_t* __restrict__ gb, int D, double wa, double wb,
+                                   double alpha, const int32_t* __restrict__ pq,
+                                   const int64_t* __restrict__ prow, const double* __restrict__ pbonus,
+                                   int64_t n, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = wid; i < n; i += nw) {
+    const uint16_t* qrow = q + (size_t)pq[i] * D;
+    const size_t off = (size_t)prow[i] * D;
+    const double sa = canon_dot_warp(qrow, ga + off, D, lane);
+    const double sb = gb ? canon_dot_warp(qrow, gb + off, D, lane) : 0.0;
+    if (lane == 0)
+      out[i] = canon_fuse(sa, sb, gb != nullptr, wa, wb, alpha, pbonus ? pbonus[i] : 0.0, pbonus != nullptr);
+  }
+}
+
+// ------------------------------------------------------------------ rank path
+// band around the target's clip-level score inside which the fp32 scan cannot decide
+__global__ void rank_band_kernel(const double* __restrict__ t, double alpha, double eps, int Q,
+                                 float* __restrict__ lo, float* __restrict__ hi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Q) return;
+  const double c = t[i] / alpha;
+  const double e = eps * (1.0 + 1.0 / 64.0) + fabs(c) * 1e-12;
+  lo[i] = __double2float_rd(c - e);
+  hi[i] = __double2float_ru(c + e);
+}
+
+__global__ void rank_sum_parts_kernel(const int32_t* __restrict__ part_count, int P, int Q,
+                                      const unsigned int* __restrict__ amb_counter, unsigned int amb_cap,
+                                      unsigned long long* __restrict__ count, int32_t* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Q) return;
+  unsigned long long s = 0;
+  for (int p = 0; p < P; ++p) s += (unsigned long long)part_count[(size_t)p * Q + i];
+  count[i] = s;
+  flags[i] = (*amb_counter > amb_cap) ? 2 : 0;
+}
+
+struct RankFixArgs {
+  const uint16_t* q;
+  const uint16_t* gal[2];
+  int G, D;
+  double w[2];
+  double alpha;
+  const double* t;            // [Q]
+  const int64_t* t_gidx;      // [Q]
+  int64_t idx_base;
+  unsigned long long* count;  // [Q]
+};
+
+// ambiguous rows: decide on canonical scores (KG bonus deliberately ignored here; the hit
+// correction below accounts for it)
+__global__ void rank_amb_kernel(RankFixArgs a, const uint32_t* __restrict__ amb_q,
+                                const uint32_t* __restrict__ amb_row,
+                                const unsigned int* __restrict__ amb_counter, unsigned int amb_cap) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned int n = min(*amb_counter, amb_cap);
+  for (int64_t i = wid; i < n; i += nw) {
+    const int qi = (int)amb_q[i];
+    const int64_t row = amb_row[i];
+    const uint16_t* qrow = a.q + (size_t)qi * a.D;
+    const size_t off = (size_t)row * a.D;
+    const double sa = canon_dot_warp(qrow, a.gal[0] + off, a.D, lane);
+    const double sb = a.G > 1 ? canon_dot_warp(qrow, a.gal[1] + off, a.D, lane) : 0.0;
+    if (lane == 0) {
+      const double f = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, 0.0, false);
+      if (ahead64(f, a.idx_base + row, a.t[qi], a.t_gidx[qi])) atomicAdd(&a.count[qi], 1ull);
+    }
+  }
+}
+
+// KG hits: replace each hit row's un-boosted verdict by its boosted one
+__global__ void rank_hits_kernel(RankFixArgs a, int Q, int64_t M, const int64_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ col, const double* __restrict__ bonus) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int qi = blockIdx.x; qi < Q; qi += gridDim.x) {
+    const uint16_t* qrow = a.q + (size_t)qi * a.D;
+    const int64_t h0 = rowptr[qi], h1 = rowptr[qi + 1];
+    for (int64_t h = h0 + warp; h < h1; h += nwarp) {
+      const int64_t row = col[h];
+      if (row < 0 || row >= M) continue;
+      const size_t off = (size_t)row * a.D;
+      const double sa = canon_dot_warp(qrow, a.gal[0] + off, a.D, lane);
+      const double sb = a.G > 1 ? canon_dot_warp(qrow, a.gal[1] + off, a.D, lane) : 0.0;
+      if (lane == 0) {
+        const double f0 = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, 0.0, false);
+        const double f1 = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, bonus[h], true);
+        const int d = (int)ahead64(f1, a.idx_base + row, a.t[qi], a.t_gidx[qi]) -
+                      (int)ahead64(f0, a.idx_base + row, a.t[qi], a.t_gidx[qi]);
+        if (d) atomicAdd(&a.count[qi], (unsigned long long)(long long)d);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ post-all-gather merge
+__global__ void merge_topk_kernel(const double* __restrict__ in_s, const int64_t* __restrict__ in_i,
+                                  int R, int Q, int k, double* __restrict__ out_s,
+                                  int64_t* __restrict__ out_i) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s = reinterpret_cast<double*>(smem_raw);
+  int64_t* ix = reinterpret_cast<int64_t*>(s + (size_t)R * k);
+  const int qi = blockIdx.x;
+  const int n = R * k;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    const int r = c / k, j = c % k;
+    const size_t o = ((size_t)r * Q + qi) * k + j;
+    s[c] = in_s[o];
+    ix[c] = in_i[o];
+  }
+  __syncthreads();
+  __shared__ int s_valid;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  int myvalid = 0;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    if (ix[c] < 0) continue;
+    ++myvalid;
+    int r = 0;
+    for (int j = 0; j < n; ++j) r += (ix[j] >= 0 && ahead64(s[j], ix[j], s[c], ix[c])) ? 1 : 0;
+    if (r < k) { out_s[(size_t)qi * k + r] = s[c]; out_i[(size_t)qi * k + r] = ix[c]; }
+  }
+  atomicAdd(&s_valid, myvalid);
+  __syncthreads();
+  for (int r = s_valid + threadIdx.x; r < k; r += blockDim.x) {
+    out_s[(size_t)qi * k + r] = -INFINITY;
+    out_i[(size_t)qi * k + r] = -1;
+  }
+}
+
+}  // namespace kemr

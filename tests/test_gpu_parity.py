@@ -1,0 +1,330 @@
+"""GPU parity: every CUDA path, called through the C ABI, against the oracle and the golden
+vectors of the unmodified reference.  Integer / index results and binary64 scores must be
+bit-exact; the fp32 scan scores only have to stay inside the eps band the certificate assumes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from knowledge_enhanced_multimodal_retrieval_b200 import _lib, engine, fusion, index, metrics, retrieval, synth
+
+pytestmark = pytest.mark.gpu
+
+PATHS = [_lib.PATH_WARP, _lib.PATH_MMA]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    _lib.load()
+
+
+def path_ok(path, D, k_sel=18):
+    if path != _lib.PATH_MMA:
+        return True
+    info = engine.device_info()
+    return bool(info["has_tcgen05"]) and D % 64 == 0
+
+
+def dev(x):
+    return engine.quantize(x)
+
+
+def same_dict(got, want):
+    assert set(got) == set(want)
+    for k in want:
+        assert float(got[k]) == float(want[k]), (k, float(got[k]), float(want[k]))
+
+
+# --------------------------------------------------------------------------- building blocks
+def test_quantize_matches_host_rounding():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((37, 72), dtype=np.float32)
+    x[0, 0] = np.float32(1.00390625)      # exact tie between two bf16 values -> even
+    got = engine.quantize(x).view(torch.int16).cpu().numpy().view(np.uint16)
+    assert np.array_equal(got, synth.f32_to_bf16_bits(x))
+    n = engine.quantize(x, normalize=True).float().cpu().numpy()
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=4e-3)
+
+
+def test_score_pairs_bit_exact(small_set):
+    q, img, tgt = small_set["query"], small_set["image"], small_set["target"]
+    si, st = O.canon_dot64(q, img), O.canon_dot64(q, tgt)
+    qq, rr = np.meshgrid(np.arange(q.shape[0]), np.arange(img.shape[0]), indexing="ij")
+    pq = torch.from_numpy(qq.ravel().astype(np.int32)).cuda()
+    pr = torch.from_numpy(rr.ravel().astype(np.int64)).cuda()
+    got = engine.score_pairs(dev(q), dev(img), None, pq, pr).cpu().numpy().reshape(si.shape)
+    assert np.array_equal(got, O.canon_fused64(si, None, 1.0))
+    got = engine.score_pairs(dev(q), dev(img), dev(tgt), pq, pr, 0.1, 0.9, 0.7).cpu().numpy().reshape(si.shape)
+    assert np.array_equal(got, O.canon_fused64(si, st, 0.1, 0.9, 0.7))
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_scan_scores_stay_inside_eps(path):
+    D = 768
+    if not path_ok(path, D):
+        pytest.skip("tcgen05 path unavailable")
+    s = synth.make_retrieval_set(Q=130, M=3000, D=D, seed=5, fused=True, lam=0.3)
+    q, img, tgt = dev(s.query), dev(s.image), dev(s.target)
+    got = engine.score_matrix(q, img, tgt, 0.1, 0.9, path=path).cpu().numpy().astype(np.float64)
+    want = O.canon_fused64(O.canon_dot64(s.query, s.image), O.canon_dot64(s.query, s.target), 0.1, 0.9)
+    err = np.abs(got - want).max()
+    print(f"path {path}: max |fp32 scan - canonical| = {err:.3e}")
+    assert err < engine.DEFAULT_EPS / 4
+
+
+# --------------------------------------------------------------------------- top-k
+SHAPES = [  # Q, M, D, fused, k
+    (1, 1, 8, False, 1), (1, 7, 64, True, 10), (2, 100, 64, False, 10), (3, 1000, 512, True, 10),
+    (5, 257, 128, True, 20), (17, 5000, 768, True, 10), (130, 2100, 768, False, 100), (64, 4099, 1024, True, 10),
+    (96, 160, 64, True, 5), (300, 700, 192, True, 3),
+]
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("Q,M,D,fused,k", SHAPES)
+def test_scan_topk_matches_canonical(path, Q, M, D, fused, k):
+    if not path_ok(path, D):
+        pytest.skip("tcgen05 path unavailable")
+    s = synth.make_retrieval_set(Q=Q, M=M, D=D, seed=100 + Q + M, fused=fused, lam=0.2, diagonal=False)
+    w = (0.1, 0.9) if fused else (1.0, 0.0)
+    idx, score = engine.scan_topk(dev(s.query), dev(s.image), dev(s.target) if fused else None, w[0], w[1],
+                                  k=k, path=path)
+    can = O.canon_fused64(O.canon_dot64(s.query, s.image), O.canon_dot64(s.query, s.target) if fused else None,
+                          w[0], w[1])
+    widx, wscore = O.canon_topk(can, k)
+    kk = min(k, M)
+    assert np.array_equal(idx.cpu().numpy()[:, :kk], widx)
+    assert np.array_equal(score.cpu().numpy()[:, :kk], wscore)
+    if kk < k:
+        assert (idx.cpu().numpy()[:, kk:] == -1).all() and np.isneginf(score.cpu().numpy()[:, kk:]).all()
+    assert int((engine.last_flags() != 0).sum()) == 0
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_scan_topk_exact_ties_lowest_index(path):
+    """Duplicate gallery rows give exactly equal scores: the lowest index must win."""
+    D = 128
+    if not path_ok(path, D):
+        pytest.skip("tcgen05 path unavailable")
+    g = synth.make_gallery(40, D, 3)
+    gal = np.concatenate([g, g, g[:13]], axis=0)          # rows j, j+40 (and j+80) identical
+    q = synth.make_queries((g,), np.arange(6), 0.5, 9)
+    idx, score = engine.scan_topk(dev(q), dev(gal), k=12, path=path)
+    widx, wscore = O.canon_topk(O.canon_fused64(O.canon_dot64(q, gal), None), 12)
+    assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(score.cpu().numpy(), wscore)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_scan_topk_with_kg_boost(path, small_set):
+    q, img, tgt = small_set["query"], small_set["image"], small_set["target"]
+    if not path_ok(path, q.shape[1]):
+        pytest.skip("tcgen05 path unavailable")
+    res, qu, au = small_set["kg_results"], small_set["query_uuids"], small_set["uuids"]
+    si, st = O.canon_dot64(q, img), O.canon_dot64(q, tgt)
+    r, c, sizes = O.kg_hits_to_pairs(res, qu, au)
+    for strategy, params in (("weighted", {"alpha": 0.6, "sparql_weight": 0.4}), ("additive", {"delta": 0.13}),
+                             ("adaptive", {"delta": 0.3})):
+        alpha, hits = fusion.kg_hits_for_strategy(res, qu, au, strategy, params)
+        if strategy == "weighted":
+            bonus = O.canon_bonus_matrix(*si.shape, r, c, 0.4, dedupe=True)
+        elif strategy == "additive":
+            bonus = O.canon_bonus_matrix(*si.shape, r, c, 0.13, dedupe=False)
+        else:
+            vals = np.array([0.3 * O.omega_for_size(int(sizes[i])) for i in r])
+            bonus = O.canon_bonus_matrix(*si.shape, r, c, vals, dedupe=False)
+        can = O.canon_fused64(si, st, 0.5, 0.5, alpha, bonus)
+        idx, score = engine.scan_topk(dev(q), dev(img), dev(tgt), 0.5, 0.5, alpha, hits, k=10, path=path)
+        widx, wscore = O.canon_topk(can, 10)
+        assert np.array_equal(idx.cpu().numpy(), widx), strategy
+        assert np.array_equal(score.cpu().numpy(), wscore), strategy
+
+
+def test_certificate_flags_and_retry():
+    """k_sel == k leaves no margin: with a huge eps the certificate must refuse, and the retry
+    loop must still return the canonical answer."""
+    s = synth.make_retrieval_set(Q=9, M=900, D=64, seed=8, fused=False, lam=0.2, diagonal=False)
+    q, g = dev(s.query), dev(s.image)
+    Q = 9
+    score = torch.empty((Q, 4), dtype=torch.float64, device="cuda")
+    idx = torch.empty((Q, 4), dtype=torch.int64, device="cuda")
+    flags = torch.empty((Q,), dtype=torch.int32, device="cuda")
+    ws = engine.workspace_for(Q, 900, 64, 4)
+    engine.scan_topk_raw(q, g, None, 1.0, 0.0, 1.0, None, 4, 4, 0.5, 0, score, idx, flags, ws, _lib.PATH_WARP)
+    assert (flags.cpu().numpy() & _lib.FLAG_UNCERTIFIED).all()
+    i2, s2 = engine.scan_topk(q, g, k=4, k_sel=4, eps=1e-3)
+    widx, wscore = O.canon_topk(O.canon_fused64(O.canon_dot64(s.query, s.image), None), 4)
+    assert np.array_equal(i2.cpu().numpy(), widx) and np.array_equal(s2.cpu().numpy(), wscore)
+
+
+# --------------------------------------------------------------------------- ranks and metrics
+@pytest.mark.parametrize("path", PATHS)
+def test_rank_targets_matches_canonical(path):
+    D = 256
+    if not path_ok(path, D):
+        pytest.skip("tcgen05 path unavailable")
+    s = synth.make_retrieval_set(Q=333, M=2500, D=D, seed=31, fused=True, lam=0.15, with_kg=True, diagonal=False)
+    q, img, tgt = dev(s.query), dev(s.image), dev(s.target)
+    si, st = O.canon_dot64(s.query, s.image), O.canon_dot64(s.query, s.target)
+    tidx = torch.from_numpy(s.target_idx).cuda()
+    got = engine.rank_targets(q, img, tgt, tidx, 0.5, 0.5, path=path).cpu().numpy()
+    assert np.array_equal(got, O.canon_rank(O.canon_fused64(si, st, 0.5, 0.5), s.target_idx))
+    got = engine.rank_targets(q, img, None, tidx, path=path).cpu().numpy()
+    assert np.array_equal(got, O.canon_rank(O.canon_fused64(si, None), s.target_idx))
+    r, c, _ = O.kg_hits_to_pairs(s.kg_results, s.query_uuids, s.uuids)
+    for alpha in (0.9, 0.3):
+        a, hits = fusion.kg_hits_for_strategy(s.kg_results, s.query_uuids, s.uuids, "weighted",
+                                              {"alpha": alpha, "sparql_weight": 1 - alpha})
+        bonus = O.canon_bonus_matrix(*si.shape, r, c, 1 - alpha, dedupe=True)
+        want = O.canon_rank(O.canon_fused64(si, st, 0.1, 0.9, a, bonus), s.target_idx)
+        got = engine.rank_targets(q, img, tgt, tidx, 0.1, 0.9, a, hits, path=path).cpu().numpy()
+        assert np.array_equal(got, want), alpha
+
+
+def test_metrics_mirror_small_golden(golden, small_set):
+    g = golden["metrics_small"]
+    q, img, tgt, sim = (small_set[k] for k in ("query", "image", "target", "sim"))
+    same_dict(metrics.compute_retrieval_metrics(q, img, prefix="T2I"), g["retrieval_metrics_T2I"])
+    same_dict(metrics.compute_retrieval_metrics(q, tgt, k_values=[1, 3, 7]), g["retrieval_metrics_noprefix_k"])
+    same_dict(metrics.compute_retrieval_metrics_final(q, tgt, img), g["final_05_05"])
+    same_dict(metrics.compute_retrieval_metrics_final(q, tgt, img, prefix="F", t2i_weight=0.1, t2t_weight=0.9),
+              g["final_01_09"])
+    sq = [small_set[k] for k in ("sq_query", "sq_target", "sq_image")]
+    same_dict(metrics.compute_all_retrieval_metrics(*sq), g["all"])
+    same_dict(metrics.compute_all_retrieval_metrics(*sq, tasks=["T2I", "T2T"], compute_recall=False),
+              g["all_T2I_T2T_mrr_only"])
+    same_dict(metrics.compute_training_metrics(*sq), g["training"])
+    same_dict(metrics.compute_recall_at_k(sim), g["recall_at_k_matrix"])
+    same_dict(metrics.compute_mrr_and_mean_rank(sim), g["mrr_matrix"])
+    same_dict(metrics.compute_retrieval_metrics_fusion(sim, prefix="X"), g["metrics_fusion_matrix"])
+    same_dict(fusion.evaluate_retrieval(sim), g["evaluate_retrieval"])
+    got = metrics.compute_retrieval_metrics(q, img)
+    assert all(isinstance(v, np.float64) for v in got.values())
+
+
+def test_metrics_mirror_mid_golden(golden):
+    """1500 x 1500 x 128 set regenerated from its seed; goldens come from the reference."""
+    g = golden["metrics_mid"]
+    s = synth.make_retrieval_set(Q=1500, M=1500, D=128, seed=23, fused=True, lam=0.4, with_kg=True)
+    same_dict(metrics.compute_all_retrieval_metrics(s.query, s.target, s.image), g["all"])
+    for wi, wt in ((0.5, 0.5), (0.1, 0.9)):
+        same_dict(metrics.compute_retrieval_metrics_final(s.query, s.target, s.image, t2i_weight=wi, t2t_weight=wt),
+                  g[f"final_{wi}_{wt}"])
+        for alpha in (0.9, 0.5, 0.1):
+            got = fusion.evaluate_fused(s.query, s.target, s.image, s.kg_results, s.query_uuids, s.uuids, wi, wt,
+                                        "weighted", {"alpha": alpha, "sparql_weight": 1 - alpha})
+            same_dict(got, g[f"sweep_{wi}_{wt}_alpha{alpha}"])
+
+
+def test_dense_fusion_bit_exact(golden, small_set):
+    sim = small_set["sim"]
+    a = (sim, small_set["kg_results"], small_set["query_uuids"], small_set["uuids"])
+    got = {
+        "weighted_default": fusion.weighted_fusion(*a),
+        "weighted_09_01": fusion.weighted_fusion(*a, alpha=0.9, sparql_weight=1 - 0.9),
+        "weighted_renorm": fusion.weighted_fusion(*a, alpha=0.6, sparql_weight=0.6),
+        "additive_default": fusion.additive_bonus_fusion(*a),
+        "additive_013": fusion.additive_bonus_fusion(*a, delta=0.13),
+        "adaptive_default": fusion.adaptive_additive_fusion(*a),
+        "adaptive_custom": fusion.adaptive_additive_fusion(*a, delta=0.3, size_thresholds={2: 0.9, 10: 0.4, 25: 0.05}),
+        "dispatch_weighted": fusion.fuse_clip_and_text2sparql(*a, fusion_strategy="weighted",
+                                                              fusion_params={"alpha": 0.4, "sparql_weight": 0.6}),
+        "dispatch_additive": fusion.fuse_clip_and_text2sparql(*a, fusion_strategy="additive"),
+        "dispatch_adaptive": fusion.fuse_clip_and_text2sparql(*a, fusion_strategy="adaptive",
+                                                              fusion_params={"delta": 0.25}),
+    }
+    for name, mat in got.items():
+        want = small_set["fusion_" + name]
+        assert isinstance(mat, np.ndarray) and mat.dtype == np.float32 and mat.shape == want.shape
+        assert np.array_equal(mat.view(np.uint32), want.view(np.uint32)), name
+        same_dict(fusion.evaluate_retrieval(mat), golden["fusion_small_metrics"][name])
+    assert np.array_equal(sim, small_set["sim"])                       # input untouched
+    with pytest.raises(ValueError):
+        fusion.fuse_clip_and_text2sparql(*a, fusion_strategy="nope")
+    with pytest.raises(AssertionError):
+        fusion.weighted_fusion(sim, a[1], a[2][:-1], a[3])
+    with pytest.raises(AssertionError):
+        fusion.additive_bonus_fusion(sim, a[1], a[2], a[3][:-1])
+
+
+def test_matrix_rank_topk_ties_nan():
+    s = np.array([[0.5, 0.9, 0.9, np.nan, 0.1, 0.3], [np.nan, 0.2, 0.2, 0.2, np.nan, -1.0]], np.float32)
+    for cols in ([2, 4], [3, 0], [0, 1]):
+        got = engine.matrix_rank(s, torch.tensor(cols)).cpu().numpy()
+        assert got.tolist() == O.canon_rank(s.astype(np.float64), np.array(cols)).tolist()
+    idx, val = engine.matrix_topk(s, 4)
+    widx, _ = O.canon_topk(s.astype(np.float64), 4)
+    assert np.array_equal(idx.cpu().numpy(), widx)
+    rng = np.random.default_rng(1)
+    big = rng.standard_normal((33, 5000)).astype(np.float32)
+    big[:, 100:200] = big[:, 300:400]                 # exact ties
+    idx, val = engine.matrix_topk(big, 20)
+    widx, wval = O.canon_topk(big.astype(np.float64), 20)
+    assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(val.cpu().numpy(), wval.astype(np.float32))
+    t = rng.integers(0, 5000, size=33)
+    assert np.array_equal(engine.matrix_rank(big, torch.from_numpy(t)).cpu().numpy(),
+                          O.canon_rank(big.astype(np.float64), t))
+
+
+def test_metrics_reduce_device_equals_host_and_numpy():
+    rng = np.random.default_rng(2)
+    for n in (1, 9, 128, 129, 1000, 4300, 70001):
+        r = rng.integers(1, 50000, size=n).astype(np.int64)
+        ks = [1, 5, 10, 20]
+        h, s, rr = engine.metrics_reduce(torch.from_numpy(r).cuda(), ks)
+        h2, s2, rr2 = engine.metrics_reduce_host(r, ks)
+        assert h.tolist() == h2.tolist() and s == s2 and rr == rr2
+        assert rr == np.sum(1.0 / r)
+
+
+def test_merge_topk():
+    rng = np.random.default_rng(4)
+    R, Q, k = 4, 19, 10
+    sc = np.round(rng.standard_normal((R, Q, k)), 1)               # plenty of exact ties
+    ix = rng.permutation(R * Q * k).reshape(R, Q, k).astype(np.int64)
+    ix[1, :, 7:] = -1
+    oi, os_ = engine.merge_topk(torch.from_numpy(sc).cuda(), torch.from_numpy(ix).cuda(), k)
+    for qi in range(Q):
+        cand = [(-(sc[r, qi, j]), ix[r, qi, j]) for r in range(R) for j in range(k) if ix[r, qi, j] >= 0]
+        cand.sort()
+        assert oi[qi].cpu().tolist() == [c[1] for c in cand[:k]]
+        assert os_[qi].cpu().tolist() == [-c[0] for c in cand[:k]]
+
+
+def test_host_index_equals_device_index(small_set):
+    q, img, tgt = small_set["query"], small_set["image"], small_set["target"]
+    gi = index.GalleryIndex(img, tgt, uuids=small_set["uuids"])
+    hi = index.HostIndex(img, tgt, max_queries=128, max_k=20)
+    i1, s1 = gi.search(q, k=10, t2i_weight=0.3, t2t_weight=0.7)
+    i2, s2, f2 = hi.search(q, k=10, t2i_weight=0.3, t2t_weight=0.7)
+    assert np.array_equal(i1.cpu().numpy(), i2) and np.array_equal(s1.cpu().numpy(), s2) and not f2.any()
+    lists = [small_set["kg_results"].get(u, []) for u in small_set["query_uuids"]]
+    hits = gi.hits_from_uuid_lists(lists, 0.2)
+    i3, s3 = gi.search(q, k=10, t2i_weight=0.5, t2t_weight=0.5, alpha=0.8, hits=hits)
+    csr = (hits.rowptr.cpu().numpy(), hits.col.cpu().numpy(), hits.bonus.cpu().numpy())
+    i4, s4, _ = hi.search(q, k=10, t2i_weight=0.5, t2t_weight=0.5, alpha=0.8, hits_csr=csr)
+    assert np.array_equal(i3.cpu().numpy(), i4) and np.array_equal(s3.cpu().numpy(), s4)
+    hi.close()
+
+
+def test_retrieval_engine_end_to_end(small_set):
+    q, img, tgt = small_set["query"], small_set["image"], small_set["target"]
+    gi = index.GalleryIndex(img, tgt, uuids=small_set["uuids"])
+    table = {f"text {i}": q[i] for i in range(4)}
+    clip = retrieval.CLIPRetrieval(retriever=retrieval.CLIPRetriever(gi, encode_text=lambda s: table[s], top_k=25))
+
+    class T2S:
+        def retrieval(self, query):
+            return [small_set["uuids"][3], "unknown-uuid"]
+
+    eng = retrieval.RetrievalEngine(clip, T2S())
+    can = O.canon_fused64(O.canon_dot64(q[:4], img), O.canon_dot64(q[:4], tgt), 0.5, 0.5)
+    widx, wscore = O.canon_topk(can, 25)
+    for i in range(4):
+        plain = eng.retrieve_text_noknowledge(f"text {i}", threshold=-1)
+        assert [r["uuid"] for r in plain] == [small_set["uuids"][j] for j in widx[i]]
+        assert [r["score"] for r in plain] == wscore[i].tolist()
+        fused = eng.retrieve_text(f"text {i}", threshold=-1)
+        want = O.ref_fuse_clip_sparql_linear(plain, T2S().retrieval(""), 0.8, 0.2)
+        assert fused == want
