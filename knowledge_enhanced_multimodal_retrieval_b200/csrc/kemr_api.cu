@@ -476,7 +476,7 @@ extern "C" int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal
   kemr_index* ix = new kemr_index();
   ix->M = M; ix->D = D; ix->max_q = max_queries; ix->max_k = max_k; ix->hit_cap = (int64_t)max_queries * 256;
   const size_t gbytes = (size_t)M * D * 2;
-  const int ksel = std::min(kMaxKSel, max_k + std::max(8, max_k / 4));
+  const int ksel = std::min(kMaxKSel, (max_k + 6 + 7) / 8 * 8);
   ix->ws_bytes = kemr_workspace_bytes(max_queries, M, D, ksel, 256);
 #define IX_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { kemr_index_destroy(ix); \
     return fail(KEMR_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } } while (0)
@@ -532,7 +532,7 @@ extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int
   }
   int rc = kemr_quantize_rows(ix->d_qf32, ix->d_q, Q, ix->D, normalize, st);
   if (rc) return rc;
-  const int ksel = std::min(kMaxKSel, k + std::max(8, k / 4));
+  const int ksel = std::min(kMaxKSel, (k + 6 + 7) / 8 * 8);
   rc = kemr_scan_topk(ix->d_q, Q, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, alpha, d_rowptr, ix->d_col,
                       ix->d_bonus, max_hits, k, ksel, 2e-5, 0, ix->d_score, nullptr, ix->d_idx, ix->d_flags,
                       ix->ws, ix->ws_bytes, KEMR_PATH_AUTO, st);

@@ -180,7 +180,8 @@ def build_hits(results, query_uuids, artefact_uuids, bonus_of_query, dedupe: boo
 
 # --------------------------------------------------------------------------- scan + top-k
 def default_k_sel(k: int) -> int:
-    return min(MAX_K_SEL, k + max(8, k // 4))
+    """k plus a margin of >= 6, rounded up to the register-list sizes of the tcgen05 epilogue."""
+    return min(MAX_K_SEL, (k + 6 + 7) // 8 * 8)
 
 
 def scan_topk_raw(q, gal_a, gal_b, w_a, w_b, alpha, hits: Optional[KGHits], k, k_sel, eps, idx_base,
