@@ -228,7 +228,7 @@ extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, c
   s.k = k; s.eps = eps; s.idx_base = idx_base;
   s.out_score64 = out_score64; s.out_score32 = out_score32; s.out_idx = out_idx; s.out_flags = out_flags;
   s.max_cand = k_sel + (int)max_hits_per_query;
-  const size_t smem = select_smem_bytes(k_sel, s.max_cand);
+  const size_t smem = select_smem_bytes(pl.P, k_sel, s.max_cand, G, D);
   if (smem > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   select_rescore_kernel<<<Q, kSelectThreads, smem, st>>>(s);

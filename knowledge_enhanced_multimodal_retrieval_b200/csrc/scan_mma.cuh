@@ -10,29 +10,40 @@
 // w_a*acc_a + w_b*acc_b in fp32.  Accumulators are double buffered in TMEM (2 x G x N_TILE <= 512
 // columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation),
-// warps 2..5 = epilogue (one TMEM lane quadrant each).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation),
+// warps 2..9 = epilogue: warp w reads TMEM lane quadrant w%4 and column half (w-2)/4 of the tile,
+// so every scheduler hosts two epilogue warps and a query's candidates come as two lists per CTA.
+// One pipeline stage holds the query chunk ONCE plus the matching chunk of every gallery (the
+// A operand is shared by the T2I and T2T MMAs).
 // Work: the (query block, gallery tile) grid is flattened and cut into equal contiguous ranges, one
 // per persistent CTA (<= #SMs); a CTA emits one K-entry candidate list per query for every query
 // block its range touches ("part slot"), merged later by select.cuh.
 //
-// Epilogue per element: 1-2 FFMA for the fusion weights, one compare against the thread's running
-// threshold; the top-K list of a query lives in REGISTERS (sorted, K <= 32) and an insert is a
-// branch-free compare/select chain, so the score matrix never exists outside TMEM.
+// Epilogue per element: 1-2 FFMA for the fusion weights and one compare against the thread's running
+// threshold.  Survivors are appended to a small per-thread buffer in shared memory; when any lane's
+// buffer is half full the whole warp folds its buffers into per-thread sorted top-K lists that live
+// in REGISTERS (K <= 32, branch-free compare/select insert), so list maintenance runs in lock-step
+// instead of diverging per lane, and the score matrix never exists outside TMEM.
 // Roofline: tensor pipe for batch >= ~250 (2*B*G*M*D flop), HBM below (G*M*D*2 bytes).
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
+#include <vector>
 #include "scan_warp.cuh"
 
 namespace kemr {
 
-constexpr int kMmaThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kMmaThreads = 64 + kEpiThreads;
+constexpr int kBufCap = 16;            // append-buffer entries per epilogue thread
+constexpr int kBufTrigger = 8;         // fold buffers into the lists when any lane holds this many
 constexpr int kBlockM = 128;           // queries per block == TMEM lanes
 constexpr int kBlockK = 64;            // bf16 elements per 128-byte swizzle row
 constexpr int kSmemBudget = 227 * 1024;
 
 struct MmaPlan {
-  int parts = 0;          // part slots per query block
+  int parts = 0;          // candidate lists per query (2 per CTA touching its block)
   int q_pad = 0;          // queries rounded up to kBlockM
   int n_tile = 0;         // gallery rows per MMA tile (128 with two galleries, else 256)
   int n_qb = 0, n_t = 0;  // query blocks, gallery tiles
@@ -69,13 +80,14 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
     const int c0 = (int)(((w0 + 1) * p->ctas - 1) / W), c1 = (int)(((w1 + 1) * p->ctas - 1) / W);
     parts = std::max(parts, c1 - c0 + 1);
   }
-  p->parts = parts;
+  p->parts = 2 * parts;
   p->kc = (D + kBlockK - 1) / kBlockK;
   p->a_rows = Q >= kBlockM ? kBlockM : (Q + 7) / 8 * 8;
   p->K = mma_round_k(K);
-  const size_t stage = (size_t)kBlockM * 128 + (size_t)p->n_tile * 128;
-  p->stages = (int)std::min<size_t>(8, (kSmemBudget - 2048) / stage);
-  p->smem = (size_t)p->stages * stage + 2048;
+  const size_t stage = (size_t)kBlockM * 128 + (size_t)G * p->n_tile * 128;
+  const size_t epi = (size_t)kBufCap * kEpiThreads * 8;
+  p->stages = (int)std::min<size_t>(8, (kSmemBudget - 2048 - epi) / stage);
+  p->smem = (size_t)p->stages * stage + epi + 1024;
   return p->stages >= 2 ? 0 : 1;
 }
 
@@ -106,6 +118,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) __trap();
   }
+}
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -166,7 +184,17 @@ struct MmaArgs {
   ScanArgs s;
   int n_tile, n_qb, n_t, stages, kc, a_rows, parts, q_pad;
   long long W;
+  long long* dbg;       // optional [ctas][8] cycle counters (KEMR_MMA_DEBUG=1)
 };
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
 
 // sorted (descending) per-thread candidate list in registers; rows arrive in increasing order, so
 // strict '>' keeps the lower index ahead among equal scores
@@ -193,29 +221,38 @@ struct RegList {
   }
 };
 
+// value of v[j] for a run-time j in [0,8): 7 selects instead of a register-indexed load
+__device__ __forceinline__ float pick8(const float* v, int j) {
+  const float a0 = (j & 1) ? v[1] : v[0], a1 = (j & 1) ? v[3] : v[2];
+  const float a2 = (j & 1) ? v[5] : v[4], a3 = (j & 1) ? v[7] : v[6];
+  const float b0 = (j & 2) ? a1 : a0, b1 = (j & 2) ? a3 : a2;
+  return (j & 4) ? b1 : b0;
+}
+
 template <int K>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g0,
                 const __grid_constant__ CUtensorMap map_g1, MmaArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) unsigned char smem_mma_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_mma_raw + 1023) & ~(uintptr_t)1023);
   const int n_tile = a.n_tile;
+  const int G = a.s.G;
   const uint32_t a_bytes = kBlockM * 128, b_bytes = (uint32_t)n_tile * 128;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  unsigned char* bar_base = smem + (size_t)a.stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  const uint32_t stage_bytes = a_bytes + (uint32_t)G * b_bytes;
+  float* buf_s = reinterpret_cast<float*>(smem + (size_t)a.stages * stage_bytes);      // [kBufCap][kEpiThreads]
+  uint32_t* buf_r = reinterpret_cast<uint32_t*>(buf_s + kBufCap * kEpiThreads);          // [kBufCap][kEpiThreads]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(buf_r + kBufCap * kEpiThreads);
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* tfull_bar = empty_bar + 8;      // [2]
   uint64_t* tempty_bar = tfull_bar + 2;     // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = a.s.G;
   const long long w_lo = a.W * blockIdx.x / gridDim.x, w_hi = a.W * (blockIdx.x + 1) / gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], kEpiWarps); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&map_q); ptx::prefetch_tmap(&map_g0);
     if (G > 1) ptx::prefetch_tmap(&map_g1);
@@ -230,21 +267,21 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ================================================================= TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)a.a_rows * 128 + b_bytes;
+      const uint32_t tx = (uint32_t)a.a_rows * 128 + (uint32_t)G * b_bytes;
+      long long w_empty = 0; const long long t_begin = clock64();
       for (long long w = w_lo; w < w_hi; ++w) {
         const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
-        for (int g = 0; g < G; ++g) {
-          const CUtensorMap* mg = g ? &map_g1 : &map_g0;
-          for (int kc = 0; kc < a.kc; ++kc) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            unsigned char* sa = smem + (size_t)stage * stage_bytes;
-            ptx::mbar_expect_tx(&full_bar[stage], tx);
-            ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kc * kBlockK, qb * kBlockM);
-            ptx::tma_load_2d(sa + a_bytes, mg, &full_bar[stage], kc * kBlockK, t * n_tile);
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
-          }
+        for (int kc = 0; kc < a.kc; ++kc) {
+          ptx::mbar_wait_timed(&empty_bar[stage], phase ^ 1, w_empty);
+          unsigned char* sa = smem + (size_t)stage * stage_bytes;
+          ptx::mbar_expect_tx(&full_bar[stage], tx);
+          ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kc * kBlockK, qb * kBlockM);
+          ptx::tma_load_2d(sa + a_bytes, &map_g0, &full_bar[stage], kc * kBlockK, t * n_tile);
+          if (G > 1) ptx::tma_load_2d(sa + a_bytes + b_bytes, &map_g1, &full_bar[stage], kc * kBlockK, t * n_tile);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (a.dbg) { a.dbg[blockIdx.x * 16 + 0] = w_empty; a.dbg[blockIdx.x * 16 + 1] = clock64() - t_begin; }
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
@@ -252,50 +289,78 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       int stage = 0; uint32_t phase = 0;
       const uint32_t idesc = umma_idesc_bf16(kBlockM, n_tile);
       long long it = 0;
+      long long w_full = 0, w_tempty = 0; const long long t_begin = clock64();
       for (long long w = w_lo; w < w_hi; ++w, ++it) {
         const int buf = (int)(it & 1);
         const uint32_t bphase = (uint32_t)((it >> 1) & 1);
-        ptx::mbar_wait(&tempty_bar[buf], bphase ^ 1);
+        ptx::mbar_wait_timed(&tempty_bar[buf], bphase ^ 1, w_tempty);
         ptx::tc_fence_after();
-        for (int g = 0; g < G; ++g) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * G + g) * (uint32_t)n_tile;
-          for (int kc = 0; kc < a.kc; ++kc) {
-            ptx::mbar_wait(&full_bar[stage], phase);
-            ptx::tc_fence_after();
-            const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + a_bytes);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * G) * (uint32_t)n_tile;
+        for (int kc = 0; kc < a.kc; ++kc) {
+          ptx::mbar_wait_timed(&full_bar[stage], phase, w_full);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          for (int g = 0; g < G; ++g) {
+            const uint64_t bdesc = umma_desc_sw128(sa + a_bytes + (uint32_t)g * b_bytes);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              ptx::mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
-            ptx::mma_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+              ptx::mma_bf16(d_tmem + (uint32_t)g * (uint32_t)n_tile, adesc + (uint64_t)(k * 2),
+                            bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
           }
+          ptx::mma_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
-        ptx::mma_commit(&tfull_bar[buf]);                // accumulators of this tile are complete
+        ptx::mma_commit(&tfull_bar[buf]);              // accumulators of this tile are complete
       }
+      if (a.dbg) { a.dbg[blockIdx.x * 16 + 2] = w_full; a.dbg[blockIdx.x * 16 + 3] = w_tempty; a.dbg[blockIdx.x * 16 + 4] = clock64() - t_begin; }
     }
   } else {
-    // ================================================================= epilogue (warps 2..5)
+    // ================================================================= epilogue (warps 2..9)
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;                    // which half of the tile's columns
+    const int et = (warp - 2) * 32 + lane;               // epilogue thread id, 0..255
     const int qrow = quad * 32 + lane;                   // query row inside the block
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float w0 = a.s.w[0], w1 = a.s.w[1];
     const int mode = a.s.mode;
+    const int half_cols = n_tile >> 1;
     RegList<K> list;
     list.reset();
+    float thr = -INFINITY;
+    int bcnt = 0;                                        // entries in this thread's append buffer
     int32_t cnt = 0;
     float blo = 0.f, bhi = 0.f;
     int cur_qb = -1;
     const long long Wt = a.W;
     const int C = gridDim.x;
     long long it = 0;
+    long long w_tfull = 0, t_fold = 0, t_ld = 0, t_sm = 0, t_app = 0; const long long t_begin = clock64();
+
+    // fold every lane's append buffer into its register list, in lock-step
+    auto fold = [&]() {
+      const long long tf0 = clock64();
+      const int nmax = __reduce_max_sync(0xffffffffu, bcnt);
+      for (int i = 0; i < nmax; ++i) {
+        if (i < bcnt) {
+          const float s = buf_s[i * kEpiThreads + et];
+          if (s > thr) {
+            list.insert(s, buf_r[i * kEpiThreads + et]);
+            thr = list.threshold();
+          }
+        }
+      }
+      bcnt = 0;
+      t_fold += clock64() - tf0;
+    };
     auto flush = [&](int qb) {
       if (qb < 0) return;
       const long long wq = (long long)qb * a.n_t;
       const int c_first = (int)(((wq + 1) * C - 1) / Wt);
-      const int slot = (int)blockIdx.x - c_first;
+      const int slot = ((int)blockIdx.x - c_first) * 2 + half;
       const int qg = qb * kBlockM + qrow;
       if (mode == kModeTopk) {
+        fold();
         uint64_t* dst = a.s.part_keys + ((size_t)slot * a.q_pad + qg) * a.s.K;
 #pragma unroll
         for (int p = 0; p < K; ++p)
@@ -304,62 +369,70 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         a.s.part_count[(size_t)slot * a.q_pad + qg] = cnt;
       }
     };
+
     for (long long w = w_lo; w < w_hi; ++w, ++it) {
       const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
       if (qb != cur_qb) {
         flush(cur_qb);
         cur_qb = qb;
         list.reset();
+        thr = -INFINITY;
         cnt = 0;
         if (mode == kModeCount) {
-          const int qg = qb * kBlockM + qrow;
-          blo = a.s.band_lo[qg]; bhi = a.s.band_hi[qg];   // padded rows hold +huge: never count
+          const int qg0 = qb * kBlockM + qrow;
+          blo = a.s.band_lo[qg0]; bhi = a.s.band_hi[qg0];   // padded rows hold +huge: never count
         }
       }
       const int buf = (int)(it & 1);
       const uint32_t bphase = (uint32_t)((it >> 1) & 1);
-      ptx::mbar_wait(&tfull_bar[buf], bphase);
+      ptx::mbar_wait_timed(&tfull_bar[buf], bphase, w_tfull);
       ptx::tc_fence_after();
       const int qg = qb * kBlockM + qrow;
       const bool qvalid = qg < a.s.Q;
       const long long row0 = (long long)t * n_tile;
       const int ncols = (int)min((long long)n_tile, a.s.M - row0);
-      float thr = list.threshold();
-      for (int c0 = 0; c0 < n_tile; c0 += 32) {
+      const uint32_t acc0 = lane_addr + (uint32_t)(buf * G) * (uint32_t)n_tile;
+      for (int c0 = half * half_cols; c0 < (half + 1) * half_cols; c0 += 16) {
         if (c0 >= ncols) break;                          // warp-uniform
-        uint32_t ra[32], rb[32];
-        ptx::tmem_ld32(lane_addr + (uint32_t)(buf * G) * (uint32_t)n_tile + (uint32_t)c0, ra);
-        if (G > 1) ptx::tmem_ld32(lane_addr + (uint32_t)(buf * G + 1) * (uint32_t)n_tile + (uint32_t)c0, rb);
+        uint32_t ra[16], rb[16];
+        const long long tl0 = clock64();
+        tmem_ld16(acc0 + (uint32_t)c0, ra);
+        if (G > 1) tmem_ld16(acc0 + (uint32_t)n_tile + (uint32_t)c0, rb);
         ptx::tmem_ld_wait();
+        const long long tl1 = clock64();
+        t_ld += tl1 - tl0;
+        float sv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float s = w0 * __uint_as_float(ra[j]);
+          if (G > 1) s = fmaf(w1, __uint_as_float(rb[j]), s);
+          sv[j] = s;
+        }
+        const bool full = c0 + 16 <= ncols;              // warp-uniform
         if (mode == kModeTopk) {
-          uint32_t mask = 0;
-          float sv[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float s = w0 * __uint_as_float(ra[j]);
-            if (G > 1) s = fmaf(w1, __uint_as_float(rb[j]), s);
-            sv[j] = s;
-            mask |= (s > thr && c0 + j < ncols) ? (1u << j) : 0u;
-          }
-          if (!qvalid) mask = 0;
-          while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            // dynamic register index: resolve with a select chain over the unrolled chunk
-            float s = sv[0];
+          for (int h = 0; h < 2; ++h) {
+            uint32_t mask = 0;
 #pragma unroll
-            for (int jj = 1; jj < 32; ++jj) s = (jj == j) ? sv[jj] : s;
-            if (s > thr) {
-              list.insert(s, (uint32_t)(row0 + c0 + j));
-              thr = list.threshold();
+            for (int j = 0; j < 8; ++j)
+              mask |= (sv[h * 8 + j] > thr && (full || c0 + h * 8 + j < ncols)) ? (1u << j) : 0u;
+            if (!qvalid) mask = 0;
+            const long long ta0 = clock64();
+            while (mask) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              buf_s[bcnt * kEpiThreads + et] = pick8(sv + h * 8, j);
+              buf_r[bcnt * kEpiThreads + et] = (uint32_t)(row0 + c0 + h * 8 + j);
+              ++bcnt;
             }
+            t_app += clock64() - ta0;
+            if (__any_sync(0xffffffffu, bcnt >= kBufTrigger)) fold();
           }
         } else if (mode == kModeCount) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float s = w0 * __uint_as_float(ra[j]);
-            if (G > 1) s = fmaf(w1, __uint_as_float(rb[j]), s);
-            const bool in = c0 + j < ncols;
+          for (int j = 0; j < 16; ++j) {
+            const float s = sv[j];
+            const bool in = full || c0 + j < ncols;
             if (in && s > bhi) ++cnt;
             else if (in && s >= blo) {
               const unsigned int slot = atomicAdd(a.s.amb_counter, 1u);
@@ -370,11 +443,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           if (qvalid) {
             float* dst = a.s.dense + (size_t)qg * a.s.ld + row0 + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float s = w0 * __uint_as_float(ra[j]);
-              if (G > 1) s = fmaf(w1, __uint_as_float(rb[j]), s);
-              if (c0 + j < ncols) dst[j] = s;
-            }
+            for (int j = 0; j < 16; ++j)
+              if (full || c0 + j < ncols) dst[j] = sv[j];
           }
         }
       }
@@ -384,6 +454,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
     }
     flush(cur_qb);
+    if (a.dbg && warp == 2 && lane == 0) { a.dbg[blockIdx.x * 16 + 5] = w_tfull; a.dbg[blockIdx.x * 16 + 6] = t_fold; a.dbg[blockIdx.x * 16 + 7] = clock64() - t_begin; a.dbg[blockIdx.x * 16 + 8] = t_ld; a.dbg[blockIdx.x * 16 + 9] = t_sm; a.dbg[blockIdx.x * 16 + 10] = t_app; }
   }
 
   ptx::tc_fence_before();
@@ -451,12 +522,34 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
   ma.n_tile = pl.n_tile; ma.n_qb = pl.n_qb; ma.n_t = pl.n_t; ma.stages = pl.stages; ma.kc = pl.kc;
   ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad;
   ma.W = (long long)pl.n_qb * pl.n_t;
-  switch (pl.K) {
-    case 8: return mma_launch_k<8>(mq, m0, m1, ma, pl, st);
-    case 16: return mma_launch_k<16>(mq, m0, m1, ma, pl, st);
-    case 24: return mma_launch_k<24>(mq, m0, m1, ma, pl, st);
-    default: return mma_launch_k<32>(mq, m0, m1, ma, pl, st);
+  ma.dbg = nullptr;
+  static const bool debug = getenv("KEMR_MMA_DEBUG") != nullptr;
+  if (debug) {
+    static long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 1024 * 16 * sizeof(long long));
+    cudaMemsetAsync(dbuf, 0, 1024 * 16 * sizeof(long long), st);
+    ma.dbg = dbuf;
   }
+  int rc_launch = 0;
+  switch (pl.K) {
+    case 8: rc_launch = mma_launch_k<8>(mq, m0, m1, ma, pl, st); break;
+    case 16: rc_launch = mma_launch_k<16>(mq, m0, m1, ma, pl, st); break;
+    case 24: rc_launch = mma_launch_k<24>(mq, m0, m1, ma, pl, st); break;
+    default: rc_launch = mma_launch_k<32>(mq, m0, m1, ma, pl, st); break;
+  }
+  if (debug && rc_launch == 0) {
+    static int printed = 0;
+    cudaStreamSynchronize(st);
+    if (printed++ < 4) {
+      std::vector<long long> h((size_t)pl.ctas * 16);
+      cudaMemcpy(h.data(), ma.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+      double avg[16] = {0};
+      for (int c = 0; c < pl.ctas; ++c) for (int i = 0; i < 16; ++i) avg[i] += (double)h[(size_t)c * 16 + i] / pl.ctas;
+      fprintf(stderr, "[kemr mma dbg] ctas=%d tiles/cta=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f ld=%.0f score+mask=%.0f append=%.0f cycles\n",
+              pl.ctas, (double)ma.W / pl.ctas, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7], avg[8], avg[9], avg[10]);
+    }
+  }
+  return rc_launch;
 }
 
 }  // namespace kemr

@@ -33,62 +33,114 @@ struct SelectArgs {
 
 constexpr int kSelectThreads = 256;
 constexpr int kSelectWarps = kSelectThreads / 32;
+constexpr int kCountMax = 4096;          // up to this many candidate keys are ranked by counting
 
-// dynamic smem: lists[kSelectWarps][K] u64 | cand_score[max_cand] f64 | cand_bonus[max_cand] f64 |
-//               cand_row[max_cand] i32 | cand_has[max_cand] u8
-inline size_t select_smem_bytes(int K, int max_cand) {
-  size_t b = (size_t)kSelectWarps * K * 8 + (size_t)max_cand * (8 + 8 + 4);
-  b += (size_t)max_cand;          // has-bonus flags
+// dynamic smem: keys[max(kSelectWarps*K, min(P*K, kCountMax))] u64 | cand_score[max_cand] f64 |
+//   cand_bonus[max_cand] f64 | cand_row[max_cand] i32 | cand_has[max_cand] u8 (padded) |
+//   qrow[D] bf16 | rows[kSelectWarps][G][D] bf16
+inline size_t select_key_slots(int P, int K) {
+  const size_t all = (size_t)P * K, per_warp = (size_t)kSelectWarps * K;
+  return all <= (size_t)kCountMax ? (all > per_warp ? all : per_warp) : per_warp;
+}
+inline size_t select_smem_bytes(int P, int K, int max_cand, int G, int D) {
+  size_t b = select_key_slots(P, K) * 8 + (size_t)max_cand * (8 + 8 + 4);
+  b += ((size_t)max_cand + 15) & ~(size_t)15;
+  b += (size_t)D * 2 + (size_t)kSelectWarps * G * D * 2;
   return (b + 15) & ~(size_t)15;
+}
+
+// canonical dot from rows staged in shared memory (same order as common.cuh::canon_dot_warp)
+__device__ __forceinline__ double canon_dot_smem(const uint16_t* a, const uint16_t* b, int D, int lane) {
+  double acc = 0.0;
+  for (int d = lane; d < D; d += 32)
+    acc = fma((double)bf16_to_f32(a[d]), (double)bf16_to_f32(b[d]), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, o));
+  return __shfl_sync(0xffffffffu, acc, 0);
 }
 
 __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = a.K;
-  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw);
-  double* cand_score = reinterpret_cast<double*>(lists + (size_t)kSelectWarps * K);
+  const int n_all = a.P * K;
+  const bool by_count = n_all <= kCountMax;
+  // carve-up (16-byte aligned pieces first): qrow | rows | keys | cand_score | cand_bonus | cand_row | cand_has
+  uint16_t* s_q = reinterpret_cast<uint16_t*>(smem_raw);
+  uint16_t* s_rows = s_q + a.D;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(s_rows + (size_t)kSelectWarps * a.G * a.D);
+  const size_t per_warp = (size_t)kSelectWarps * K;
+  const size_t key_slots = by_count ? ((size_t)n_all > per_warp ? (size_t)n_all : per_warp) : per_warp;
+  double* cand_score = reinterpret_cast<double*>(lists + key_slots);
   double* cand_bonus = cand_score + a.max_cand;
   int32_t* cand_row = reinterpret_cast<int32_t*>(cand_bonus + a.max_cand);
   unsigned char* cand_has = reinterpret_cast<unsigned char*>(cand_row + a.max_cand);
   __shared__ int s_nsel, s_extra;
+  __shared__ uint64_t s_sel[kMaxKSel];
 
   const int qi = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // ---- A. per-warp selection over the parts, then fold into warp 0's list
-  uint64_t* mine = lists + (size_t)warp * K;
-  for (int i = lane; i < K; i += 32) mine[i] = 0;
-  __syncwarp();
-  uint64_t thr = 0;
-  for (int p = warp; p < a.P; p += kSelectWarps) {
-    const uint64_t* src = a.part_keys + ((size_t)p * a.Q + qi) * K;
-    for (int i = 0; i < K; ++i) {
-      const uint64_t x = src[i];
-      if (x <= thr) break;                      // lists are sorted: nothing further can enter
-      warp_list_insert(mine, K, x, lane);
-      thr = mine[K - 1];
+  // stage the query row (coalesced 16-byte loads)
+  for (int c = threadIdx.x; c < (a.D >> 3); c += blockDim.x)
+    reinterpret_cast<uint4*>(s_q)[c] = reinterpret_cast<const uint4*>(a.q + (size_t)qi * a.D)[c];
+
+  // ---- A. the K best fp32 candidates over all parts
+  if (by_count) {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s_sel[i] = 0;
+    for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+      const int p = i / K, j = i - p * K;
+      lists[i] = a.part_keys[((size_t)p * a.Q + qi) * K + j];
     }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    thr = mine[K - 1];
-    for (int w2 = 1; w2 < kSelectWarps; ++w2) {
-      const uint64_t* other = lists + (size_t)w2 * K;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+      const uint64_t x = lists[i];
+      if (!x) continue;
+      int r = 0;
+      for (int j = 0; j < n_all; ++j) r += lists[j] > x ? 1 : 0;
+      if (r < K) s_sel[r] = x;                            // keys are distinct -> ranks are distinct
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int n = 0;
+      for (int i = lane; i < K; i += 32) n += (s_sel[i] != 0);
+      for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+      if (lane == 0) { s_nsel = n; s_extra = 0; }
+    }
+  } else {
+    uint64_t* mine = lists + (size_t)warp * K;
+    for (int i = lane; i < K; i += 32) mine[i] = 0;
+    __syncwarp();
+    uint64_t thr = 0;
+    for (int p = warp; p < a.P; p += kSelectWarps) {
+      const uint64_t* src = a.part_keys + ((size_t)p * a.Q + qi) * K;
       for (int i = 0; i < K; ++i) {
-        const uint64_t x = other[i];
-        if (x <= thr) break;
+        const uint64_t x = src[i];
+        if (x <= thr) break;                      // lists are sorted: nothing further can enter
         warp_list_insert(mine, K, x, lane);
         thr = mine[K - 1];
       }
     }
-    int n = 0;
-    for (int i = lane; i < K; i += 32) n += (mine[i] != 0);
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-    if (lane == 0) { s_nsel = n; s_extra = 0; }
+    __syncthreads();
+    if (warp == 0) {
+      thr = mine[K - 1];
+      for (int w2 = 1; w2 < kSelectWarps; ++w2) {
+        const uint64_t* other = lists + (size_t)w2 * K;
+        for (int i = 0; i < K; ++i) {
+          const uint64_t x = other[i];
+          if (x <= thr) break;
+          warp_list_insert(mine, K, x, lane);
+          thr = mine[K - 1];
+        }
+      }
+      int n = 0;
+      for (int i = lane; i < K; i += 32) { s_sel[i] = mine[i]; n += (mine[i] != 0); }
+      for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+      if (lane == 0) { s_nsel = n; s_extra = 0; }
+    }
   }
   __syncthreads();
   const int nsel = s_nsel;
-  const uint64_t* sel = lists;                  // warp 0's list
+  const uint64_t* sel = s_sel;
 
   // ---- B. candidate table = scan candidates U KG hits
   for (int i = threadIdx.x; i < nsel; i += blockDim.x) {
@@ -116,14 +168,21 @@ __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectAr
   __syncthreads();
   const int n = min(nsel + s_extra, a.max_cand);
 
-  // ---- C. canonical re-scoring, one warp per candidate
-  const uint16_t* qrow = a.q + (size_t)qi * a.D;
+  // ---- C. canonical re-scoring, one warp per candidate; rows are fetched with coalesced
+  //         16-byte loads into shared memory, then accumulated in the canonical lane order
+  uint16_t* my_rows = s_rows + (size_t)warp * a.G * a.D;
+  const int nchunk = a.D >> 3;
   for (int c = warp; c < n; c += kSelectWarps) {
     const size_t off = (size_t)cand_row[c] * a.D;
-    const double sa = canon_dot_warp(qrow, a.gal[0] + off, a.D, lane);
-    const double sb = a.G > 1 ? canon_dot_warp(qrow, a.gal[1] + off, a.D, lane) : 0.0;
+    for (int g = 0; g < a.G; ++g)
+      for (int ch = lane; ch < nchunk; ch += 32)
+        reinterpret_cast<uint4*>(my_rows + (size_t)g * a.D)[ch] = ldg_stream(a.gal[g] + off + ch * 8);
+    __syncwarp();
+    const double sa = canon_dot_smem(s_q, my_rows, a.D, lane);
+    const double sb = a.G > 1 ? canon_dot_smem(s_q, my_rows + a.D, a.D, lane) : 0.0;
     if (lane == 0)
       cand_score[c] = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, cand_bonus[c], cand_has[c] != 0);
+    __syncwarp();
   }
   __syncthreads();
 
