@@ -112,6 +112,7 @@ struct ScanPlan {
   int path;        // KEMR_PATH_WARP / KEMR_PATH_MMA
   int QB, CH;      // warp path
   int P;           // parts (lists per query)
+  int Kp;          // entries per part list
   int groups;      // warp path: query groups (grid.y)
   MmaPlan mma;     // mma path
 };
@@ -138,6 +139,7 @@ static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, 
     int rc = mma_make_plan(Q, M, D, G, K, mode, dv.sms, &pl->mma);
     if (rc) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path: cannot plan this shape");
     pl->P = pl->mma.parts;
+    pl->Kp = pl->mma.K;
     return KEMR_OK;
   }
   pl->QB = Q == 1 ? 1 : 2;
@@ -147,6 +149,7 @@ static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, 
   int P = std::max(1, (want + pl->groups - 1) / pl->groups);
   P = (int)std::min<int64_t>(P, std::max<int64_t>(1, (M + 15) / 16));
   pl->P = P;
+  pl->Kp = K;
   return KEMR_OK;
 }
 
@@ -204,14 +207,14 @@ extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, c
   ScanPlan pl;
   if ((rc = make_plan(Q, M, D, G, k_sel, kModeTopk, path, dv, &pl))) return rc;
   const int Qrows = pl.path == KEMR_PATH_MMA ? pl.mma.q_pad : Q;
-  const size_t need = parts_bytes(pl.P, Qrows, k_sel);
+  const size_t need = parts_bytes(pl.P, Qrows, pl.Kp);
   if (!workspace || workspace_bytes < need) return fail(KEMR_ERR_WORKSPACE, "scan_topk needs %zu workspace bytes, got %zu", need, workspace_bytes);
   cudaStream_t st = S(stream);
   uint64_t* part_keys = reinterpret_cast<uint64_t*>(workspace);
 
   ScanArgs a{};
   a.q = q; a.Q = Q; a.gal[0] = gal_a; a.gal[1] = gal_b; a.G = G; a.M = M; a.D = D;
-  a.w[0] = (float)w_a; a.w[1] = (float)w_b; a.mode = kModeTopk; a.K = k_sel; a.part_keys = part_keys;
+  a.w[0] = (float)w_a; a.w[1] = (float)w_b; a.mode = kModeTopk; a.K = pl.Kp; a.part_keys = part_keys;
   if (pl.path == KEMR_PATH_MMA) {
     CUDA_TRY(cudaMemsetAsync(part_keys, 0, need, st));
     if ((rc = mma_launch(a, pl.mma, st))) return fail(KEMR_ERR_CUDA, "tcgen05 scan launch failed: %s", mma_last_error());
@@ -221,14 +224,14 @@ extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, c
   if (g_scan_done_event) CUDA_TRY(cudaEventRecord(g_scan_done_event, st));
 
   SelectArgs s{};
-  s.part_keys = part_keys; s.P = pl.P; s.Q = Qrows; s.K = k_sel;
+  s.part_keys = part_keys; s.P = pl.P; s.Q = Qrows; s.K = k_sel; s.Kp = pl.Kp;
   s.q = q; s.gal[0] = gal_a; s.gal[1] = gal_b; s.G = G; s.D = D; s.M = M;
   s.w[0] = w_a; s.w[1] = w_b; s.alpha = alpha;
   s.hit_rowptr = hit_rowptr; s.hit_col = hit_col; s.hit_bonus = hit_bonus;
   s.k = k; s.eps = eps; s.idx_base = idx_base;
   s.out_score64 = out_score64; s.out_score32 = out_score32; s.out_idx = out_idx; s.out_flags = out_flags;
   s.max_cand = k_sel + (int)max_hits_per_query;
-  const size_t smem = select_smem_bytes(pl.P, k_sel, s.max_cand, G, D);
+  const size_t smem = select_smem_bytes(pl.P, pl.Kp, k_sel, s.max_cand, G, D);
   if (smem > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   select_rescore_kernel<<<Q, kSelectThreads, smem, st>>>(s);

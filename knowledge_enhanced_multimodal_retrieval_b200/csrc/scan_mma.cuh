@@ -37,10 +37,11 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kMmaThreads = 64 + kEpiThreads;
 constexpr int kBufCap = 16;            // append-buffer entries per epilogue thread
-constexpr int kBufTrigger = 8;         // fold buffers into the lists when any lane holds this many
+constexpr int kBufTrigger = 8;         // fold buffers into the lists when any lane holds this many (+8 new fit)
 constexpr int kBlockM = 128;           // queries per block == TMEM lanes
 constexpr int kBlockK = 64;            // bf16 elements per 128-byte swizzle row
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int kMaxStages = 16;
 
 struct MmaPlan {
   int parts = 0;          // candidate lists per query (2 per CTA touching its block)
@@ -52,6 +53,8 @@ struct MmaPlan {
   int kc = 0;             // K chunks of 64
   int a_rows = 0;         // query rows actually loaded per block
   int K = 0;              // list length (8, 16, 24, 32)
+  int ts = 0;             // 1: query block lives in TMEM (A operand from TMEM), only B is streamed
+  int acc_col = 0;        // first TMEM column of the accumulators
   size_t smem = 0;
 };
 
@@ -65,7 +68,21 @@ inline int mma_round_k(int K) { return K <= 8 ? 8 : K <= 16 ? 16 : K <= 24 ? 24 
 
 inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sms, MmaPlan* p) {
   (void)mode;
-  p->n_tile = G == 2 ? 128 : 256;
+  p->kc = (D + kBlockK - 1) / kBlockK;
+  // A-in-TMEM variant: the 128 x D query block takes kc*32 TMEM columns (two bf16 per cell); what is
+  // left holds the double-buffered accumulators.  It halves shared-memory and L2 traffic because
+  // only gallery rows are streamed.  Falls back to both-operands-in-smem when D is too large.
+  {
+    // Measured on B200: reading the 128x16 A tile from TMEM costs ~64 cycles per MMA whatever N is,
+    // so this variant only pays for N >= 256; it is kept as an opt-in experiment (KEMR_MMA_TS=1).
+    static const bool no_ts = getenv("KEMR_MMA_TS") == nullptr;
+    const int avail = 512 - p->kc * 32;
+    int n = 256;
+    while (n >= 32 && 2 * G * n > avail) n >>= 1;
+    p->ts = (!no_ts && n >= 32) ? 1 : 0;
+    p->n_tile = p->ts ? n : (G == 2 ? 128 : 256);
+    p->acc_col = p->ts ? p->kc * 32 : 0;
+  }
   p->n_qb = (Q + kBlockM - 1) / kBlockM;
   p->q_pad = p->n_qb * kBlockM;
   const int64_t nt = (M + p->n_tile - 1) / p->n_tile;
@@ -81,12 +98,13 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
     parts = std::max(parts, c1 - c0 + 1);
   }
   p->parts = 2 * parts;
-  p->kc = (D + kBlockK - 1) / kBlockK;
   p->a_rows = Q >= kBlockM ? kBlockM : (Q + 7) / 8 * 8;
-  p->K = mma_round_k(K);
-  const size_t stage = (size_t)kBlockM * 128 + (size_t)G * p->n_tile * 128;
+  // Many parts per query: each keeps a short list (the global top-k spreads over the parts); the
+  // select kernel's certificate flags the rare query whose winners crowd into one part.
+  p->K = mma_round_k(p->parts >= 12 && K <= 24 ? std::min(K, 8) : K);
+  const size_t stage = (p->ts ? 0 : (size_t)kBlockM * 128) + (size_t)G * p->n_tile * 128;
   const size_t epi = (size_t)kBufCap * kEpiThreads * 8;
-  p->stages = (int)std::min<size_t>(8, (kSmemBudget - 2048 - epi) / stage);
+  p->stages = (int)std::min<size_t>(kMaxStages, (kSmemBudget - 2048 - epi) / stage);
   p->smem = (size_t)p->stages * stage + epi + 1024;
   return p->stages >= 2 ? 0 : 1;
 }
@@ -119,9 +137,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
+template <bool DBG>
 __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  if (!DBG) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();     // try_wait itself may block, so time the whole wait
   mbar_wait(bar, parity);
   acc += clock64() - t0;
 }
@@ -149,6 +168,20 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -182,7 +215,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 
 struct MmaArgs {
   ScanArgs s;
-  int n_tile, n_qb, n_t, stages, kc, a_rows, parts, q_pad;
+  int n_tile, n_qb, n_t, stages, kc, a_rows, parts, q_pad, acc_col;
   long long W;
   long long* dbg;       // optional [ctas][8] cycle counters (KEMR_MMA_DEBUG=1)
 };
@@ -198,6 +231,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 // sorted (descending) per-thread candidate list in registers; rows arrive in increasing order, so
 // strict '>' keeps the lower index ahead among equal scores
+template <bool DBG>
+__device__ __forceinline__ long long tick() { return DBG ? clock64() : 0ll; }
+
 template <int K>
 struct RegList {
   float sc[K];
@@ -229,7 +265,7 @@ __device__ __forceinline__ float pick8(const float* v, int j) {
   return (j & 4) ? b1 : b0;
 }
 
-template <int K>
+template <int K, bool DBG, bool TS>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g0,
                 const __grid_constant__ CUtensorMap map_g1, MmaArgs a) {
@@ -237,15 +273,16 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_mma_raw + 1023) & ~(uintptr_t)1023);
   const int n_tile = a.n_tile;
   const int G = a.s.G;
-  const uint32_t a_bytes = kBlockM * 128, b_bytes = (uint32_t)n_tile * 128;
+  const uint32_t a_bytes = TS ? 0u : (uint32_t)kBlockM * 128u, b_bytes = (uint32_t)n_tile * 128;
   const uint32_t stage_bytes = a_bytes + (uint32_t)G * b_bytes;
   float* buf_s = reinterpret_cast<float*>(smem + (size_t)a.stages * stage_bytes);      // [kBufCap][kEpiThreads]
   uint32_t* buf_r = reinterpret_cast<uint32_t*>(buf_s + kBufCap * kEpiThreads);          // [kBufCap][kEpiThreads]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(buf_r + kBufCap * kEpiThreads);
-  uint64_t* empty_bar = full_bar + 8;
-  uint64_t* tfull_bar = empty_bar + 8;      // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;     // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;      // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2]
+  uint64_t* aready_bar = tempty_bar + 2;             // [1] query block written to TMEM (TS)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aready_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long w_lo = a.W * blockIdx.x / gridDim.x, w_hi = a.W * (blockIdx.x + 1) / gridDim.x;
@@ -253,6 +290,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], kEpiWarps); }
+    ptx::mbar_init(aready_bar, kEpiWarps);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&map_q); ptx::prefetch_tmap(&map_g0);
     if (G > 1) ptx::prefetch_tmap(&map_g1);
@@ -267,53 +305,73 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ================================================================= TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)a.a_rows * 128 + (uint32_t)G * b_bytes;
-      long long w_empty = 0; const long long t_begin = clock64();
+      const uint32_t tx = (TS ? 0u : (uint32_t)a.a_rows * 128u) + (uint32_t)G * b_bytes;
+      long long w_empty = 0; const long long t_begin = tick<DBG>();
       for (long long w = w_lo; w < w_hi; ++w) {
         const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
         for (int kc = 0; kc < a.kc; ++kc) {
-          ptx::mbar_wait_timed(&empty_bar[stage], phase ^ 1, w_empty);
+          ptx::mbar_wait_timed<DBG>(&empty_bar[stage], phase ^ 1, w_empty);
           unsigned char* sa = smem + (size_t)stage * stage_bytes;
           ptx::mbar_expect_tx(&full_bar[stage], tx);
-          ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kc * kBlockK, qb * kBlockM);
+          if (!TS) ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kc * kBlockK, qb * kBlockM);
           ptx::tma_load_2d(sa + a_bytes, &map_g0, &full_bar[stage], kc * kBlockK, t * n_tile);
           if (G > 1) ptx::tma_load_2d(sa + a_bytes + b_bytes, &map_g1, &full_bar[stage], kc * kBlockK, t * n_tile);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (a.dbg) { a.dbg[blockIdx.x * 16 + 0] = w_empty; a.dbg[blockIdx.x * 16 + 1] = clock64() - t_begin; }
+      if (DBG && a.dbg) { a.dbg[blockIdx.x * 16 + 0] = w_empty; a.dbg[blockIdx.x * 16 + 1] = tick<DBG>() - t_begin; }
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t idesc = umma_idesc_bf16(kBlockM, n_tile);
+      const uint32_t idesc_all = umma_idesc_bf16(kBlockM, G * n_tile);
       long long it = 0;
-      long long w_full = 0, w_tempty = 0; const long long t_begin = clock64();
+      long long w_full = 0, w_tempty = 0; const long long t_begin = tick<DBG>();
+      int mma_qb = -1; uint32_t aphase = 0;
       for (long long w = w_lo; w < w_hi; ++w, ++it) {
+        if (TS) {
+          const int qb = (int)(w / a.n_t);
+          if (qb != mma_qb) {                       // wait until the epilogue warps stored this query block
+            ptx::mbar_wait_timed<DBG>(aready_bar, aphase, w_tempty);
+            ptx::tc_fence_after();
+            aphase ^= 1; mma_qb = qb;
+          }
+        }
         const int buf = (int)(it & 1);
         const uint32_t bphase = (uint32_t)((it >> 1) & 1);
-        ptx::mbar_wait_timed(&tempty_bar[buf], bphase ^ 1, w_tempty);
+        ptx::mbar_wait_timed<DBG>(&tempty_bar[buf], bphase ^ 1, w_tempty);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * G) * (uint32_t)n_tile;
+        const uint32_t d_tmem = tmem_base + (uint32_t)a.acc_col + (uint32_t)(buf * G) * (uint32_t)n_tile;
         for (int kc = 0; kc < a.kc; ++kc) {
-          ptx::mbar_wait_timed(&full_bar[stage], phase, w_full);
+          ptx::mbar_wait_timed<DBG>(&full_bar[stage], phase, w_full);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t adesc = umma_desc_sw128(sa);
-          for (int g = 0; g < G; ++g) {
-            const uint64_t bdesc = umma_desc_sw128(sa + a_bytes + (uint32_t)g * b_bytes);
+          if (TS) {
+            for (int g = 0; g < G; ++g) {
+              const uint64_t bdesc = umma_desc_sw128(sa + a_bytes + (uint32_t)g * b_bytes);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                ptx::mma_bf16_ts(d_tmem + (uint32_t)g * (uint32_t)n_tile, tmem_base + (uint32_t)(kc * 32 + k * 8),
+                                 bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+            }
+          } else {
+            // The galleries' chunks sit back to back in the stage, i.e. they form ONE K-major tile of
+            // G*n_tile rows: a single MMA with N = G*n_tile fills both accumulators (columns
+            // [0,n_tile) = T2I, [n_tile,2*n_tile) = T2T) and reads the query chunk once.
+            const uint64_t bdesc = umma_desc_sw128(sa + a_bytes);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              ptx::mma_bf16(d_tmem + (uint32_t)g * (uint32_t)n_tile, adesc + (uint64_t)(k * 2),
-                            bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+              ptx::mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_all, (kc | k) ? 1u : 0u);
           }
           ptx::mma_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         ptx::mma_commit(&tfull_bar[buf]);              // accumulators of this tile are complete
       }
-      if (a.dbg) { a.dbg[blockIdx.x * 16 + 2] = w_full; a.dbg[blockIdx.x * 16 + 3] = w_tempty; a.dbg[blockIdx.x * 16 + 4] = clock64() - t_begin; }
+      if (DBG && a.dbg) { a.dbg[blockIdx.x * 16 + 2] = w_full; a.dbg[blockIdx.x * 16 + 3] = w_tempty; a.dbg[blockIdx.x * 16 + 4] = tick<DBG>() - t_begin; }
     }
   } else {
     // ================================================================= epilogue (warps 2..9)
@@ -335,11 +393,11 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const long long Wt = a.W;
     const int C = gridDim.x;
     long long it = 0;
-    long long w_tfull = 0, t_fold = 0, t_ld = 0, t_sm = 0, t_app = 0; const long long t_begin = clock64();
+    long long w_tfull = 0, t_fold = 0, t_ld = 0, t_sm = 0, t_app = 0; const long long t_begin = tick<DBG>();
 
     // fold every lane's append buffer into its register list, in lock-step
     auto fold = [&]() {
-      const long long tf0 = clock64();
+      const long long tf0 = tick<DBG>();
       const int nmax = __reduce_max_sync(0xffffffffu, bcnt);
       for (int i = 0; i < nmax; ++i) {
         if (i < bcnt) {
@@ -351,7 +409,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
       bcnt = 0;
-      t_fold += clock64() - tf0;
+      t_fold += tick<DBG>() - tf0;
     };
     auto flush = [&](int qb) {
       if (qb < 0) return;
@@ -378,6 +436,29 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         list.reset();
         thr = -INFINITY;
         cnt = 0;
+        if (TS) {
+          // This warp has seen the last tile of the previous block complete (tfull), so no MMA still
+          // reads the old block: store the new 128 x D query block into TMEM, one row per lane,
+          // two bf16 per 32-bit cell, 16 cells per store; pad rows/columns are zero.
+          const int qg0 = qb * kBlockM + qrow;
+          const uint16_t* qsrc = a.s.q + (size_t)qg0 * a.s.D;
+          const int nblk = a.kc * 2;                    // 16-cell blocks per row
+          for (int cb = half; cb < nblk; cb += 2) {
+            uint32_t r[16];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const int e0 = cb * 32 + v * 8;           // first bf16 element of this 16-byte piece
+              uint4 x = make_uint4(0, 0, 0, 0);
+              if (qg0 < a.s.Q && e0 < a.s.D) x = *reinterpret_cast<const uint4*>(qsrc + e0);
+              r[v * 4 + 0] = x.x; r[v * 4 + 1] = x.y; r[v * 4 + 2] = x.z; r[v * 4 + 3] = x.w;
+            }
+            ptx::tmem_st16(lane_addr + (uint32_t)(cb * 16), r);
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(aready_bar);
+        }
         if (mode == kModeCount) {
           const int qg0 = qb * kBlockM + qrow;
           blo = a.s.band_lo[qg0]; bhi = a.s.band_hi[qg0];   // padded rows hold +huge: never count
@@ -385,21 +466,21 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       const int buf = (int)(it & 1);
       const uint32_t bphase = (uint32_t)((it >> 1) & 1);
-      ptx::mbar_wait_timed(&tfull_bar[buf], bphase, w_tfull);
+      ptx::mbar_wait_timed<DBG>(&tfull_bar[buf], bphase, w_tfull);
       ptx::tc_fence_after();
       const int qg = qb * kBlockM + qrow;
       const bool qvalid = qg < a.s.Q;
       const long long row0 = (long long)t * n_tile;
       const int ncols = (int)min((long long)n_tile, a.s.M - row0);
-      const uint32_t acc0 = lane_addr + (uint32_t)(buf * G) * (uint32_t)n_tile;
+      const uint32_t acc0 = lane_addr + (uint32_t)a.acc_col + (uint32_t)(buf * G) * (uint32_t)n_tile;
       for (int c0 = half * half_cols; c0 < (half + 1) * half_cols; c0 += 16) {
         if (c0 >= ncols) break;                          // warp-uniform
         uint32_t ra[16], rb[16];
-        const long long tl0 = clock64();
+        const long long tl0 = tick<DBG>();
         tmem_ld16(acc0 + (uint32_t)c0, ra);
         if (G > 1) tmem_ld16(acc0 + (uint32_t)n_tile + (uint32_t)c0, rb);
         ptx::tmem_ld_wait();
-        const long long tl1 = clock64();
+        const long long tl1 = tick<DBG>();
         t_ld += tl1 - tl0;
         float sv[16];
 #pragma unroll
@@ -410,22 +491,27 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         const bool full = c0 + 16 <= ncols;              // warp-uniform
         if (mode == kModeTopk) {
+          // per 8-column run: fast reject on the run's maximum, else append the survivors
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            uint32_t mask = 0;
+            float m = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              mask |= (sv[h * 8 + j] > thr && (full || c0 + h * 8 + j < ncols)) ? (1u << j) : 0u;
-            if (!qvalid) mask = 0;
-            const long long ta0 = clock64();
-            while (mask) {
-              const int j = __ffs(mask) - 1;
-              mask &= mask - 1;
-              buf_s[bcnt * kEpiThreads + et] = pick8(sv + h * 8, j);
-              buf_r[bcnt * kEpiThreads + et] = (uint32_t)(row0 + c0 + h * 8 + j);
-              ++bcnt;
+            for (int j = 0; j < 8; ++j) m = (full || c0 + h * 8 + j < ncols) ? fmaxf(m, sv[h * 8 + j]) : m;
+            if (qvalid && m > thr) {
+              const long long ta0 = tick<DBG>();
+              uint32_t mask = 0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                mask |= (sv[h * 8 + j] > thr && (full || c0 + h * 8 + j < ncols)) ? (1u << j) : 0u;
+              while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                buf_s[bcnt * kEpiThreads + et] = pick8(sv + h * 8, j);
+                buf_r[bcnt * kEpiThreads + et] = (uint32_t)(row0 + c0 + h * 8 + j);
+                ++bcnt;
+              }
+              t_app += tick<DBG>() - ta0;
             }
-            t_app += clock64() - ta0;
             if (__any_sync(0xffffffffu, bcnt >= kBufTrigger)) fold();
           }
         } else if (mode == kModeCount) {
@@ -454,7 +540,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
     }
     flush(cur_qb);
-    if (a.dbg && warp == 2 && lane == 0) { a.dbg[blockIdx.x * 16 + 5] = w_tfull; a.dbg[blockIdx.x * 16 + 6] = t_fold; a.dbg[blockIdx.x * 16 + 7] = clock64() - t_begin; a.dbg[blockIdx.x * 16 + 8] = t_ld; a.dbg[blockIdx.x * 16 + 9] = t_sm; a.dbg[blockIdx.x * 16 + 10] = t_app; }
+    if (DBG && a.dbg && warp == 2 && lane == 0) { a.dbg[blockIdx.x * 16 + 5] = w_tfull; a.dbg[blockIdx.x * 16 + 6] = t_fold; a.dbg[blockIdx.x * 16 + 7] = tick<DBG>() - t_begin; a.dbg[blockIdx.x * 16 + 8] = t_ld; a.dbg[blockIdx.x * 16 + 9] = t_sm; a.dbg[blockIdx.x * 16 + 10] = t_app; }
   }
 
   ptx::tc_fence_before();
@@ -500,15 +586,21 @@ inline int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int D,
   return 0;
 }
 
-template <int K>
-inline int mma_launch_k(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
-                        const MmaPlan& pl, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
+template <int K, bool DBG, bool TS>
+inline int mma_launch_kdt(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
+                          const MmaPlan& pl, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<K, DBG, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "smem attribute: %s", cudaGetErrorString(e)); return 1; }
-  scan_mma_kernel<K><<<pl.ctas, kMmaThreads, pl.smem + 1024, st>>>(mq, m0, m1, ma);
+  scan_mma_kernel<K, DBG, TS><<<pl.ctas, kMmaThreads, pl.smem + 1024, st>>>(mq, m0, m1, ma);
   e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
+}
+template <int K>
+inline int mma_launch_k(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
+                        const MmaPlan& pl, cudaStream_t st) {
+  if (pl.ts) return ma.dbg ? mma_launch_kdt<K, true, true>(mq, m0, m1, ma, pl, st) : mma_launch_kdt<K, false, true>(mq, m0, m1, ma, pl, st);
+  return ma.dbg ? mma_launch_kdt<K, true, false>(mq, m0, m1, ma, pl, st) : mma_launch_kdt<K, false, false>(mq, m0, m1, ma, pl, st);
 }
 
 inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
@@ -520,7 +612,7 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
   MmaArgs ma;
   ma.s = s;
   ma.n_tile = pl.n_tile; ma.n_qb = pl.n_qb; ma.n_t = pl.n_t; ma.stages = pl.stages; ma.kc = pl.kc;
-  ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad;
+  ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.acc_col = pl.acc_col;
   ma.W = (long long)pl.n_qb * pl.n_t;
   ma.dbg = nullptr;
   static const bool debug = getenv("KEMR_MMA_DEBUG") != nullptr;
@@ -545,8 +637,8 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
       cudaMemcpy(h.data(), ma.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
       double avg[16] = {0};
       for (int c = 0; c < pl.ctas; ++c) for (int i = 0; i < 16; ++i) avg[i] += (double)h[(size_t)c * 16 + i] / pl.ctas;
-      fprintf(stderr, "[kemr mma dbg] ctas=%d tiles/cta=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f ld=%.0f score+mask=%.0f append=%.0f cycles\n",
-              pl.ctas, (double)ma.W / pl.ctas, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7], avg[8], avg[9], avg[10]);
+      fprintf(stderr, "[kemr mma dbg] ts=%d n_tile=%d K=%d ctas=%d tiles/cta=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f ld=%.0f score+mask=%.0f append=%.0f cycles\n",
+              pl.ts, pl.n_tile, pl.K, pl.ctas, (double)ma.W / pl.ctas, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7], avg[8], avg[9], avg[10]);
     }
   }
   return rc_launch;

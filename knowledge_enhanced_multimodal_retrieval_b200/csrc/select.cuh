@@ -10,8 +10,9 @@
 namespace kemr {
 
 struct SelectArgs {
-  const uint64_t* part_keys;   // [P][Q][K]
-  int P, Q, K;
+  const uint64_t* part_keys;   // [P][Q][Kp]
+  int P, Q, K;                 // K = candidates re-scored per query
+  int Kp;                      // entries per part list (Kp <= K)
   const uint16_t* q;
   const uint16_t* gal[2];
   int G, D;
@@ -38,12 +39,12 @@ constexpr int kCountMax = 4096;          // up to this many candidate keys are r
 // dynamic smem: keys[max(kSelectWarps*K, min(P*K, kCountMax))] u64 | cand_score[max_cand] f64 |
 //   cand_bonus[max_cand] f64 | cand_row[max_cand] i32 | cand_has[max_cand] u8 (padded) |
 //   qrow[D] bf16 | rows[kSelectWarps][G][D] bf16
-inline size_t select_key_slots(int P, int K) {
-  const size_t all = (size_t)P * K, per_warp = (size_t)kSelectWarps * K;
+inline size_t select_key_slots(int P, int Kp, int K) {
+  const size_t all = (size_t)P * Kp, per_warp = (size_t)kSelectWarps * K;
   return all <= (size_t)kCountMax ? (all > per_warp ? all : per_warp) : per_warp;
 }
-inline size_t select_smem_bytes(int P, int K, int max_cand, int G, int D) {
-  size_t b = select_key_slots(P, K) * 8 + (size_t)max_cand * (8 + 8 + 4);
+inline size_t select_smem_bytes(int P, int Kp, int K, int max_cand, int G, int D) {
+  size_t b = select_key_slots(P, Kp, K) * 8 + (size_t)max_cand * (8 + 8 + 4);
   b += ((size_t)max_cand + 15) & ~(size_t)15;
   b += (size_t)D * 2 + (size_t)kSelectWarps * G * D * 2;
   return (b + 15) & ~(size_t)15;
@@ -61,8 +62,8 @@ __device__ __forceinline__ double canon_dot_smem(const uint16_t* a, const uint16
 
 __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int K = a.K;
-  const int n_all = a.P * K;
+  const int K = a.K, Kp = a.Kp;
+  const int n_all = a.P * Kp;
   const bool by_count = n_all <= kCountMax;
   // carve-up (16-byte aligned pieces first): qrow | rows | keys | cand_score | cand_bonus | cand_row | cand_has
   uint16_t* s_q = reinterpret_cast<uint16_t*>(smem_raw);
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectAr
   unsigned char* cand_has = reinterpret_cast<unsigned char*>(cand_row + a.max_cand);
   __shared__ int s_nsel, s_extra;
   __shared__ uint64_t s_sel[kMaxKSel];
+  __shared__ unsigned long long s_bound;     // largest key any stage rejected (0 = nothing rejected)
 
   const int qi = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -87,9 +89,10 @@ __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectAr
   // ---- A. the K best fp32 candidates over all parts
   if (by_count) {
     for (int i = threadIdx.x; i < K; i += blockDim.x) s_sel[i] = 0;
+    if (threadIdx.x == 0) s_bound = 0;
     for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
-      const int p = i / K, j = i - p * K;
-      lists[i] = a.part_keys[((size_t)p * a.Q + qi) * K + j];
+      const int p = i / Kp, j = i - p * Kp;
+      lists[i] = a.part_keys[((size_t)p * a.Q + qi) * Kp + j];
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
@@ -98,6 +101,8 @@ __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectAr
       int r = 0;
       for (int j = 0; j < n_all; ++j) r += lists[j] > x ? 1 : 0;
       if (r < K) s_sel[r] = x;                            // keys are distinct -> ranks are distinct
+      // rejected here (rank >= K), or last entry of a full part list (the part rejected rows below it)
+      if (r >= K || (i % Kp) == Kp - 1) atomicMax(&s_bound, (unsigned long long)x);
     }
     __syncthreads();
     if (warp == 0) {
@@ -111,15 +116,21 @@ __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectAr
     for (int i = lane; i < K; i += 32) mine[i] = 0;
     __syncwarp();
     uint64_t thr = 0;
+    if (threadIdx.x == 0) s_bound = 0;
+    __syncthreads();
+    unsigned long long bnd = 0;
     for (int p = warp; p < a.P; p += kSelectWarps) {
-      const uint64_t* src = a.part_keys + ((size_t)p * a.Q + qi) * K;
-      for (int i = 0; i < K; ++i) {
+      const uint64_t* src = a.part_keys + ((size_t)p * a.Q + qi) * Kp;
+      const uint64_t last = src[Kp - 1];
+      if (last > bnd) bnd = last;                 // a full part list rejected rows below its last key
+      for (int i = 0; i < Kp; ++i) {
         const uint64_t x = src[i];
-        if (x <= thr) break;                      // lists are sorted: nothing further can enter
+        if (x <= thr) { if (x > bnd) bnd = x; break; }   // sorted: this and the rest are rejected here
         warp_list_insert(mine, K, x, lane);
         thr = mine[K - 1];
       }
     }
+    if (lane == 0 && bnd) atomicMax(&s_bound, bnd);
     __syncthreads();
     if (warp == 0) {
       thr = mine[K - 1];
@@ -132,6 +143,8 @@ __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectAr
           thr = mine[K - 1];
         }
       }
+      // keys displaced from / never admitted to the final list are bounded by its last key
+      if (lane == 0 && mine[K - 1]) atomicMax(&s_bound, (unsigned long long)mine[K - 1]);
       int n = 0;
       for (int i = lane; i < K; i += 32) { s_sel[i] = mine[i]; n += (mine[i] != 0); }
       for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
@@ -214,8 +227,8 @@ __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectAr
   // ---- E. certificate: nothing the scan rejected can reach the k-th canonical score
   if (threadIdx.x == 0) {
     int flag = 0;
-    if (nsel == K) {                            // list full -> rows were rejected
-      const double bound = (double)key_score(sel[K - 1]) + a.eps * (1.0 + 1.0 / 64.0);
+    if (s_bound) {                              // something was rejected on its fp32 score
+      const double bound = (double)key_score((uint64_t)s_bound) + a.eps * (1.0 + 1.0 / 64.0);
       const double reach = a.alpha * bound + 1e-300;
       if (!(n >= a.k && s_kth > reach)) flag = 1;
     }
