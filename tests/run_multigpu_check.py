@@ -1,0 +1,42 @@
+"""Multi-GPU check, launched by torchrun (one rank per GPU, NCCL):
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/run_multigpu_check.py
+Row-sharded gallery search + ranks must equal the single-GPU result bit for bit."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from knowledge_enhanced_multimodal_retrieval_b200 import engine, fusion, synth  # noqa: E402
+from knowledge_enhanced_multimodal_retrieval_b200.distributed import CudaLocal, ShardedGallery, shard_bounds  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    s = synth.make_retrieval_set(Q=500, M=20011, D=768, seed=9, fused=True, lam=0.1, with_kg=True, diagonal=True)
+    lo, hi = shard_bounds(s.M, world, rank)
+    sg = ShardedGallery(CudaLocal(s.image[lo:hi], s.target[lo:hi]), s.M)
+    alpha, hits = fusion.kg_hits_for_strategy(s.kg_results, s.query_uuids, s.uuids, "weighted",
+                                              {"alpha": 0.8, "sparql_weight": 0.2})
+    idx, score = sg.search(s.query, k=10, w_a=0.5, w_b=0.5, alpha=alpha, hits=hits)
+    ranks = sg.rank_targets(s.query, torch.from_numpy(s.target_idx).cuda(), 0.5, 0.5, alpha, hits)
+    # single-GPU reference on every rank
+    q, img, tgt = engine.quantize(s.query), engine.quantize(s.image), engine.quantize(s.target)
+    wi, ws = engine.scan_topk(q, img, tgt, 0.5, 0.5, alpha, hits, k=10)
+    wr = engine.rank_targets(q, img, tgt, torch.from_numpy(s.target_idx).cuda(), 0.5, 0.5, alpha, hits)
+    ok = torch.equal(idx, wi) and torch.equal(score, ws) and torch.equal(ranks, wr)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"multigpu check world={world}: {'OK' if flag.item() else 'MISMATCH'}")
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
