@@ -65,18 +65,84 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Canonical binary64 dot product of two bf16 rows, computed by one full warp; every lane
-// returns the result.  Lane l accumulates d = l, l+32, ... in increasing d (products of two
-// bf16 are exact in binary64), then the 32 partials fold 16,8,4,2,1 -- exactly
-// oracle/oracle.py::canon_dot64.
+// exact bf16 -> binary64 (bf16 -> fp32 is a shift, fp32 -> fp64 is exact incl. subnormals)
+__device__ __forceinline__ double bf16_to_f64(uint32_t b16) { return (double)__uint_as_float(b16 << 16); }
+__device__ __forceinline__ double bf16hi_to_f64(uint32_t packed) { return (double)__uint_as_float(packed & 0xffff0000u); }
+
+// Canonical binary64 dot product (oracle/oracle.py::canon_dot64): the row is cut into 16-byte
+// pieces of 8 bf16; lane l owns pieces l, l+32, ... (exactly what it fetches with coalesced
+// 16-byte loads) and keeps one running sum per element position of its pieces (products of two
+// bf16 are exact in binary64), combines the 8 sums with a fixed tree, and the 32 lanes then fold
+// 16,8,4,2,1.  NP = pieces per lane = ceil(D/256).
+constexpr int kCanonPieces = 4;
+
+// raw 16-byte pieces of one row owned by this lane
+template <int NP>
+struct CanonRow {
+  uint4 x[NP];
+  __device__ __forceinline__ void load(const uint16_t* __restrict__ g, int D, int lane) {
+    const int npiece = D >> 3;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const int c = lane + 32 * j;
+      x[j] = (c < npiece) ? ldg_stream(g + (size_t)c * 8) : make_uint4(0, 0, 0, 0);
+    }
+  }
+};
+
+// the lane's share of a query row, widened to binary64 once and reused for many gallery rows
+template <int NP>
+struct CanonQueryT {
+  double v[NP][8];
+  __device__ __forceinline__ void load(const uint16_t* __restrict__ q, int D, int lane) {
+    const int npiece = D >> 3;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const int c = lane + 32 * j;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (c < npiece) x = *reinterpret_cast<const uint4*>(q + (size_t)c * 8);
+      v[j][0] = bf16_to_f64(x.x & 0xffffu); v[j][1] = bf16hi_to_f64(x.x);
+      v[j][2] = bf16_to_f64(x.y & 0xffffu); v[j][3] = bf16hi_to_f64(x.y);
+      v[j][4] = bf16_to_f64(x.z & 0xffffu); v[j][5] = bf16hi_to_f64(x.z);
+      v[j][6] = bf16_to_f64(x.w & 0xffffu); v[j][7] = bf16hi_to_f64(x.w);
+    }
+  }
+  // every lane returns the canonical dot with an already-fetched row: 8 independent running sums
+  // per lane (one per element of its 16-byte pieces, pieces in increasing order), an 8-to-1 tree,
+  // then the 32 lanes fold 16,8,4,2,1
+  __device__ __forceinline__ double dot(const CanonRow<NP>& r, int D, int lane) const {
+    const int npiece = D >> 3;
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0, p5 = 0.0, p6 = 0.0, p7 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      if (lane + 32 * j < npiece) {
+        const uint4 x = r.x[j];
+        p0 = fma(v[j][0], bf16_to_f64(x.x & 0xffffu), p0); p1 = fma(v[j][1], bf16hi_to_f64(x.x), p1);
+        p2 = fma(v[j][2], bf16_to_f64(x.y & 0xffffu), p2); p3 = fma(v[j][3], bf16hi_to_f64(x.y), p3);
+        p4 = fma(v[j][4], bf16_to_f64(x.z & 0xffffu), p4); p5 = fma(v[j][5], bf16hi_to_f64(x.z), p5);
+        p6 = fma(v[j][6], bf16_to_f64(x.w & 0xffffu), p6); p7 = fma(v[j][7], bf16hi_to_f64(x.w), p7);
+      }
+    }
+    double acc = __dadd_rn(__dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3)), __dadd_rn(__dadd_rn(p4, p5), __dadd_rn(p6, p7)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, o));
+    return __shfl_sync(0xffffffffu, acc, 0);
+  }
+};
+using CanonQuery = CanonQueryT<kCanonPieces>;
+
+__device__ __forceinline__ double canon_dot_q(const CanonQuery& cq, const uint16_t* __restrict__ g, int D, int lane) {
+  CanonRow<kCanonPieces> r;
+  r.load(g, D, lane);
+  return cq.dot(r, D, lane);
+}
+
+// convenience: one-off pair
 __device__ __forceinline__ double canon_dot_warp(const uint16_t* __restrict__ a,
                                                  const uint16_t* __restrict__ b, int D, int lane) {
-  double acc = 0.0;
-  for (int d = lane; d < D; d += 32)
-    acc = fma((double)bf16_to_f32(a[d]), (double)bf16_to_f32(b[d]), acc);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, o));
-  return __shfl_sync(0xffffffffu, acc, 0);
+  CanonQuery cq;
+  cq.load(a, D, lane);
+  return canon_dot_q(cq, b, D, lane);
 }
 
 // final = fl(fl(alpha * fl(fl(w_a*S_a) + fl(w_b*S_b))) + bonus); no contraction allowed.

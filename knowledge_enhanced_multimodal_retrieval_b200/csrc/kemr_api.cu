@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -129,6 +130,11 @@ static int check_common(const void* q, int Q, const void* ga, int64_t M, int D) 
 static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, const DevInfo& dv, ScanPlan* pl) {
   pl->path = path;
   if (path == KEMR_PATH_AUTO) {
+    static const char* force = getenv("KEMR_FORCE_PATH");     // experiments: 1 = warp-dot, 2 = tcgen05
+    if (force && (force[0] == '1' || force[0] == '2')) path = force[0] - '0';
+    pl->path = path;
+  }
+  if (path == KEMR_PATH_AUTO) {
     // tensor-core kernel when there is a batch to amortise its prologue; warp-dot for the
     // latency-bound tiny batches
     pl->path = (dv.major == 10 && Q >= 5 && mma_supported(D, K)) ? KEMR_PATH_MMA : KEMR_PATH_WARP;
@@ -231,7 +237,20 @@ extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, c
   s.k = k; s.eps = eps; s.idx_base = idx_base;
   s.out_score64 = out_score64; s.out_score32 = out_score32; s.out_idx = out_idx; s.out_flags = out_flags;
   s.max_cand = k_sel + (int)max_hits_per_query;
+  if (select_warp_ok(pl.P, pl.Kp, k_sel, s.max_cand)) {
+    const dim3 grid((Q + kSelWarpWarps - 1) / kSelWarpWarps), block(kSelWarpWarps * 32);
+    switch ((D + 255) / 256) {
+      case 1: select_warp_kernel<1><<<grid, block, 0, st>>>(s, Q); break;
+      case 2: select_warp_kernel<2><<<grid, block, 0, st>>>(s, Q); break;
+      case 3: select_warp_kernel<3><<<grid, block, 0, st>>>(s, Q); break;
+      default: select_warp_kernel<4><<<grid, block, 0, st>>>(s, Q); break;
+    }
+    LAUNCH_CHECK("select_warp_kernel");
+    return KEMR_OK;
+  }
+  if (pl.P > kMaxParts) return fail(KEMR_ERR_UNSUPPORTED, "too many part lists per query (%d)", pl.P);
   const size_t smem = select_smem_bytes(pl.P, pl.Kp, k_sel, s.max_cand, G, D);
+  if (smem > 200 * 1024) return fail(KEMR_ERR_UNSUPPORTED, "select kernel needs %zu bytes of shared memory", smem);
   if (smem > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   select_rescore_kernel<<<Q, kSelectThreads, smem, st>>>(s);

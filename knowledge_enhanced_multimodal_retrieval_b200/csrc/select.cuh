@@ -34,93 +34,87 @@ struct SelectArgs {
 
 constexpr int kSelectThreads = 256;
 constexpr int kSelectWarps = kSelectThreads / 32;
-constexpr int kCountMax = 4096;          // up to this many candidate keys are ranked by counting
+constexpr int kCountMax = 1024;          // up to this many gathered keys are ranked by counting
+constexpr int kMaxParts = 4096;          // part lists per query the head pass can hold
 
-// dynamic smem: keys[max(kSelectWarps*K, min(P*K, kCountMax))] u64 | cand_score[max_cand] f64 |
-//   cand_bonus[max_cand] f64 | cand_row[max_cand] i32 | cand_has[max_cand] u8 (padded) |
-//   qrow[D] bf16 | rows[kSelectWarps][G][D] bf16
-inline size_t select_key_slots(int P, int Kp, int K) {
-  const size_t all = (size_t)P * Kp, per_warp = (size_t)kSelectWarps * K;
-  return all <= (size_t)kCountMax ? (all > per_warp ? all : per_warp) : per_warp;
+// dynamic smem (16-byte aligned pieces first):
+//   heads[P] u64 | keys[max(K*Kp, kSelectWarps*K)] u64 |
+//   cand_score[max_cand] f64 | cand_bonus[max_cand] f64 | cand_row[max_cand] i32 | cand_has[max_cand] u8
+inline size_t select_key_slots(int Kp, int K) {
+  const size_t gathered = (size_t)K * Kp, per_warp = (size_t)kSelectWarps * K;
+  return gathered > per_warp ? gathered : per_warp;
 }
 inline size_t select_smem_bytes(int P, int Kp, int K, int max_cand, int G, int D) {
-  size_t b = select_key_slots(P, Kp, K) * 8 + (size_t)max_cand * (8 + 8 + 4);
+  (void)G; (void)D;
+  size_t b = (size_t)P * 8 + select_key_slots(Kp, K) * 8 + (size_t)max_cand * (8 + 8 + 4);
   b += ((size_t)max_cand + 15) & ~(size_t)15;
-  b += (size_t)D * 2 + (size_t)kSelectWarps * G * D * 2;
   return (b + 15) & ~(size_t)15;
-}
-
-// canonical dot from rows staged in shared memory (same order as common.cuh::canon_dot_warp)
-__device__ __forceinline__ double canon_dot_smem(const uint16_t* a, const uint16_t* b, int D, int lane) {
-  double acc = 0.0;
-  for (int d = lane; d < D; d += 32)
-    acc = fma((double)bf16_to_f32(a[d]), (double)bf16_to_f32(b[d]), acc);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, o));
-  return __shfl_sync(0xffffffffu, acc, 0);
 }
 
 __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int K = a.K, Kp = a.Kp;
-  const int n_all = a.P * Kp;
-  const bool by_count = n_all <= kCountMax;
-  // carve-up (16-byte aligned pieces first): qrow | rows | keys | cand_score | cand_bonus | cand_row | cand_has
-  uint16_t* s_q = reinterpret_cast<uint16_t*>(smem_raw);
-  uint16_t* s_rows = s_q + a.D;
-  uint64_t* lists = reinterpret_cast<uint64_t*>(s_rows + (size_t)kSelectWarps * a.G * a.D);
-  const size_t per_warp = (size_t)kSelectWarps * K;
-  const size_t key_slots = by_count ? ((size_t)n_all > per_warp ? (size_t)n_all : per_warp) : per_warp;
-  double* cand_score = reinterpret_cast<double*>(lists + key_slots);
+  const int K = a.K, Kp = a.Kp, P = a.P;
+  uint64_t* heads = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* lists = heads + P;
+  const size_t gathered = (size_t)K * Kp, per_warp = (size_t)kSelectWarps * K;
+  double* cand_score = reinterpret_cast<double*>(lists + (gathered > per_warp ? gathered : per_warp));
   double* cand_bonus = cand_score + a.max_cand;
   int32_t* cand_row = reinterpret_cast<int32_t*>(cand_bonus + a.max_cand);
   unsigned char* cand_has = reinterpret_cast<unsigned char*>(cand_row + a.max_cand);
-  __shared__ int s_nsel, s_extra;
+  __shared__ int s_nsel, s_extra, s_nlist;
   __shared__ uint64_t s_sel[kMaxKSel];
+  __shared__ int s_listid[kMaxKSel];
   __shared__ unsigned long long s_bound;     // largest key any stage rejected (0 = nothing rejected)
 
   const int qi = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // stage the query row (coalesced 16-byte loads)
-  for (int c = threadIdx.x; c < (a.D >> 3); c += blockDim.x)
-    reinterpret_cast<uint4*>(s_q)[c] = reinterpret_cast<const uint4*>(a.q + (size_t)qi * a.D)[c];
+  // this lane's share of the query row, widened to binary64 once
+  CanonQuery cq;
+  cq.load(a.q + (size_t)qi * a.D, a.D, lane);
 
-  // ---- A. the K best fp32 candidates over all parts
-  if (by_count) {
-    for (int i = threadIdx.x; i < K; i += blockDim.x) s_sel[i] = 0;
-    if (threadIdx.x == 0) s_bound = 0;
-    for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
-      const int p = i / Kp, j = i - p * Kp;
-      lists[i] = a.part_keys[((size_t)p * a.Q + qi) * Kp + j];
+  // ---- A1. heads of all part lists; only the K lists with the largest heads can hold a top-K key
+  for (int i = threadIdx.x; i < K; i += blockDim.x) { s_sel[i] = 0; s_listid[i] = -1; }
+  if (threadIdx.x == 0) { s_bound = 0; s_nlist = 0; s_extra = 0; }
+  for (int p = threadIdx.x; p < P; p += blockDim.x) heads[p] = a.part_keys[((size_t)p * a.Q + qi) * Kp];
+  __syncthreads();
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const uint64_t x = heads[p];
+    if (!x) continue;
+    int r = 0;
+    for (int j = 0; j < P; ++j) r += heads[j] > x ? 1 : 0;
+    if (r < K) { s_listid[r] = p; atomicAdd(&s_nlist, 1); }
+    else atomicMax(&s_bound, (unsigned long long)x);       // whole list rejected: nothing in it beats its head
+  }
+  __syncthreads();
+  const int nlist = s_nlist;                                // selected lists occupy s_listid[0..nlist)
+
+  // ---- A2. the K best keys among the selected lists
+  const int n2 = nlist * Kp;
+  if (n2 <= kCountMax) {
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      const int l = i / Kp, j = i - l * Kp;
+      lists[i] = a.part_keys[((size_t)s_listid[l] * a.Q + qi) * Kp + j];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
       const uint64_t x = lists[i];
       if (!x) continue;
       int r = 0;
-      for (int j = 0; j < n_all; ++j) r += lists[j] > x ? 1 : 0;
-      if (r < K) s_sel[r] = x;                            // keys are distinct -> ranks are distinct
-      // rejected here (rank >= K), or last entry of a full part list (the part rejected rows below it)
+      for (int j = 0; j < n2; ++j) r += lists[j] > x ? 1 : 0;
+      if (r < K) s_sel[r] = x;                              // keys are distinct -> ranks are distinct
+      // rejected here, or last entry of a full part list (that part rejected rows below it)
       if (r >= K || (i % Kp) == Kp - 1) atomicMax(&s_bound, (unsigned long long)x);
     }
     __syncthreads();
-    if (warp == 0) {
-      int n = 0;
-      for (int i = lane; i < K; i += 32) n += (s_sel[i] != 0);
-      for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-      if (lane == 0) { s_nsel = n; s_extra = 0; }
-    }
   } else {
     uint64_t* mine = lists + (size_t)warp * K;
     for (int i = lane; i < K; i += 32) mine[i] = 0;
     __syncwarp();
     uint64_t thr = 0;
-    if (threadIdx.x == 0) s_bound = 0;
-    __syncthreads();
     unsigned long long bnd = 0;
-    for (int p = warp; p < a.P; p += kSelectWarps) {
-      const uint64_t* src = a.part_keys + ((size_t)p * a.Q + qi) * Kp;
+    for (int l = warp; l < nlist; l += kSelectWarps) {
+      const uint64_t* src = a.part_keys + ((size_t)s_listid[l] * a.Q + qi) * Kp;
       const uint64_t last = src[Kp - 1];
       if (last > bnd) bnd = last;                 // a full part list rejected rows below its last key
       for (int i = 0; i < Kp; ++i) {
@@ -138,18 +132,22 @@ __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectAr
         const uint64_t* other = lists + (size_t)w2 * K;
         for (int i = 0; i < K; ++i) {
           const uint64_t x = other[i];
-          if (x <= thr) break;
+          if (x <= thr) { if (lane == 0 && x) atomicMax(&s_bound, (unsigned long long)x); break; }
           warp_list_insert(mine, K, x, lane);
           thr = mine[K - 1];
         }
       }
-      // keys displaced from / never admitted to the final list are bounded by its last key
+      // keys displaced from the final list are bounded by its last key
       if (lane == 0 && mine[K - 1]) atomicMax(&s_bound, (unsigned long long)mine[K - 1]);
-      int n = 0;
-      for (int i = lane; i < K; i += 32) { s_sel[i] = mine[i]; n += (mine[i] != 0); }
-      for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-      if (lane == 0) { s_nsel = n; s_extra = 0; }
+      for (int i = lane; i < K; i += 32) s_sel[i] = mine[i];
     }
+    __syncthreads();
+  }
+  if (warp == 0) {
+    int n = 0;
+    for (int i = lane; i < K; i += 32) n += (s_sel[i] != 0);
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) s_nsel = n;
   }
   __syncthreads();
   const int nsel = s_nsel;
@@ -181,21 +179,13 @@ __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectAr
   __syncthreads();
   const int n = min(nsel + s_extra, a.max_cand);
 
-  // ---- C. canonical re-scoring, one warp per candidate; rows are fetched with coalesced
-  //         16-byte loads into shared memory, then accumulated in the canonical lane order
-  uint16_t* my_rows = s_rows + (size_t)warp * a.G * a.D;
-  const int nchunk = a.D >> 3;
+  // ---- C. canonical re-scoring, one warp per candidate, straight from coalesced 16-byte loads
   for (int c = warp; c < n; c += kSelectWarps) {
     const size_t off = (size_t)cand_row[c] * a.D;
-    for (int g = 0; g < a.G; ++g)
-      for (int ch = lane; ch < nchunk; ch += 32)
-        reinterpret_cast<uint4*>(my_rows + (size_t)g * a.D)[ch] = ldg_stream(a.gal[g] + off + ch * 8);
-    __syncwarp();
-    const double sa = canon_dot_smem(s_q, my_rows, a.D, lane);
-    const double sb = a.G > 1 ? canon_dot_smem(s_q, my_rows + a.D, a.D, lane) : 0.0;
+    const double sa = canon_dot_q(cq, a.gal[0] + off, a.D, lane);
+    const double sb = a.G > 1 ? canon_dot_q(cq, a.gal[1] + off, a.D, lane) : 0.0;
     if (lane == 0)
       cand_score[c] = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, cand_bonus[c], cand_has[c] != 0);
-    __syncwarp();
   }
   __syncthreads();
 
@@ -231,6 +221,170 @@ __global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectAr
       const double bound = (double)key_score((uint64_t)s_bound) + a.eps * (1.0 + 1.0 / 64.0);
       const double reach = a.alpha * bound + 1e-300;
       if (!(n >= a.k && s_kth > reach)) flag = 1;
+    }
+    a.out_flags[qi] = flag;
+  }
+}
+
+// ------------------------------------------------------------------ fast path: one WARP per query
+// Same contract as select_rescore_kernel for the common small case (few parts, short lists, at
+// most 64 candidates): no block barriers, 4 independent queries per CTA, so a 1000-query batch
+// fits the GPU in a single wave and the re-scoring loads of different queries overlap.
+constexpr int kSelWarpWarps = 4;
+constexpr int kSelWarpMaxP = 64;
+constexpr int kSelWarpMaxKeys = 256;
+constexpr int kSelWarpMaxCand = 64;
+
+inline bool select_warp_ok(int P, int Kp, int K, int max_cand) {
+  const int nl = P < K ? P : K;
+  return P <= kSelWarpMaxP && K <= 32 && nl * Kp <= kSelWarpMaxKeys && max_cand <= kSelWarpMaxCand;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(kSelWarpWarps * 32) select_warp_kernel(SelectArgs a, int nq) {
+  __shared__ uint64_t s_heads[kSelWarpWarps][kSelWarpMaxP];
+  __shared__ uint64_t s_keys[kSelWarpWarps][kSelWarpMaxKeys];
+  __shared__ uint64_t s_selk[kSelWarpWarps][32];
+  __shared__ int s_lid[kSelWarpWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qi = blockIdx.x * kSelWarpWarps + warp;
+  if (qi >= nq) return;
+  const int K = a.K, Kp = a.Kp, P = a.P;
+  uint64_t* heads = s_heads[warp];
+  uint64_t* keys = s_keys[warp];
+  uint64_t* selk = s_selk[warp];
+  int* lid = s_lid[warp];
+  unsigned long long bound = 0;                    // per-lane partial, max-reduced at the end
+
+  CanonQueryT<NP> cq;
+  cq.load(a.q + (size_t)qi * a.D, a.D, lane);
+
+  // A1. heads of the part lists -> the (at most K) lists that can hold a top-K key
+  for (int p = lane; p < P; p += 32) heads[p] = a.part_keys[((size_t)p * a.Q + qi) * Kp];
+  selk[lane] = 0; lid[lane] = -1;
+  __syncwarp();
+  int nlist = 0;
+  for (int p = lane; p < P; p += 32) {
+    const uint64_t x = heads[p];
+    if (!x) continue;
+    int r = 0;
+    for (int j = 0; j < P; ++j) r += heads[j] > x ? 1 : 0;
+    if (r < K) { lid[r] = p; ++nlist; }
+    else if (x > bound) bound = x;
+  }
+  for (int o = 16; o > 0; o >>= 1) nlist += __shfl_xor_sync(0xffffffffu, nlist, o);
+  __syncwarp();
+
+  // A2. K best keys among the selected lists
+  const int n2 = nlist * Kp;
+  for (int i = lane; i < n2; i += 32) {
+    const int l = i / Kp, j = i - l * Kp;
+    keys[i] = a.part_keys[((size_t)lid[l] * a.Q + qi) * Kp + j];
+  }
+  __syncwarp();
+  for (int i = lane; i < n2; i += 32) {
+    const uint64_t x = keys[i];
+    if (!x) continue;
+    int r = 0;
+    for (int j = 0; j < n2; ++j) r += keys[j] > x ? 1 : 0;
+    if (r < K) selk[r] = x;
+    if ((r >= K || (i % Kp) == Kp - 1) && x > bound) bound = x;
+  }
+  __syncwarp();
+  const uint64_t mykey = selk[lane];                // lane i <-> candidate i (K <= 32)
+  const int nsel = __popc(__ballot_sync(0xffffffffu, mykey != 0));
+
+  // B. candidates: lane holds candidate `lane` and (KG hits) candidate `32+lane`
+  int32_t row0 = mykey ? (int32_t)key_row(mykey) : -1, row1 = -1;
+  double bon0 = 0.0, bon1 = 0.0;
+  bool has0 = false, has1 = false;
+  int n = nsel;
+  if (a.hit_rowptr) {
+    const int64_t h0 = a.hit_rowptr[qi], h1 = a.hit_rowptr[qi + 1];
+    for (int64_t h = h0; h < h1; ++h) {             // few dozen hits: walk them warp-uniformly
+      const int32_t col = a.hit_col[h];
+      if (col < 0 || (int64_t)col >= a.M) continue;
+      const double b = a.hit_bonus[h];
+      const unsigned m0 = __ballot_sync(0xffffffffu, row0 == col);
+      const unsigned m1 = __ballot_sync(0xffffffffu, row1 == col);
+      if (m0) { if (row0 == col) { bon0 = b; has0 = true; } }
+      else if (m1) { if (row1 == col) { bon1 = b; has1 = true; } }
+      else if (n < kSelWarpMaxCand) {
+        if (n < 32) { if (lane == n) { row0 = col; bon0 = b; has0 = true; } }
+        else if (lane == n - 32) { row1 = col; bon1 = b; has1 = true; }
+        ++n;
+      }
+    }
+  }
+
+  // C. canonical re-scoring; the whole warp works on one candidate at a time, and the rows of
+  //    candidate c+1 (both galleries) are already in flight while candidate c is accumulated
+  double sc0 = 0.0, sc1 = 0.0;
+  CanonRow<NP> cur[2], nxt[2];
+  if (n > 0) {
+    const size_t off = (size_t)__shfl_sync(0xffffffffu, row0, 0) * a.D;
+    cur[0].load(a.gal[0] + off, a.D, lane);
+    if (a.G > 1) cur[1].load(a.gal[1] + off, a.D, lane);
+  }
+  for (int c = 0; c < n; ++c) {
+    if (c + 1 < n) {
+      const int32_t rown = __shfl_sync(0xffffffffu, c + 1 < 32 ? row0 : row1, (c + 1) & 31);
+      const size_t off = (size_t)rown * a.D;
+      nxt[0].load(a.gal[0] + off, a.D, lane);
+      if (a.G > 1) nxt[1].load(a.gal[1] + off, a.D, lane);
+    }
+    const double sa = cq.dot(cur[0], a.D, lane);
+    const double sb = a.G > 1 ? cq.dot(cur[1], a.D, lane) : 0.0;
+    if (lane == (c & 31)) {
+      if (c < 32) sc0 = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, bon0, has0);
+      else sc1 = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, bon1, has1);
+    }
+    cur[0] = nxt[0];
+    cur[1] = nxt[1];
+  }
+
+  // D. order by (score desc, row asc) by counting over shuffled copies; write the first k
+  int r0 = 0, r1 = 0;
+  for (int j = 0; j < n; ++j) {
+    const double sj = __shfl_sync(0xffffffffu, j < 32 ? sc0 : sc1, j & 31);
+    const int32_t rj = __shfl_sync(0xffffffffu, j < 32 ? row0 : row1, j & 31);
+    r0 += ahead64(sj, rj, sc0, row0) ? 1 : 0;
+    r1 += ahead64(sj, rj, sc1, row1) ? 1 : 0;
+  }
+  double kth = -INFINITY;
+  if (lane < n && r0 < a.k) {
+    const size_t o = (size_t)qi * a.k + r0;
+    a.out_score64[o] = sc0;
+    if (a.out_score32) a.out_score32[o] = (float)sc0;
+    a.out_idx[o] = a.idx_base + row0;
+    if (r0 == a.k - 1) kth = sc0;
+  }
+  if (32 + lane < n && r1 < a.k) {
+    const size_t o = (size_t)qi * a.k + r1;
+    a.out_score64[o] = sc1;
+    if (a.out_score32) a.out_score32[o] = (float)sc1;
+    a.out_idx[o] = a.idx_base + row1;
+    if (r1 == a.k - 1) kth = sc1;
+  }
+  for (int r = n + lane; r < a.k; r += 32) {
+    const size_t o = (size_t)qi * a.k + r;
+    a.out_score64[o] = -INFINITY;
+    if (a.out_score32) a.out_score32[o] = -INFINITY;
+    a.out_idx[o] = -1;
+  }
+
+  // E. certificate
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bound, o);
+    bound = ob > bound ? ob : bound;
+    kth = fmax(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+  }
+  if (lane == 0) {
+    int flag = 0;
+    if (bound) {
+      const double b = (double)key_score((uint64_t)bound) + a.eps * (1.0 + 1.0 / 64.0);
+      const double reach = a.alpha * b + 1e-300;
+      if (!(n >= a.k && kth > reach)) flag = 1;
     }
     a.out_flags[qi] = flag;
   }

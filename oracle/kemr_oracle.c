@@ -4,8 +4,8 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline leg -- never by the product package.
  *
  * It restates, for sizes numpy cannot cover in seconds, what oracle/oracle.py defines:
- *   score   = sum_d q[d]*g[d] in binary64, 32 interleaved partial sums (element d -> partial
- *             d mod 32, increasing d) folded 16,8,4,2,1            (oracle.py::canon_dot64)
+ *   score   = sum_d q[d]*g[d] in binary64: 256 running sums (d mod 256, increasing d), 8-to-1 tree
+ *             per 16-byte piece, 32 pieces folded 16,8,4,2,1       (oracle.py::canon_dot64)
  *   clip    = fl(fl(w_a*S_a) + fl(w_b*S_b)); final = fl(fl(alpha*clip) + bonus)  (canon_fused64)
  *   ranking = final descending, ties by lowest index                 (canon_topk / canon_rank)
  * which in turn pins the reference's similarity + fusion + argsort path
@@ -24,17 +24,24 @@ static inline double bf16_to_f64(uint16_t b) {
   return (double)f;
 }
 
-/* canonical dot of one query (already widened to double, padded to Dp) with one bf16 row */
+/* canonical dot of one query (already widened to double) with one bf16 row: 256 running sums
+ * (position inside a 256-element block, blocks in increasing order), 8-to-1 tree per 16-byte piece,
+ * then the 32 pieces fold 16,8,4,2,1 */
 static inline double canon_dot(const double* q, const uint16_t* g, int D) {
-  double acc[32];
-  for (int l = 0; l < 32; ++l) acc[l] = 0.0;
-  int d = 0;
-  for (; d + 32 <= D; d += 32)
-    for (int l = 0; l < 32; ++l) acc[l] += q[d + l] * bf16_to_f64(g[d + l]);   /* product exact in binary64 */
-  for (int l = 0; d + l < D; ++l) acc[l] += q[d + l] * bf16_to_f64(g[d + l]);
+  double acc[256];
+  for (int r = 0; r < 256; ++r) acc[r] = 0.0;
+  for (int d0 = 0; d0 < D; d0 += 256) {
+    const int n = D - d0 < 256 ? D - d0 : 256;
+    for (int r = 0; r < n; ++r) acc[r] += q[d0 + r] * bf16_to_f64(g[d0 + r]);   /* product exact in binary64 */
+  }
+  double lane[32];
+  for (int l = 0; l < 32; ++l) {
+    const double* a = acc + 8 * l;
+    lane[l] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  }
   for (int off = 16; off >= 1; off >>= 1)
-    for (int l = 0; l < off; ++l) acc[l] = acc[l] + acc[l + off];
-  return acc[0];
+    for (int l = 0; l < off; ++l) lane[l] = lane[l] + lane[l + off];
+  return lane[0];
 }
 
 static inline double fuse(double sa, double sb, int two, double wa, double wb, double alpha) {

@@ -18,9 +18,10 @@ Two layers, both numpy:
    BLAS sgemm (`metrics.py:102`) and the tie order of numpy's non-stable argsort
    (`metrics.py:34,62`).  The canonical oracle fixes both:
      * score: products of two bf16 values are exact in binary64; they are accumulated in
-       binary64 in a fixed order -- 32 interleaved partial sums (element d goes to partial
-       d mod 32, added in increasing d) followed by a fixed halving tree
-       (16,8,4,2,1) -- which is the order a 32-lane warp uses;
+       binary64 in a fixed order -- 256 running sums (one per position inside a 256-element
+       block, blocks in increasing order), an 8-to-1 tree inside every 16-byte piece, then a
+       fixed halving tree (16,8,4,2,1) over the 32 pieces -- which is the order a 32-lane
+       warp doing coalesced 16-byte loads uses;
      * fusion: ``fl(fl(w_a*S_a) + fl(w_b*S_b))`` then ``fl(fl(alpha*clip) + bonus)`` in
        binary64 with the python-float weights taken as doubles;
      * ranking: descending score, ties broken by the lowest gallery index (what a stable
@@ -233,28 +234,35 @@ def ref_threshold_filter(items: List[dict], threshold: float = 0) -> List[dict]:
 def canon_dot64(query: np.ndarray, gallery: np.ndarray) -> np.ndarray:
     """Canonical binary64 scores, shape (Q, M).  Inputs hold bf16-representable values.
 
-    Partial l accumulates elements d = l, l+32, l+64, ... in increasing d (each product of
-    two bf16 values is exact in binary64, so add-after-multiply equals a fused multiply-add);
-    the 32 partials are then folded 16, 8, 4, 2, 1.
+    The row is zero-padded to a multiple of 256 elements.  256 running sums, one per position r
+    inside a 256-element block, each add their products block after block (a product of two bf16
+    values is exact in binary64, so add-after-multiply equals a fused multiply-add).  The 8 sums of
+    one 16-byte piece (r = 8l .. 8l+7) are combined as ((0+1)+(2+3))+((4+5)+(6+7)), and the 32
+    piece sums are folded 16, 8, 4, 2, 1 -- a warp doing coalesced 16-byte loads, lane l owning
+    piece l of every block.
     """
     q = np.asarray(query, dtype=np.float64)
     g = np.asarray(gallery, dtype=np.float64)
     Q, D = q.shape
     M = g.shape[0]
-    Dp = (D + 31) // 32 * 32
+    Dp = (D + 255) // 256 * 256
     if Dp != D:
         q = np.pad(q, ((0, 0), (0, Dp - D)))
         g = np.pad(g, ((0, 0), (0, Dp - D)))
+    J = Dp // 256
     out = np.empty((Q, M), dtype=np.float64)
-    g3 = g.reshape(M, Dp // 32, 32)
+    g3 = g.reshape(M, J, 256)
     for i in range(Q):
-        q3 = q[i].reshape(Dp // 32, 32)
-        acc = np.zeros((M, 32), dtype=np.float64)
-        for t in range(Dp // 32):
-            acc += g3[:, t, :] * q3[t][None, :]
+        q3 = q[i].reshape(J, 256)
+        acc = np.zeros((M, 256), dtype=np.float64)
+        for j in range(J):
+            acc += g3[:, j, :] * q3[j][None, :]
+        a = acc.reshape(M, 32, 8)
+        lane = ((a[:, :, 0] + a[:, :, 1]) + (a[:, :, 2] + a[:, :, 3])) + \
+               ((a[:, :, 4] + a[:, :, 5]) + (a[:, :, 6] + a[:, :, 7]))
         for off in (16, 8, 4, 2, 1):
-            acc = acc[:, :off] + acc[:, off:2 * off]
-        out[i] = acc[:, 0]
+            lane = lane[:, :off] + lane[:, off:2 * off]
+        out[i] = lane[:, 0]
     return out
 
 

@@ -97,20 +97,23 @@ def test_ref_and_canonical_mid(golden):
 
 def test_canonical_order_is_what_it_says():
     rng = np.random.default_rng(0)
-    q = synth.round_to_bf16(rng.standard_normal((3, 80), dtype=np.float32))
-    g = synth.round_to_bf16(rng.standard_normal((5, 80), dtype=np.float32))
-    got = O.canon_dot64(q, g)
-    for i in range(3):
-        for j in range(5):
-            part = [0.0] * 32
-            for d in range(80):
-                part[d % 32] += float(q[i, d]) * float(g[j, d])
-            n = 32
-            while n > 1:
-                n //= 2
-                part = [part[l] + part[l + n] for l in range(n)]
-            assert got[i, j] == part[0]
-    assert np.allclose(got, q.astype(np.float64) @ g.astype(np.float64).T, rtol=0, atol=1e-12)
+    for D in (80, 264, 520):
+        q = synth.round_to_bf16(rng.standard_normal((3, D), dtype=np.float32))
+        g = synth.round_to_bf16(rng.standard_normal((5, D), dtype=np.float32))
+        got = O.canon_dot64(q, g)
+        for i in range(3):
+            for j in range(5):
+                run = [0.0] * 256                          # one running sum per position in a 256-block
+                for d in range(D):
+                    run[d % 256] += float(q[i, d]) * float(g[j, d])
+                part = [((run[8 * l] + run[8 * l + 1]) + (run[8 * l + 2] + run[8 * l + 3])) +
+                        ((run[8 * l + 4] + run[8 * l + 5]) + (run[8 * l + 6] + run[8 * l + 7])) for l in range(32)]
+                n = 32
+                while n > 1:
+                    n //= 2
+                    part = [part[l] + part[l + n] for l in range(n)]
+                assert got[i, j] == part[0]
+        assert np.allclose(got, q.astype(np.float64) @ g.astype(np.float64).T, rtol=0, atol=1e-12)
 
 
 def test_canon_topk_and_rank_ties_nan():
