@@ -244,8 +244,11 @@ def run_ours(args, cfg):
                          None if not cfg["fused"] else (synth.f32_to_bf16_bits(host_sets.target) if host_sets
                                                         else tgt.view(torch.int16).cpu().numpy().view(np.uint16)),
                          max_queries=Q, max_k=k)
-    out = (np.empty((Q, k), np.int64), np.empty((Q, k), np.float64), np.empty((Q,), np.int32))
-    qh = np.ascontiguousarray(q_host, dtype=np.float32)
+    # step inputs/outputs live in page-locked host memory (used in place by the C call)
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    out = (pin((Q, k), torch.int64), pin((Q, k), torch.float64), pin((Q,), torch.int32))
+    qh = pin((Q, D), torch.float32)
+    qh[:] = np.ascontiguousarray(q_host, dtype=np.float32)
     for _ in range(3):
         hi.search(qh, k=k, t2i_weight=wi, t2t_weight=wt, out=out)
     if world > 1:

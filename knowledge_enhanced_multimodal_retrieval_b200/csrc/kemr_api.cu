@@ -534,8 +534,16 @@ extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int
   if (Q <= 0 || Q > ix->max_q || k <= 0 || k > ix->max_k) return fail(KEMR_ERR_ARG, "index_search_host: Q or k beyond the handle's limits");
   cudaStream_t st = ix->stream;
   const size_t qbytes = (size_t)Q * ix->D * 4;
-  memcpy(ix->h_q, q_host, qbytes);
-  CUDA_TRY(cudaMemcpyAsync(ix->d_qf32, ix->h_q, qbytes, cudaMemcpyHostToDevice, st));
+  // page-locked caller buffers are used in place; pageable ones are staged through pinned memory
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const bool q_pinned = is_pinned(q_host);
+  const bool out_pinned = is_pinned(out_idx_host) && is_pinned(out_score64_host) && (!out_flags_host || is_pinned(out_flags_host));
+  if (!q_pinned) memcpy(ix->h_q, q_host, qbytes);
+  CUDA_TRY(cudaMemcpyAsync(ix->d_qf32, q_pinned ? q_host : ix->h_q, qbytes, cudaMemcpyHostToDevice, st));
   int64_t max_hits = 0;
   const int64_t* d_rowptr = nullptr;
   if (hit_rowptr_host) {
@@ -559,6 +567,13 @@ extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int
                       ix->d_bonus, max_hits, k, ksel, 2e-5, 0, ix->d_score, nullptr, ix->d_idx, ix->d_flags,
                       ix->ws, ix->ws_bytes, KEMR_PATH_AUTO, st);
   if (rc) return rc;
+  if (out_pinned) {
+    CUDA_TRY(cudaMemcpyAsync(out_idx_host, ix->d_idx, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_score64_host, ix->d_score, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
+    if (out_flags_host) CUDA_TRY(cudaMemcpyAsync(out_flags_host, ix->d_flags, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return KEMR_OK;
+  }
   CUDA_TRY(cudaMemcpyAsync(ix->h_idx, ix->d_idx, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(ix->h_score, ix->d_score, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(ix->h_flags, ix->d_flags, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
