@@ -168,7 +168,7 @@ extern "C" size_t kemr_workspace_bytes(int Q, int64_t M, int D, int k_sel, int64
   if (dev_info(&dv) == KEMR_OK && dv.sms > 0) sms = dv.sms;
   const int P = 2 * sms + 8;                    // upper bound of any plan's part count
   const int K = std::max(1, std::min(k_sel, kMaxKSel));
-  const int Qp = (Q + 127) / 128 * 128;
+  const int Qp = (Q + 255) / 256 * 256;       // query rows padded to a CTA pair's block
   size_t topk = parts_bytes(P, Qp, K);
   size_t count = align_up((size_t)Q * 8) + align_up((size_t)Q * 8) + align_up((size_t)P * Qp * 4) + 256 +
                  align_up(((size_t)1 << 20) * 8 + (size_t)Q * 256 * 8);
@@ -331,7 +331,7 @@ extern "C" int kemr_rank_count(const uint16_t* q, int Q, const uint16_t* gal_a, 
   if (g_scan_done_event) CUDA_TRY(cudaEventRecord(g_scan_done_event, st));
 
   unsigned long long* count = reinterpret_cast<unsigned long long*>(out_count);
-  rank_sum_parts_kernel<<<(Q + 255) / 256, 256, 0, st>>>(part_count, pl.P, Qrows, amb_counter, amb_cap, count, out_flags);
+  rank_sum_parts_kernel<<<(Q + 255) / 256, 256, 0, st>>>(part_count, pl.P, Q, Qrows, amb_counter, amb_cap, count, out_flags);
   LAUNCH_CHECK("rank_sum_parts_kernel");
   RankFixArgs f{};
   f.q = q; f.gal[0] = gal_a; f.gal[1] = gal_b; f.G = G; f.D = D; f.w[0] = w_a; f.w[1] = w_b; f.alpha = alpha;

@@ -25,6 +25,16 @@
 // in REGISTERS (K <= 32, branch-free compare/select insert), so list maintenance runs in lock-step
 // instead of diverging per lane, and the score matrix never exists outside TMEM.
 // Roofline: tensor pipe for batch >= ~250 (2*B*G*M*D flop), HBM below (G*M*D*2 bytes).
+//
+// CTA pairs (PAIR = true, batches above 128 queries): two CTAs of one cluster run ONE
+// tcgen05.mma.cta_group::2 with M = 256 queries (128 per CTA) and N = 256 gallery columns; each CTA
+// stages its own 128 query rows and only HALF of the gallery chunk (CTA 0: T2I rows / first 128 rows,
+// CTA 1: T2T rows / second 128 rows), so a pipeline stage is 32 KB instead of 48 KB and the bytes
+// pulled through L2 per flop drop by a third -- the single-CTA kernel was bound by L2->SM bandwidth
+// (ncu: tensor pipe 61 % of active cycles, 11.5 TB/s of TMA reads).  The leader CTA's elected thread
+// issues every MMA; tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both
+// CTAs, the peer's TMA loads complete on the leader's full barrier, and both CTAs' epilogue warps
+// arrive on the leader's accumulator-empty barrier.
 #pragma once
 #include <cuda.h>
 #include <stdlib.h>
@@ -42,6 +52,7 @@ constexpr int kBlockM = 128;           // queries per block == TMEM lanes
 constexpr int kBlockK = 64;            // bf16 elements per 128-byte swizzle row
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kMaxStages = 16;
+constexpr int kTraceBase = 8192, kTraceLen = 96;   // KEMR_MMA_DEBUG: per-stage timestamps of CTA 0/1
 
 struct MmaPlan {
   int parts = 0;          // candidate lists per query (2 per CTA touching its block)
@@ -53,8 +64,8 @@ struct MmaPlan {
   int kc = 0;             // K chunks of 64
   int a_rows = 0;         // query rows actually loaded per block
   int K = 0;              // list length (8, 16, 24, 32)
-  int ts = 0;             // 1: query block lives in TMEM (A operand from TMEM), only B is streamed
-  int acc_col = 0;        // first TMEM column of the accumulators
+  int pair = 0;           // 1: CTA pairs (cta_group::2), 256 queries per block
+  int q_blk = 0;          // queries per block (128, or 256 for CTA pairs)
   size_t smem = 0;
 };
 
@@ -69,40 +80,35 @@ inline int mma_round_k(int K) { return K <= 8 ? 8 : K <= 16 ? 16 : K <= 24 ? 24 
 inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sms, MmaPlan* p) {
   (void)mode;
   p->kc = (D + kBlockK - 1) / kBlockK;
-  // A-in-TMEM variant: the 128 x D query block takes kc*32 TMEM columns (two bf16 per cell); what is
-  // left holds the double-buffered accumulators.  It halves shared-memory and L2 traffic because
-  // only gallery rows are streamed.  Falls back to both-operands-in-smem when D is too large.
-  {
-    // Measured on B200: reading the 128x16 A tile from TMEM costs ~64 cycles per MMA whatever N is,
-    // so this variant only pays for N >= 256; it is kept as an opt-in experiment (KEMR_MMA_TS=1).
-    static const bool no_ts = getenv("KEMR_MMA_TS") == nullptr;
-    const int avail = 512 - p->kc * 32;
-    int n = 256;
-    while (n >= 32 && 2 * G * n > avail) n >>= 1;
-    p->ts = (!no_ts && n >= 32) ? 1 : 0;
-    p->n_tile = p->ts ? n : (G == 2 ? 128 : 256);
-    p->acc_col = p->ts ? p->kc * 32 : 0;
-  }
-  p->n_qb = (Q + kBlockM - 1) / kBlockM;
-  p->q_pad = p->n_qb * kBlockM;
+  // Measured and rejected on B200: A operand from TMEM (tcgen05.mma TS form) costs ~70 cycles + N/2
+  // per MMA whatever N is (TMEM read of the 128x16 A tile), 5x slower at N = 32 -- removed.
+  static const char* force_pair = getenv("KEMR_MMA_PAIR");          // experiments: 0 = never, 1 = always
+  p->pair = force_pair ? (force_pair[0] == '1') : (Q > kBlockM);
+  if (sms < 2) p->pair = 0;
+  p->q_blk = p->pair ? 2 * kBlockM : kBlockM;
+  p->n_tile = G == 2 ? 128 : 256;
+  p->n_qb = (Q + p->q_blk - 1) / p->q_blk;
+  p->q_pad = p->n_qb * p->q_blk;
   const int64_t nt = (M + p->n_tile - 1) / p->n_tile;
   if (nt > (1ll << 30)) return 1;
   p->n_t = (int)nt;
   const int64_t W = (int64_t)p->n_qb * p->n_t;
-  p->ctas = (int)std::min<int64_t>(sms, W);
-  // widest span of CTAs touching one query block
+  const int units = p->pair ? sms / 2 : sms;       // persistent CTAs, or CTA pairs
+  const int nu = (int)std::min<int64_t>(units, W);
+  p->ctas = p->pair ? 2 * nu : nu;
+  // widest span of CTAs (pairs) touching one query block
   int parts = 1;
   for (int qb = 0; qb < p->n_qb; ++qb) {
     const int64_t w0 = (int64_t)qb * p->n_t, w1 = w0 + p->n_t - 1;
-    const int c0 = (int)(((w0 + 1) * p->ctas - 1) / W), c1 = (int)(((w1 + 1) * p->ctas - 1) / W);
+    const int c0 = (int)(((w0 + 1) * nu - 1) / W), c1 = (int)(((w1 + 1) * nu - 1) / W);
     parts = std::max(parts, c1 - c0 + 1);
   }
   p->parts = 2 * parts;
-  p->a_rows = Q >= kBlockM ? kBlockM : (Q + 7) / 8 * 8;
+  p->a_rows = (p->pair || Q >= kBlockM) ? kBlockM : (Q + 7) / 8 * 8;
   // Many parts per query: each keeps a short list (the global top-k spreads over the parts); the
   // select kernel's certificate flags the rare query whose winners crowd into one part.
   p->K = mma_round_k(p->parts >= 12 && K <= 24 ? std::min(K, 8) : K);
-  const size_t stage = (p->ts ? 0 : (size_t)kBlockM * 128) + (size_t)G * p->n_tile * 128;
+  const size_t stage = (size_t)kBlockM * 128 + (p->pair ? (size_t)128 * 128 : (size_t)G * p->n_tile * 128);
   const size_t epi = (size_t)kBufCap * kEpiThreads * 8;
   p->stages = (int)std::min<size_t>(kMaxStages, (kSmemBudget - 2048 - epi) / stage);
   p->smem = (size_t)p->stages * stage + epi + 1024;
@@ -168,22 +174,48 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// ---- CTA pair (cta_group::2) forms
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory object in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope): a
+// cluster-scope release made the issuing thread wait ~1.5-2.5k cycles for its outstanding TMA loads.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of one CTA's share of a pair's stage; completion bytes go to the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair when the MMAs retire
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -215,9 +247,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 
 struct MmaArgs {
   ScanArgs s;
-  int n_tile, n_qb, n_t, stages, kc, a_rows, parts, q_pad, acc_col;
+  int n_tile, n_qb, n_t, stages, kc, a_rows, parts, q_pad, q_blk;
   long long W;
-  long long* dbg;       // optional [ctas][8] cycle counters (KEMR_MMA_DEBUG=1)
+  long long* dbg;       // optional [ctas][16] cycle counters (KEMR_MMA_DEBUG=1)
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -265,39 +297,44 @@ __device__ __forceinline__ float pick8(const float* v, int j) {
   return (j & 4) ? b1 : b0;
 }
 
-template <int K, bool DBG, bool TS>
+template <int K, bool DBG, bool PAIR>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g0,
                 const __grid_constant__ CUtensorMap map_g1, MmaArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_mma_raw[];
+  // identical shared-memory layout in both CTAs of a pair (the MMA addresses the peer by offset)
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_mma_raw + 1023) & ~(uintptr_t)1023);
   const int n_tile = a.n_tile;
   const int G = a.s.G;
-  const uint32_t a_bytes = TS ? 0u : (uint32_t)kBlockM * 128u, b_bytes = (uint32_t)n_tile * 128;
-  const uint32_t stage_bytes = a_bytes + (uint32_t)G * b_bytes;
+  const uint32_t a_bytes = (uint32_t)kBlockM * 128u;
+  const uint32_t b_bytes = PAIR ? 128u * 128u : (uint32_t)n_tile * 128u;     // per TMA box of gallery rows
+  const uint32_t stage_bytes = a_bytes + (PAIR ? b_bytes : (uint32_t)G * b_bytes);
   float* buf_s = reinterpret_cast<float*>(smem + (size_t)a.stages * stage_bytes);      // [kBufCap][kEpiThreads]
   uint32_t* buf_r = reinterpret_cast<uint32_t*>(buf_s + kBufCap * kEpiThreads);          // [kBufCap][kEpiThreads]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(buf_r + kBufCap * kEpiThreads);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;      // [2]
   uint64_t* tempty_bar = tfull_bar + 2;              // [2]
-  uint64_t* aready_bar = tempty_bar + 2;             // [1] query block written to TMEM (TS)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aready_bar + 1);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long w_lo = a.W * blockIdx.x / gridDim.x, w_hi = a.W * (blockIdx.x + 1) / gridDim.x;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // persistent CTA or CTA pair
+  const int units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const long long w_lo = a.W * unit / units, w_hi = a.W * (unit + 1) / units;
 
   if (threadIdx.x == 0) {
+    // full: one arrival (the leader's expect_tx covers both CTAs' bytes; the peer's TMA loads complete
+    // on the leader's barrier); tempty: epilogue warps of both CTAs
     for (int i = 0; i < a.stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], kEpiWarps); }
-    ptx::mbar_init(aready_bar, kEpiWarps);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiWarps : kEpiWarps); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&map_q); ptx::prefetch_tmap(&map_g0);
     if (G > 1) ptx::prefetch_tmap(&map_g1);
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_ptr, 512);
+  if (warp == 1) { if (PAIR) ptx::tmem_alloc_pair(tmem_ptr, 512); else ptx::tmem_alloc(tmem_ptr, 512); }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -305,71 +342,81 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ================================================================= TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (TS ? 0u : (uint32_t)a.a_rows * 128u) + (uint32_t)G * b_bytes;
       long long w_empty = 0; const long long t_begin = tick<DBG>();
-      for (long long w = w_lo; w < w_hi; ++w) {
-        const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
-        for (int kc = 0; kc < a.kc; ++kc) {
-          ptx::mbar_wait_timed<DBG>(&empty_bar[stage], phase ^ 1, w_empty);
-          unsigned char* sa = smem + (size_t)stage * stage_bytes;
-          ptx::mbar_expect_tx(&full_bar[stage], tx);
-          if (!TS) ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kc * kBlockK, qb * kBlockM);
-          ptx::tma_load_2d(sa + a_bytes, &map_g0, &full_bar[stage], kc * kBlockK, t * n_tile);
-          if (G > 1) ptx::tma_load_2d(sa + a_bytes + b_bytes, &map_g1, &full_bar[stage], kc * kBlockK, t * n_tile);
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      int tr = 0;
+      if (PAIR) {
+        // this CTA's 128 query rows + its half of the stacked gallery chunk; bytes land on the leader's barrier
+        const CUtensorMap* map_b = (G > 1 && rank == 1) ? &map_g1 : &map_g0;
+        const int b_row_off = G > 1 ? 0 : (int)rank * 128;
+        for (long long w = w_lo; w < w_hi; ++w) {
+          const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
+          for (int kc = 0; kc < a.kc; ++kc) {
+            ptx::mbar_wait_timed<DBG>(&empty_bar[stage], phase ^ 1, w_empty);
+            if (DBG && a.dbg && blockIdx.x < 2 && tr < kTraceLen) a.dbg[kTraceBase + (blockIdx.x * 4 + 0) * kTraceLen + tr] = clock64();
+            unsigned char* sa = smem + (size_t)stage * stage_bytes;
+            const uint32_t lbar = ptx::map_to_cta(ptx::smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
+            ptx::tma_load_2d_pair(sa, &map_q, lbar, kc * kBlockK, qb * (2 * kBlockM) + (int)rank * kBlockM);
+            ptx::tma_load_2d_pair(sa + a_bytes, map_b, lbar, kc * kBlockK, t * n_tile + b_row_off);
+            if (DBG && a.dbg && blockIdx.x < 2 && tr < kTraceLen) { a.dbg[kTraceBase + (blockIdx.x * 4 + 1) * kTraceLen + tr] = clock64(); ++tr; }
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else {
+        const uint32_t tx = (uint32_t)a.a_rows * 128u + (uint32_t)G * b_bytes;
+        for (long long w = w_lo; w < w_hi; ++w) {
+          const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
+          for (int kc = 0; kc < a.kc; ++kc) {
+            ptx::mbar_wait_timed<DBG>(&empty_bar[stage], phase ^ 1, w_empty);
+            if (DBG && a.dbg && blockIdx.x < 2 && tr < kTraceLen) a.dbg[kTraceBase + (blockIdx.x * 4 + 0) * kTraceLen + tr] = clock64();
+            unsigned char* sa = smem + (size_t)stage * stage_bytes;
+            ptx::mbar_expect_tx(&full_bar[stage], tx);
+            ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kc * kBlockK, qb * kBlockM);
+            ptx::tma_load_2d(sa + a_bytes, &map_g0, &full_bar[stage], kc * kBlockK, t * n_tile);
+            if (G > 1) ptx::tma_load_2d(sa + a_bytes + b_bytes, &map_g1, &full_bar[stage], kc * kBlockK, t * n_tile);
+            if (DBG && a.dbg && blockIdx.x < 2 && tr < kTraceLen) { a.dbg[kTraceBase + (blockIdx.x * 4 + 1) * kTraceLen + tr] = clock64(); ++tr; }
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          }
         }
       }
       if (DBG && a.dbg) { a.dbg[blockIdx.x * 16 + 0] = w_empty; a.dbg[blockIdx.x * 16 + 1] = tick<DBG>() - t_begin; }
     }
   } else if (warp == 1) {
-    // ================================================================= MMA issuer
-    if (lane == 0) {
+    // ================================================================= MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t idesc = umma_idesc_bf16(kBlockM, n_tile);
-      const uint32_t idesc_all = umma_idesc_bf16(kBlockM, G * n_tile);
+      // The gallery chunks of a stage form ONE K-major tile of 256 rows (T2I rows then T2T rows, or
+      // 256 rows of the single gallery; split across the two CTAs in pair mode): a single MMA with
+      // N = 256 fills the whole accumulator buffer and reads the query chunk once.
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, G * n_tile);
       long long it = 0;
       long long w_full = 0, w_tempty = 0; const long long t_begin = tick<DBG>();
-      int mma_qb = -1; uint32_t aphase = 0;
+      int tr = 0;
       for (long long w = w_lo; w < w_hi; ++w, ++it) {
-        if (TS) {
-          const int qb = (int)(w / a.n_t);
-          if (qb != mma_qb) {                       // wait until the epilogue warps stored this query block
-            ptx::mbar_wait_timed<DBG>(aready_bar, aphase, w_tempty);
-            ptx::tc_fence_after();
-            aphase ^= 1; mma_qb = qb;
-          }
-        }
         const int buf = (int)(it & 1);
         const uint32_t bphase = (uint32_t)((it >> 1) & 1);
         ptx::mbar_wait_timed<DBG>(&tempty_bar[buf], bphase ^ 1, w_tempty);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)a.acc_col + (uint32_t)(buf * G) * (uint32_t)n_tile;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * G) * (uint32_t)n_tile;
         for (int kc = 0; kc < a.kc; ++kc) {
           ptx::mbar_wait_timed<DBG>(&full_bar[stage], phase, w_full);
+          if (DBG && a.dbg && blockIdx.x == 0 && tr < kTraceLen) a.dbg[kTraceBase + 2 * kTraceLen + tr] = clock64();
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t adesc = umma_desc_sw128(sa);
-          if (TS) {
-            for (int g = 0; g < G; ++g) {
-              const uint64_t bdesc = umma_desc_sw128(sa + a_bytes + (uint32_t)g * b_bytes);
+          const uint64_t bdesc = umma_desc_sw128(sa + a_bytes);
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                ptx::mma_bf16_ts(d_tmem + (uint32_t)g * (uint32_t)n_tile, tmem_base + (uint32_t)(kc * 32 + k * 8),
-                                 bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
-            }
-          } else {
-            // The galleries' chunks sit back to back in the stage, i.e. they form ONE K-major tile of
-            // G*n_tile rows: a single MMA with N = G*n_tile fills both accumulators (columns
-            // [0,n_tile) = T2I, [n_tile,2*n_tile) = T2T) and reads the query chunk once.
-            const uint64_t bdesc = umma_desc_sw128(sa + a_bytes);
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              ptx::mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_all, (kc | k) ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if (PAIR) ptx::mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+            else ptx::mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
           }
-          ptx::mma_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs) when these MMAs retire
+          if (PAIR) ptx::mma_commit_pair(&empty_bar[stage]); else ptx::mma_commit(&empty_bar[stage]);
+          if (DBG && a.dbg && blockIdx.x == 0 && tr < kTraceLen) { a.dbg[kTraceBase + 3 * kTraceLen + tr] = clock64(); ++tr; }
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
-        ptx::mma_commit(&tfull_bar[buf]);              // accumulators of this tile are complete
+        // accumulators of this tile are complete
+        if (PAIR) ptx::mma_commit_pair(&tfull_bar[buf]); else ptx::mma_commit(&tfull_bar[buf]);
       }
       if (DBG && a.dbg) { a.dbg[blockIdx.x * 16 + 2] = w_full; a.dbg[blockIdx.x * 16 + 3] = w_tempty; a.dbg[blockIdx.x * 16 + 4] = tick<DBG>() - t_begin; }
     }
@@ -378,7 +425,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
     const int half = (warp - 2) >> 2;                    // which half of the tile's columns
     const int et = (warp - 2) * 32 + lane;               // epilogue thread id, 0..255
-    const int qrow = quad * 32 + lane;                   // query row inside the block
+    const int qrow = (int)rank * kBlockM + quad * 32 + lane;     // query row inside the block
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float w0 = a.s.w[0], w1 = a.s.w[1];
     const int mode = a.s.mode;
@@ -391,9 +438,10 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     float blo = 0.f, bhi = 0.f;
     int cur_qb = -1;
     const long long Wt = a.W;
-    const int C = gridDim.x;
     long long it = 0;
     long long w_tfull = 0, t_fold = 0, t_ld = 0, t_sm = 0, t_app = 0; const long long t_begin = tick<DBG>();
+    const uint32_t tempty0 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tempty_bar[0]), 0) : ptx::smem_u32(&tempty_bar[0]);
+    const uint32_t tempty1 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tempty_bar[1]), 0) : ptx::smem_u32(&tempty_bar[1]);
 
     // fold every lane's append buffer into its register list, in lock-step
     auto fold = [&]() {
@@ -414,9 +462,9 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     auto flush = [&](int qb) {
       if (qb < 0) return;
       const long long wq = (long long)qb * a.n_t;
-      const int c_first = (int)(((wq + 1) * C - 1) / Wt);
-      const int slot = ((int)blockIdx.x - c_first) * 2 + half;
-      const int qg = qb * kBlockM + qrow;
+      const int c_first = (int)(((wq + 1) * units - 1) / Wt);
+      const int slot = (unit - c_first) * 2 + half;
+      const int qg = qb * a.q_blk + qrow;
       if (mode == kModeTopk) {
         fold();
         uint64_t* dst = a.s.part_keys + ((size_t)slot * a.q_pad + qg) * a.s.K;
@@ -436,31 +484,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         list.reset();
         thr = -INFINITY;
         cnt = 0;
-        if (TS) {
-          // This warp has seen the last tile of the previous block complete (tfull), so no MMA still
-          // reads the old block: store the new 128 x D query block into TMEM, one row per lane,
-          // two bf16 per 32-bit cell, 16 cells per store; pad rows/columns are zero.
-          const int qg0 = qb * kBlockM + qrow;
-          const uint16_t* qsrc = a.s.q + (size_t)qg0 * a.s.D;
-          const int nblk = a.kc * 2;                    // 16-cell blocks per row
-          for (int cb = half; cb < nblk; cb += 2) {
-            uint32_t r[16];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const int e0 = cb * 32 + v * 8;           // first bf16 element of this 16-byte piece
-              uint4 x = make_uint4(0, 0, 0, 0);
-              if (qg0 < a.s.Q && e0 < a.s.D) x = *reinterpret_cast<const uint4*>(qsrc + e0);
-              r[v * 4 + 0] = x.x; r[v * 4 + 1] = x.y; r[v * 4 + 2] = x.z; r[v * 4 + 3] = x.w;
-            }
-            ptx::tmem_st16(lane_addr + (uint32_t)(cb * 16), r);
-          }
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(aready_bar);
-        }
         if (mode == kModeCount) {
-          const int qg0 = qb * kBlockM + qrow;
+          const int qg0 = qb * a.q_blk + qrow;
           blo = a.s.band_lo[qg0]; bhi = a.s.band_hi[qg0];   // padded rows hold +huge: never count
         }
       }
@@ -468,11 +493,11 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint32_t bphase = (uint32_t)((it >> 1) & 1);
       ptx::mbar_wait_timed<DBG>(&tfull_bar[buf], bphase, w_tfull);
       ptx::tc_fence_after();
-      const int qg = qb * kBlockM + qrow;
+      const int qg = qb * a.q_blk + qrow;
       const bool qvalid = qg < a.s.Q;
       const long long row0 = (long long)t * n_tile;
       const int ncols = (int)min((long long)n_tile, a.s.M - row0);
-      const uint32_t acc0 = lane_addr + (uint32_t)a.acc_col + (uint32_t)(buf * G) * (uint32_t)n_tile;
+      const uint32_t acc0 = lane_addr + (uint32_t)(buf * G) * (uint32_t)n_tile;
       for (int c0 = half * half_cols; c0 < (half + 1) * half_cols; c0 += 16) {
         if (c0 >= ncols) break;                          // warp-uniform
         uint32_t ra[16], rb[16];
@@ -534,20 +559,24 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
         }
       }
-      // release this accumulator buffer to the MMA warp
+      // release this accumulator buffer to the (leader's) MMA warp
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) {
+        if (PAIR && rank != 0) ptx::mbar_arrive_remote(buf ? tempty1 : tempty0);
+        else ptx::mbar_arrive(&tempty_bar[buf]);
+      }
     }
     flush(cur_qb);
     if (DBG && a.dbg && warp == 2 && lane == 0) { a.dbg[blockIdx.x * 16 + 5] = w_tfull; a.dbg[blockIdx.x * 16 + 6] = t_fold; a.dbg[blockIdx.x * 16 + 7] = tick<DBG>() - t_begin; a.dbg[blockIdx.x * 16 + 8] = t_ld; a.dbg[blockIdx.x * 16 + 9] = t_sm; a.dbg[blockIdx.x * 16 + 10] = t_app; }
   }
 
+  // no CTA of a pair may leave (or free TMEM) while its peer can still signal its barriers
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -586,33 +615,44 @@ inline int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int D,
   return 0;
 }
 
-template <int K, bool DBG, bool TS>
+template <int K, bool DBG, bool PAIR>
 inline int mma_launch_kdt(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
                           const MmaPlan& pl, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<K, DBG, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
+  cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<K, DBG, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "smem attribute: %s", cudaGetErrorString(e)); return 1; }
-  scan_mma_kernel<K, DBG, TS><<<pl.ctas, kMmaThreads, pl.smem + 1024, st>>>(mq, m0, m1, ma);
-  e = cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)pl.ctas);
+  cfg.blockDim = dim3(kMmaThreads);
+  cfg.dynamicSmemBytes = pl.smem + 1024;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, scan_mma_kernel<K, DBG, PAIR>, mq, m0, m1, ma);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
 }
 template <int K>
 inline int mma_launch_k(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
                         const MmaPlan& pl, cudaStream_t st) {
-  if (pl.ts) return ma.dbg ? mma_launch_kdt<K, true, true>(mq, m0, m1, ma, pl, st) : mma_launch_kdt<K, false, true>(mq, m0, m1, ma, pl, st);
+  if (pl.pair) return ma.dbg ? mma_launch_kdt<K, true, true>(mq, m0, m1, ma, pl, st) : mma_launch_kdt<K, false, true>(mq, m0, m1, ma, pl, st);
   return ma.dbg ? mma_launch_kdt<K, true, false>(mq, m0, m1, ma, pl, st) : mma_launch_kdt<K, false, false>(mq, m0, m1, ma, pl, st);
 }
 
 inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
   CUtensorMap mq, m0, m1;
   if (make_tmap_2d(&mq, s.q, s.Q, s.D, pl.a_rows)) return 1;
-  if (make_tmap_2d(&m0, s.gal[0], s.M, s.D, pl.n_tile)) return 1;
-  if (s.G > 1) { if (make_tmap_2d(&m1, s.gal[1], s.M, s.D, pl.n_tile)) return 1; }
+  const int b_box = pl.pair ? 128 : pl.n_tile;     // gallery rows per TMA box
+  if (make_tmap_2d(&m0, s.gal[0], s.M, s.D, b_box)) return 1;
+  if (s.G > 1) { if (make_tmap_2d(&m1, s.gal[1], s.M, s.D, b_box)) return 1; }
   else m1 = m0;
   MmaArgs ma;
   ma.s = s;
   ma.n_tile = pl.n_tile; ma.n_qb = pl.n_qb; ma.n_t = pl.n_t; ma.stages = pl.stages; ma.kc = pl.kc;
-  ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.acc_col = pl.acc_col;
+  ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.q_blk = pl.q_blk;
   ma.W = (long long)pl.n_qb * pl.n_t;
   ma.dbg = nullptr;
   static const bool debug = getenv("KEMR_MMA_DEBUG") != nullptr;
@@ -636,9 +676,32 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
       std::vector<long long> h((size_t)pl.ctas * 16);
       cudaMemcpy(h.data(), ma.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
       double avg[16] = {0};
-      for (int c = 0; c < pl.ctas; ++c) for (int i = 0; i < 16; ++i) avg[i] += (double)h[(size_t)c * 16 + i] / pl.ctas;
-      fprintf(stderr, "[kemr mma dbg] ts=%d n_tile=%d K=%d ctas=%d tiles/cta=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f ld=%.0f score+mask=%.0f append=%.0f cycles\n",
-              pl.ts, pl.n_tile, pl.K, pl.ctas, (double)ma.W / pl.ctas, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7], avg[8], avg[9], avg[10]);
+      const int stride = pl.pair ? 2 : 1;        // the MMA role runs in the leader CTA of a pair
+      const int nu = pl.ctas / stride;
+      for (int c = 0; c < pl.ctas; c += stride) for (int i = 0; i < 16; ++i) avg[i] += (double)h[(size_t)c * 16 + i] / nu;
+      long long tmin = 1ll << 62, tmax = 0; int cmin = 0, cmax = 0;
+      for (int c = 0; c < pl.ctas; c += stride) {
+        const long long t = h[(size_t)c * 16 + 4];
+        if (t < tmin) { tmin = t; cmin = c; }
+        if (t > tmax) { tmax = t; cmax = c; }
+      }
+      fprintf(stderr, "[kemr mma dbg] pair=%d n_tile=%d K=%d ctas=%d tiles/unit=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f (min %lld @cta %d, max %lld @cta %d; max cta: wait_full=%lld wait_tempty=%lld) | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f ld=%.0f score+mask=%.0f append=%.0f cycles\n",
+              pl.pair, pl.n_tile, pl.K, pl.ctas, (double)ma.W / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
+              tmin, cmin, tmax, cmax, h[(size_t)cmax * 16 + 2], h[(size_t)cmax * 16 + 3], avg[5], avg[6], avg[7], avg[8], avg[9], avg[10]);
+      if (getenv("KEMR_MMA_DEBUG_TRACE")) {
+        std::vector<long long> tr((size_t)8 * kTraceLen);
+        cudaMemcpy(tr.data(), ma.dbg + kTraceBase, tr.size() * 8, cudaMemcpyDeviceToHost);
+        const long long t0 = tr[0];
+        fprintf(stderr, "[kemr mma trace] stage-iteration: cta0 producer saw-empty / issued | cta0 mma saw-full / committed | cta1 producer saw-empty / issued (cta1 on its own SM clock, relative to its first)\n");
+        for (int i = 0; i < kTraceLen; ++i)
+          fprintf(stderr, "[kemr mma trace] %3d: %7lld %7lld | %7lld %7lld | %7lld %7lld\n", i, tr[i] - t0, tr[kTraceLen + i] - t0,
+                  tr[2 * kTraceLen + i] - t0, tr[3 * kTraceLen + i] - t0, tr[4 * kTraceLen + i] - tr[4 * kTraceLen], tr[5 * kTraceLen + i] - tr[4 * kTraceLen]);
+      }
+      if (getenv("KEMR_MMA_DEBUG_ALL")) {
+        for (int c = 0; c < pl.ctas; c += stride)
+          fprintf(stderr, "[kemr mma dbg] cta %d: mma total=%lld wait_full=%lld wait_tempty=%lld | epi total=%lld wait_tfull=%lld fold=%lld\n", c,
+                  h[(size_t)c * 16 + 4], h[(size_t)c * 16 + 2], h[(size_t)c * 16 + 3], h[(size_t)c * 16 + 7], h[(size_t)c * 16 + 5], h[(size_t)c * 16 + 6]);
+      }
     }
   }
   return rc_launch;

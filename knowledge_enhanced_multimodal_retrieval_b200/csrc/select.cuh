@@ -421,13 +421,14 @@ __global__ void rank_band_kernel(const double* __restrict__ t, double alpha, dou
   hi[i] = __double2float_ru(c + e);
 }
 
-__global__ void rank_sum_parts_kernel(const int32_t* __restrict__ part_count, int P, int Q,
+// part_count is [P][q_stride] (q_stride = query rows padded by the scan kernel); outputs hold Q entries
+__global__ void rank_sum_parts_kernel(const int32_t* __restrict__ part_count, int P, int Q, int q_stride,
                                       const unsigned int* __restrict__ amb_counter, unsigned int amb_cap,
                                       unsigned long long* __restrict__ count, int32_t* __restrict__ flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Q) return;
   unsigned long long s = 0;
-  for (int p = 0; p < P; ++p) s += (unsigned long long)part_count[(size_t)p * Q + i];
+  for (int p = 0; p < P; ++p) s += (unsigned long long)part_count[(size_t)p * q_stride + i];
   count[i] = s;
   flags[i] = (*amb_counter > amb_cap) ? 2 : 0;
 }

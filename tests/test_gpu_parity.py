@@ -160,6 +160,28 @@ def test_certificate_flags_and_retry():
 
 # --------------------------------------------------------------------------- ranks and metrics
 @pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("shape", [(130, 128, 64, False), (333, 2500, 256, True), (257, 300, 128, False)])
+def test_rank_targets_padded_query_blocks(path, shape):
+    """Query counts that are not multiples of the tensor kernel's block (128 / 256 for CTA pairs):
+    padded rows must neither count nor be written (regression: the part-count reduction once wrote
+    count[] / flags[] for the padded rows too and clobbered neighbouring allocations)."""
+    Q, M, D, fused = shape
+    if not path_ok(path, D):
+        pytest.skip("tcgen05 path unavailable")
+    s = synth.make_retrieval_set(Q=Q, M=M, D=D, seed=31, fused=fused, lam=0.15, with_kg=False, diagonal=False)
+    q, img = dev(s.query), dev(s.image)
+    tgt = dev(s.target) if fused else None
+    wa, wb = (0.5, 0.5) if fused else (1.0, 0.0)
+    si = O.canon_dot64(s.query, s.image)
+    st = O.canon_dot64(s.query, s.target) if fused else None
+    tidx = torch.from_numpy(s.target_idx).cuda()
+    guard = torch.full((4096,), 7, dtype=torch.int64, device="cuda")      # neighbours of the outputs
+    got = engine.rank_targets(q, img, tgt, tidx, wa, wb, path=path).cpu().numpy()
+    assert np.array_equal(got, O.canon_rank(O.canon_fused64(si, st, wa, wb), s.target_idx))
+    assert bool((guard == 7).all())
+
+
+@pytest.mark.parametrize("path", PATHS)
 def test_rank_targets_matches_canonical(path):
     D = 256
     if not path_ok(path, D):
