@@ -127,7 +127,7 @@ static int check_common(const void* q, int Q, const void* ga, int64_t M, int D) 
   return KEMR_OK;
 }
 
-static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, const DevInfo& dv, ScanPlan* pl) {
+static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, bool equal_weights, const DevInfo& dv, ScanPlan* pl) {
   pl->path = path;
   if (path == KEMR_PATH_AUTO) {
     static const char* force = getenv("KEMR_FORCE_PATH");     // experiments: 1 = warp-dot, 2 = tcgen05
@@ -142,7 +142,7 @@ static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, 
   if (pl->path == KEMR_PATH_MMA) {
     if (dv.major != 10) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path needs compute capability 10.x (have %d.%d)", dv.major, dv.minor);
     if (!mma_supported(D, K)) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path: unsupported D=%d / k_sel=%d", D, K);
-    int rc = mma_make_plan(Q, M, D, G, K, mode, dv.sms, &pl->mma);
+    int rc = mma_make_plan(Q, M, D, G, K, mode, dv.sms, equal_weights, &pl->mma);
     if (rc) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path: cannot plan this shape");
     pl->P = pl->mma.parts;
     pl->Kp = pl->mma.K;
@@ -211,7 +211,7 @@ extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, c
   if ((rc = dev_info(&dv))) return rc;
   const int G = gal_b ? 2 : 1;
   ScanPlan pl;
-  if ((rc = make_plan(Q, M, D, G, k_sel, kModeTopk, path, dv, &pl))) return rc;
+  if ((rc = make_plan(Q, M, D, G, k_sel, kModeTopk, path, (float)w_a == (float)w_b, dv, &pl))) return rc;
   const int Qrows = pl.path == KEMR_PATH_MMA ? pl.mma.q_pad : Q;
   const size_t need = parts_bytes(pl.P, Qrows, pl.Kp);
   if (!workspace || workspace_bytes < need) return fail(KEMR_ERR_WORKSPACE, "scan_topk needs %zu workspace bytes, got %zu", need, workspace_bytes);
@@ -288,7 +288,7 @@ extern "C" int kemr_rank_count(const uint16_t* q, int Q, const uint16_t* gal_a, 
   if ((rc = dev_info(&dv))) return rc;
   const int G = gal_b ? 2 : 1;
   ScanPlan pl;
-  if ((rc = make_plan(Q, M, D, G, 16, kModeCount, path, dv, &pl))) return rc;
+  if ((rc = make_plan(Q, M, D, G, 16, kModeCount, path, (float)w_a == (float)w_b, dv, &pl))) return rc;
   const int Qrows = pl.path == KEMR_PATH_MMA ? pl.mma.q_pad : Q;
 
   // carve: band_lo | band_hi | part_count | amb_counter | amb_q | amb_row
@@ -357,7 +357,7 @@ extern "C" int kemr_score_matrix(const uint16_t* q, int Q, const uint16_t* gal_a
   if ((rc = dev_info(&dv))) return rc;
   const int G = gal_b ? 2 : 1;
   ScanPlan pl;
-  if ((rc = make_plan(Q, M, D, G, 16, kModeDense, path, dv, &pl))) return rc;
+  if ((rc = make_plan(Q, M, D, G, 16, kModeDense, path, w_a == w_b, dv, &pl))) return rc;
   ScanArgs a{};
   a.q = q; a.Q = Q; a.gal[0] = gal_a; a.gal[1] = gal_b; a.G = G; a.M = M; a.D = D;
   a.w[0] = w_a; a.w[1] = w_b; a.mode = kModeDense; a.K = 16; a.dense = out; a.ld = ld;

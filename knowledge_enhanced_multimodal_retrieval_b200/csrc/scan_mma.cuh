@@ -65,6 +65,9 @@ struct MmaPlan {
   int a_rows = 0;         // query rows actually loaded per block
   int K = 0;              // list length (8, 16, 24, 32)
   int pair = 0;           // 1: CTA pairs (cta_group::2), 256 queries per block
+  int upq = 0;            // units (CTAs or pairs) per query block; 0 = flattened (block, tile) ranges
+  int two = 0;            // 1: two accumulators (T2I, T2T) with their own weights
+  int merged = 0;         // 1: two galleries, equal weights: one accumulator over 2*kc K chunks
   int q_blk = 0;          // queries per block (128, or 256 for CTA pairs)
   size_t smem = 0;
 };
@@ -77,16 +80,22 @@ inline const char* mma_last_error() { return g_mma_error; }
 
 inline int mma_round_k(int K) { return K <= 8 ? 8 : K <= 16 ? 16 : K <= 24 ? 24 : 32; }
 
-inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sms, MmaPlan* p) {
+inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sms, bool equal_weights, MmaPlan* p) {
   (void)mode;
   p->kc = (D + kBlockK - 1) / kBlockK;
+  // Two galleries with EQUAL fusion weights: w*(q.a) + w*(q.b) = w*(q.a + q.b), so both galleries'
+  // K chunks accumulate into one accumulator of 256 gallery rows and the epilogue sees half as many
+  // scores per flop.  Different weights keep one accumulator per gallery (128 rows each).
+  static const bool no_merge = getenv("KEMR_MMA_NO_MERGE") != nullptr;
+  p->merged = (G == 2 && equal_weights && !no_merge) ? 1 : 0;
+  p->two = (G == 2 && !p->merged) ? 1 : 0;
   // Measured and rejected on B200: A operand from TMEM (tcgen05.mma TS form) costs ~70 cycles + N/2
   // per MMA whatever N is (TMEM read of the 128x16 A tile), 5x slower at N = 32 -- removed.
   static const char* force_pair = getenv("KEMR_MMA_PAIR");          // experiments: 0 = never, 1 = always
   p->pair = force_pair ? (force_pair[0] == '1') : (Q > kBlockM);
   if (sms < 2) p->pair = 0;
   p->q_blk = p->pair ? 2 * kBlockM : kBlockM;
-  p->n_tile = G == 2 ? 128 : 256;
+  p->n_tile = p->two ? 128 : 256;
   p->n_qb = (Q + p->q_blk - 1) / p->q_blk;
   p->q_pad = p->n_qb * p->q_blk;
   const int64_t nt = (M + p->n_tile - 1) / p->n_tile;
@@ -94,21 +103,32 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
   p->n_t = (int)nt;
   const int64_t W = (int64_t)p->n_qb * p->n_t;
   const int units = p->pair ? sms / 2 : sms;       // persistent CTAs, or CTA pairs
-  const int nu = (int)std::min<int64_t>(units, W);
-  p->ctas = p->pair ? 2 * nu : nu;
-  // widest span of CTAs (pairs) touching one query block
-  int parts = 1;
-  for (int qb = 0; qb < p->n_qb; ++qb) {
-    const int64_t w0 = (int64_t)qb * p->n_t, w1 = w0 + p->n_t - 1;
-    const int c0 = (int)(((w0 + 1) * nu - 1) / W), c1 = (int)(((w1 + 1) * nu - 1) / W);
-    parts = std::max(parts, c1 - c0 + 1);
+  int nu, parts = 1;
+  const int upq_try = (int)std::min<int64_t>(units / std::max(1, p->n_qb), nt);
+  if (upq_try >= 1 && ((int64_t)upq_try * p->n_qb * 10 >= (int64_t)std::min<int64_t>(units, W) * 9)) {
+    // Every unit stays inside ONE query block (its lists and thresholds are never restarted): the
+    // units are dealt evenly to the blocks and a block's tiles evenly to its units.  A few units may
+    // idle (74 pairs over 4 blocks leave 2); taken only when at least 90 % of the units get work.
+    p->upq = upq_try;
+    nu = p->upq * p->n_qb;
+    parts = p->upq;
+  } else {
+    // more query blocks than units: flattened (block, tile) grid cut into equal contiguous ranges
+    p->upq = 0;
+    nu = (int)std::min<int64_t>(units, W);
+    for (int qb = 0; qb < p->n_qb; ++qb) {
+      const int64_t w0 = (int64_t)qb * p->n_t, w1 = w0 + p->n_t - 1;
+      const int c0 = (int)(((w0 + 1) * nu - 1) / W), c1 = (int)(((w1 + 1) * nu - 1) / W);
+      parts = std::max(parts, c1 - c0 + 1);
+    }
   }
+  p->ctas = p->pair ? 2 * nu : nu;
   p->parts = 2 * parts;
   p->a_rows = (p->pair || Q >= kBlockM) ? kBlockM : (Q + 7) / 8 * 8;
   // Many parts per query: each keeps a short list (the global top-k spreads over the parts); the
   // select kernel's certificate flags the rare query whose winners crowd into one part.
   p->K = mma_round_k(p->parts >= 12 && K <= 24 ? std::min(K, 8) : K);
-  const size_t stage = (size_t)kBlockM * 128 + (p->pair ? (size_t)128 * 128 : (size_t)G * p->n_tile * 128);
+  const size_t stage = (size_t)kBlockM * 128 + (p->pair ? (size_t)128 * 128 : (size_t)256 * 128);
   const size_t epi = (size_t)kBufCap * kEpiThreads * 8;
   p->stages = (int)std::min<size_t>(kMaxStages, (kSmemBudget - 2048 - epi) / stage);
   p->smem = (size_t)p->stages * stage + epi + 1024;
@@ -142,13 +162,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) __trap();
   }
-}
-template <bool DBG>
-__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc) {
-  if (!DBG) { mbar_wait(bar, parity); return; }
-  const long long t0 = clock64();     // try_wait itself may block, so time the whole wait
-  mbar_wait(bar, parity);
-  acc += clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -247,9 +260,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 
 struct MmaArgs {
   ScanArgs s;
-  int n_tile, n_qb, n_t, stages, kc, a_rows, parts, q_pad, q_blk;
+  int n_tile;       // gallery rows per tile (128 with two accumulators, else 256)
+  int merged;       // both galleries accumulate into ONE accumulator (equal weights): 2*kc K chunks
+  int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, upq;
   long long W;
-  long long* dbg;       // optional [ctas][16] cycle counters (KEMR_MMA_DEBUG=1)
+  long long* dbg;   // optional [ctas][16] cycle counters + stage trace (KEMR_MMA_DEBUG=1)
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -261,11 +276,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr) : "memory");
 }
 
+// bounded wait that optionally accumulates the cycles spent waiting (debug counters)
+__device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, bool dbg, long long& acc) {
+  if (!dbg) { ptx::mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  ptx::mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
 // sorted (descending) per-thread candidate list in registers; rows arrive in increasing order, so
 // strict '>' keeps the lower index ahead among equal scores
-template <bool DBG>
-__device__ __forceinline__ long long tick() { return DBG ? clock64() : 0ll; }
-
 template <int K>
 struct RegList {
   float sc[K];
@@ -289,29 +309,36 @@ struct RegList {
   }
 };
 
-// value of v[j] for a run-time j in [0,8): 7 selects instead of a register-indexed load
-__device__ __forceinline__ float pick8(const float* v, int j) {
-  const float a0 = (j & 1) ? v[1] : v[0], a1 = (j & 1) ? v[3] : v[2];
-  const float a2 = (j & 1) ? v[5] : v[4], a3 = (j & 1) ? v[7] : v[6];
-  const float b0 = (j & 2) ? a1 : a0, b1 = (j & 2) ? a3 : a2;
-  return (j & 4) ? b1 : b0;
+__device__ __forceinline__ float max8(const float* v) {
+  return fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, float s, uint32_t r) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(__float_as_uint(s)), "r"(r) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v2(uint32_t addr, float& s, uint32_t& r) {
+  uint32_t u;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u), "=r"(r) : "r"(addr) : "memory");
+  s = __uint_as_float(u);
 }
 
-template <int K, bool DBG, bool PAIR>
+// K = register list length; PAIR = CTA pairs (cta_group::2, 256 queries per block); TWO = two
+// accumulators (T2I, T2T) of 128 columns each, fused in the epilogue with their own weights
+// (otherwise ONE accumulator of 256 gallery rows: single gallery, or both galleries with equal
+// weights accumulated over 2*kc K chunks).
+template <int K, bool PAIR, bool TWO>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g0,
                 const __grid_constant__ CUtensorMap map_g1, MmaArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_mma_raw[];
   // identical shared-memory layout in both CTAs of a pair (the MMA addresses the peer by offset)
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_mma_raw + 1023) & ~(uintptr_t)1023);
-  const int n_tile = a.n_tile;
-  const int G = a.s.G;
-  const uint32_t a_bytes = (uint32_t)kBlockM * 128u;
-  const uint32_t b_bytes = PAIR ? 128u * 128u : (uint32_t)n_tile * 128u;     // per TMA box of gallery rows
-  const uint32_t stage_bytes = a_bytes + (PAIR ? b_bytes : (uint32_t)G * b_bytes);
-  float* buf_s = reinterpret_cast<float*>(smem + (size_t)a.stages * stage_bytes);      // [kBufCap][kEpiThreads]
-  uint32_t* buf_r = reinterpret_cast<uint32_t*>(buf_s + kBufCap * kEpiThreads);          // [kBufCap][kEpiThreads]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(buf_r + kBufCap * kEpiThreads);
+  constexpr int n_tile = TWO ? 128 : 256;                       // gallery rows per tile
+  constexpr uint32_t a_bytes = (uint32_t)kBlockM * 128u;
+  constexpr uint32_t b_box = PAIR ? 128u : (uint32_t)n_tile;     // gallery rows per TMA box
+  constexpr uint32_t b_bytes = b_box * 128u;
+  constexpr uint32_t stage_bytes = a_bytes + (PAIR ? b_bytes : 256u * 128u);
+  const uint32_t buf_u32 = ptx::smem_u32(smem + (size_t)a.stages * stage_bytes);      // [kBufCap][kEpiThreads] x 8 B
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes + (size_t)kBufCap * kEpiThreads * 8);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;      // [2]
   uint64_t* tempty_bar = tfull_bar + 2;              // [2]
@@ -321,7 +348,15 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
   const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // persistent CTA or CTA pair
   const int units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const long long w_lo = a.W * unit / units, w_hi = a.W * (unit + 1) / units;
+  const bool dbg = a.dbg != nullptr;
+  long long w_lo, w_hi;                      // this unit's range of the flattened (query block, tile) grid
+  if (a.upq > 0) {
+    const int j = unit % a.upq;
+    const long long base = (long long)(unit / a.upq) * a.n_t;
+    w_lo = base + (long long)a.n_t * j / a.upq; w_hi = base + (long long)a.n_t * (j + 1) / a.upq;
+  } else {
+    w_lo = a.W * unit / units; w_hi = a.W * (unit + 1) / units;
+  }
 
   if (threadIdx.x == 0) {
     // full: one arrival (the leader's expect_tx covers both CTAs' bytes; the peer's TMA loads complete
@@ -330,7 +365,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiWarps : kEpiWarps); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&map_q); ptx::prefetch_tmap(&map_g0);
-    if (G > 1) ptx::prefetch_tmap(&map_g1);
+    if (a.s.G > 1) ptx::prefetch_tmap(&map_g1);
   }
   if (warp == 1) { if (PAIR) ptx::tmem_alloc_pair(tmem_ptr, 512); else ptx::tmem_alloc(tmem_ptr, 512); }
   ptx::tc_fence_before();
@@ -342,129 +377,137 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ================================================================= TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      long long w_empty = 0; const long long t_begin = tick<DBG>();
+      long long w_empty = 0; const long long t_begin = dbg ? clock64() : 0;
       int tr = 0;
-      if (PAIR) {
-        // this CTA's 128 query rows + its half of the stacked gallery chunk; bytes land on the leader's barrier
-        const CUtensorMap* map_b = (G > 1 && rank == 1) ? &map_g1 : &map_g0;
-        const int b_row_off = G > 1 ? 0 : (int)rank * 128;
-        for (long long w = w_lo; w < w_hi; ++w) {
-          const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
-          for (int kc = 0; kc < a.kc; ++kc) {
-            ptx::mbar_wait_timed<DBG>(&empty_bar[stage], phase ^ 1, w_empty);
-            if (DBG && a.dbg && blockIdx.x < 2 && tr < kTraceLen) a.dbg[kTraceBase + (blockIdx.x * 4 + 0) * kTraceLen + tr] = clock64();
-            unsigned char* sa = smem + (size_t)stage * stage_bytes;
+      const uint32_t tx = PAIR ? 2u * stage_bytes : (uint32_t)a.a_rows * 128u + 256u * 128u;
+      for (long long w = w_lo; w < w_hi; ++w) {
+        const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
+        for (int kcc = 0; kcc < a.kc_total; ++kcc) {
+          const int g = kcc >= a.kc ? 1 : 0;              // merged mode: second gallery's chunks follow the first's
+          const int kx = (kcc - g * a.kc) * kBlockK;
+          mbar_wait_dbg(&empty_bar[stage], phase ^ 1, dbg, w_empty);
+          if (dbg && blockIdx.x < 2 && tr < kTraceLen) a.dbg[kTraceBase + (blockIdx.x * 4 + 0) * kTraceLen + tr] = clock64();
+          unsigned char* sa = smem + (size_t)stage * stage_bytes;
+          if (PAIR) {
+            // this CTA's 128 query rows + its half of the gallery chunk; bytes land on the leader's barrier
             const uint32_t lbar = ptx::map_to_cta(ptx::smem_u32(&full_bar[stage]), 0);
-            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
-            ptx::tma_load_2d_pair(sa, &map_q, lbar, kc * kBlockK, qb * (2 * kBlockM) + (int)rank * kBlockM);
-            ptx::tma_load_2d_pair(sa + a_bytes, map_b, lbar, kc * kBlockK, t * n_tile + b_row_off);
-            if (DBG && a.dbg && blockIdx.x < 2 && tr < kTraceLen) { a.dbg[kTraceBase + (blockIdx.x * 4 + 1) * kTraceLen + tr] = clock64(); ++tr; }
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
-          }
-        }
-      } else {
-        const uint32_t tx = (uint32_t)a.a_rows * 128u + (uint32_t)G * b_bytes;
-        for (long long w = w_lo; w < w_hi; ++w) {
-          const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
-          for (int kc = 0; kc < a.kc; ++kc) {
-            ptx::mbar_wait_timed<DBG>(&empty_bar[stage], phase ^ 1, w_empty);
-            if (DBG && a.dbg && blockIdx.x < 2 && tr < kTraceLen) a.dbg[kTraceBase + (blockIdx.x * 4 + 0) * kTraceLen + tr] = clock64();
-            unsigned char* sa = smem + (size_t)stage * stage_bytes;
+            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], tx);
+            ptx::tma_load_2d_pair(sa, &map_q, lbar, kx, qb * (2 * kBlockM) + (int)rank * kBlockM);
+            const CUtensorMap* mb = TWO ? (rank ? &map_g1 : &map_g0) : (g ? &map_g1 : &map_g0);
+            ptx::tma_load_2d_pair(sa + a_bytes, mb, lbar, kx, t * n_tile + (TWO ? 0 : (int)rank * 128));
+          } else {
             ptx::mbar_expect_tx(&full_bar[stage], tx);
-            ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kc * kBlockK, qb * kBlockM);
-            ptx::tma_load_2d(sa + a_bytes, &map_g0, &full_bar[stage], kc * kBlockK, t * n_tile);
-            if (G > 1) ptx::tma_load_2d(sa + a_bytes + b_bytes, &map_g1, &full_bar[stage], kc * kBlockK, t * n_tile);
-            if (DBG && a.dbg && blockIdx.x < 2 && tr < kTraceLen) { a.dbg[kTraceBase + (blockIdx.x * 4 + 1) * kTraceLen + tr] = clock64(); ++tr; }
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kx, qb * kBlockM);
+            if (TWO) {
+              ptx::tma_load_2d(sa + a_bytes, &map_g0, &full_bar[stage], kx, t * n_tile);
+              ptx::tma_load_2d(sa + a_bytes + b_bytes, &map_g1, &full_bar[stage], kx, t * n_tile);
+            } else {
+              ptx::tma_load_2d(sa + a_bytes, g ? &map_g1 : &map_g0, &full_bar[stage], kx, t * n_tile);
+            }
           }
+          if (dbg && blockIdx.x < 2 && tr < kTraceLen) { a.dbg[kTraceBase + (blockIdx.x * 4 + 1) * kTraceLen + tr] = clock64(); ++tr; }
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (DBG && a.dbg) { a.dbg[blockIdx.x * 16 + 0] = w_empty; a.dbg[blockIdx.x * 16 + 1] = tick<DBG>() - t_begin; }
+      if (dbg) { a.dbg[blockIdx.x * 16 + 0] = w_empty; a.dbg[blockIdx.x * 16 + 1] = clock64() - t_begin; }
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0;
-      // The gallery chunks of a stage form ONE K-major tile of 256 rows (T2I rows then T2T rows, or
-      // 256 rows of the single gallery; split across the two CTAs in pair mode): a single MMA with
-      // N = 256 fills the whole accumulator buffer and reads the query chunk once.
-      const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, G * n_tile);
+      // The gallery chunk(s) of a stage form ONE K-major tile of 256 rows (T2I rows then T2T rows, or
+      // 256 rows of one gallery; split across the two CTAs in pair mode): a single MMA with N = 256
+      // fills the whole accumulator buffer and reads the query chunk once.
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, 256);
       long long it = 0;
-      long long w_full = 0, w_tempty = 0; const long long t_begin = tick<DBG>();
+      long long w_full = 0, w_tempty = 0; const long long t_begin = dbg ? clock64() : 0;
       int tr = 0;
       for (long long w = w_lo; w < w_hi; ++w, ++it) {
         const int buf = (int)(it & 1);
         const uint32_t bphase = (uint32_t)((it >> 1) & 1);
-        ptx::mbar_wait_timed<DBG>(&tempty_bar[buf], bphase ^ 1, w_tempty);
+        mbar_wait_dbg(&tempty_bar[buf], bphase ^ 1, dbg, w_tempty);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * G) * (uint32_t)n_tile;
-        for (int kc = 0; kc < a.kc; ++kc) {
-          ptx::mbar_wait_timed<DBG>(&full_bar[stage], phase, w_full);
-          if (DBG && a.dbg && blockIdx.x == 0 && tr < kTraceLen) a.dbg[kTraceBase + 2 * kTraceLen + tr] = clock64();
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
+        for (int kcc = 0; kcc < a.kc_total; ++kcc) {
+          mbar_wait_dbg(&full_bar[stage], phase, dbg, w_full);
+          if (dbg && blockIdx.x == 0 && tr < kTraceLen) a.dbg[kTraceBase + 2 * kTraceLen + tr] = clock64();
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + a_bytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            if (PAIR) ptx::mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
-            else ptx::mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+            if (PAIR) ptx::mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kcc | k) ? 1u : 0u);
+            else ptx::mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kcc | k) ? 1u : 0u);
           }
           // frees the smem stage (in both CTAs) when these MMAs retire
           if (PAIR) ptx::mma_commit_pair(&empty_bar[stage]); else ptx::mma_commit(&empty_bar[stage]);
-          if (DBG && a.dbg && blockIdx.x == 0 && tr < kTraceLen) { a.dbg[kTraceBase + 3 * kTraceLen + tr] = clock64(); ++tr; }
+          if (dbg && blockIdx.x == 0 && tr < kTraceLen) { a.dbg[kTraceBase + 3 * kTraceLen + tr] = clock64(); ++tr; }
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         // accumulators of this tile are complete
         if (PAIR) ptx::mma_commit_pair(&tfull_bar[buf]); else ptx::mma_commit(&tfull_bar[buf]);
       }
-      if (DBG && a.dbg) { a.dbg[blockIdx.x * 16 + 2] = w_full; a.dbg[blockIdx.x * 16 + 3] = w_tempty; a.dbg[blockIdx.x * 16 + 4] = tick<DBG>() - t_begin; }
+      if (dbg) { a.dbg[blockIdx.x * 16 + 2] = w_full; a.dbg[blockIdx.x * 16 + 3] = w_tempty; a.dbg[blockIdx.x * 16 + 4] = clock64() - t_begin; }
     }
   } else {
     // ================================================================= epilogue (warps 2..9)
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;                    // which half of the tile's columns
+    const int half = (warp - 2) >> 2;                    // which half of the tile's score columns
     const int et = (warp - 2) * 32 + lane;               // epilogue thread id, 0..255
     const int qrow = (int)rank * kBlockM + quad * 32 + lane;     // query row inside the block
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t my_buf = buf_u32 + (uint32_t)et * 8u;  // append-buffer entry i of this thread: + i * kEpiThreads * 8
     const float w0 = a.s.w[0], w1 = a.s.w[1];
     const int mode = a.s.mode;
-    const int half_cols = n_tile >> 1;
+    constexpr int kHalfCols = n_tile / 2;                // score columns per warp and tile
     RegList<K> list;
     list.reset();
-    float thr = -INFINITY;
+    float thr = INFINITY;
     int bcnt = 0;                                        // entries in this thread's append buffer
     int32_t cnt = 0;
     float blo = 0.f, bhi = 0.f;
     int cur_qb = -1;
+    bool qvalid = false;
+    int qg = 0;
     const long long Wt = a.W;
     long long it = 0;
-    long long w_tfull = 0, t_fold = 0, t_ld = 0, t_sm = 0, t_app = 0; const long long t_begin = tick<DBG>();
-    const uint32_t tempty0 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tempty_bar[0]), 0) : ptx::smem_u32(&tempty_bar[0]);
-    const uint32_t tempty1 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tempty_bar[1]), 0) : ptx::smem_u32(&tempty_bar[1]);
+    long long w_tfull = 0, t_fold = 0; const long long t_begin = dbg ? clock64() : 0;
+    const uint32_t tempty0 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
+    const uint32_t tempty1 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tempty_bar[1]), 0) : 0u;
 
     // fold every lane's append buffer into its register list, in lock-step
     auto fold = [&]() {
-      const long long tf0 = tick<DBG>();
+      const long long tf0 = dbg ? clock64() : 0;
       const int nmax = __reduce_max_sync(0xffffffffu, bcnt);
       for (int i = 0; i < nmax; ++i) {
         if (i < bcnt) {
-          const float s = buf_s[i * kEpiThreads + et];
+          float s; uint32_t r;
+          ld_shared_v2(my_buf + (uint32_t)i * (kEpiThreads * 8u), s, r);
           if (s > thr) {
-            list.insert(s, buf_r[i * kEpiThreads + et]);
+            list.insert(s, r);
             thr = list.threshold();
           }
         }
       }
       bcnt = 0;
-      t_fold += tick<DBG>() - tf0;
+      if (dbg) t_fold += clock64() - tf0;
+    };
+    // predicated, unrolled: every survivor of an 8-column run goes to the append buffer
+    auto append8 = [&](const float* v, uint32_t row) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (v[j] > thr) {
+          st_shared_v2(my_buf + (uint32_t)bcnt * (kEpiThreads * 8u), v[j], row + (uint32_t)j);
+          ++bcnt;
+        }
+      }
     };
     auto flush = [&](int qb) {
       if (qb < 0) return;
       const long long wq = (long long)qb * a.n_t;
       const int c_first = (int)(((wq + 1) * units - 1) / Wt);
-      const int slot = (unit - c_first) * 2 + half;
-      const int qg = qb * a.q_blk + qrow;
+      const int slot = (a.upq > 0 ? unit % a.upq : unit - c_first) * 2 + half;
       if (mode == kModeTopk) {
         fold();
         uint64_t* dst = a.s.part_keys + ((size_t)slot * a.q_pad + qg) * a.s.K;
@@ -481,69 +524,54 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (qb != cur_qb) {
         flush(cur_qb);
         cur_qb = qb;
+        qg = qb * a.q_blk + qrow;
+        qvalid = qg < a.s.Q;
         list.reset();
-        thr = -INFINITY;
+        thr = qvalid ? -INFINITY : INFINITY;             // padded query rows never collect candidates
         cnt = 0;
-        if (mode == kModeCount) {
-          const int qg0 = qb * a.q_blk + qrow;
-          blo = a.s.band_lo[qg0]; bhi = a.s.band_hi[qg0];   // padded rows hold +huge: never count
-        }
+        if (mode == kModeCount) { blo = a.s.band_lo[qg]; bhi = a.s.band_hi[qg]; }   // padded rows hold +huge: never count
       }
       const int buf = (int)(it & 1);
       const uint32_t bphase = (uint32_t)((it >> 1) & 1);
-      ptx::mbar_wait_timed<DBG>(&tfull_bar[buf], bphase, w_tfull);
+      mbar_wait_dbg(&tfull_bar[buf], bphase, dbg, w_tfull);
       ptx::tc_fence_after();
-      const int qg = qb * a.q_blk + qrow;
-      const bool qvalid = qg < a.s.Q;
       const long long row0 = (long long)t * n_tile;
       const int ncols = (int)min((long long)n_tile, a.s.M - row0);
-      const uint32_t acc0 = lane_addr + (uint32_t)(buf * G) * (uint32_t)n_tile;
-      for (int c0 = half * half_cols; c0 < (half + 1) * half_cols; c0 += 16) {
-        if (c0 >= ncols) break;                          // warp-uniform
-        uint32_t ra[16], rb[16];
-        const long long tl0 = tick<DBG>();
+      const bool full_tile = ncols == n_tile;            // warp-uniform
+      const uint32_t acc0 = lane_addr + (uint32_t)buf * 256u;
+      const int cbeg = half * kHalfCols;
+      const int nch = max(0, min(kHalfCols, ncols - cbeg) + 15) >> 4;       // 16-column chunks for this warp
+
+      auto load = [&](int c0, uint32_t (&ra)[16], uint32_t (&rb)[16]) {
         tmem_ld16(acc0 + (uint32_t)c0, ra);
-        if (G > 1) tmem_ld16(acc0 + (uint32_t)n_tile + (uint32_t)c0, rb);
-        ptx::tmem_ld_wait();
-        const long long tl1 = tick<DBG>();
-        t_ld += tl1 - tl0;
+        if (TWO) tmem_ld16(acc0 + 128u + (uint32_t)c0, rb);
+      };
+      auto process = [&](int c0, const uint32_t (&ra)[16], const uint32_t (&rb)[16]) {
         float sv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float s = w0 * __uint_as_float(ra[j]);
-          if (G > 1) s = fmaf(w1, __uint_as_float(rb[j]), s);
+          if (TWO) s = fmaf(w1, __uint_as_float(rb[j]), s);
           sv[j] = s;
         }
-        const bool full = c0 + 16 <= ncols;              // warp-uniform
         if (mode == kModeTopk) {
-          // per 8-column run: fast reject on the run's maximum, else append the survivors
+          if (!full_tile) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float m = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) m = (full || c0 + h * 8 + j < ncols) ? fmaxf(m, sv[h * 8 + j]) : m;
-            if (qvalid && m > thr) {
-              const long long ta0 = tick<DBG>();
-              uint32_t mask = 0;
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                mask |= (sv[h * 8 + j] > thr && (full || c0 + h * 8 + j < ncols)) ? (1u << j) : 0u;
-              while (mask) {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1;
-                buf_s[bcnt * kEpiThreads + et] = pick8(sv + h * 8, j);
-                buf_r[bcnt * kEpiThreads + et] = (uint32_t)(row0 + c0 + h * 8 + j);
-                ++bcnt;
-              }
-              t_app += tick<DBG>() - ta0;
-            }
+            for (int j = 0; j < 16; ++j) sv[j] = (c0 + j < ncols) ? sv[j] : -INFINITY;
+          }
+          const float m0 = max8(sv), m1 = max8(sv + 8);
+          if (__any_sync(0xffffffffu, fmaxf(m0, m1) > thr)) {
+            const uint32_t r = (uint32_t)(row0 + c0);
+            if (m0 > thr) append8(sv, r);
+            if (__any_sync(0xffffffffu, bcnt >= kBufTrigger)) fold();
+            if (m1 > thr) append8(sv + 8, r + 8u);
             if (__any_sync(0xffffffffu, bcnt >= kBufTrigger)) fold();
           }
         } else if (mode == kModeCount) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float s = sv[j];
-            const bool in = full || c0 + j < ncols;
+            const bool in = full_tile || c0 + j < ncols;
             if (in && s > bhi) ++cnt;
             else if (in && s >= blo) {
               const unsigned int slot = atomicAdd(a.s.amb_counter, 1u);
@@ -555,8 +583,22 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             float* dst = a.s.dense + (size_t)qg * a.s.ld + row0 + c0;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (full || c0 + j < ncols) dst[j] = sv[j];
+              if (full_tile || c0 + j < ncols) dst[j] = sv[j];
           }
+        }
+      };
+
+      // double-buffered TMEM reads: chunk i+1 is in flight while chunk i is processed
+      uint32_t ra0[16], rb0[16], ra1[16], rb1[16];
+      if (nch > 0) load(cbeg, ra0, rb0);
+      for (int i = 0; i < nch; i += 2) {
+        ptx::tmem_ld_wait();
+        if (i + 1 < nch) load(cbeg + (i + 1) * 16, ra1, rb1);
+        process(cbeg + i * 16, ra0, rb0);
+        if (i + 1 < nch) {
+          ptx::tmem_ld_wait();
+          if (i + 2 < nch) load(cbeg + (i + 2) * 16, ra0, rb0);
+          process(cbeg + (i + 1) * 16, ra1, rb1);
         }
       }
       // release this accumulator buffer to the (leader's) MMA warp
@@ -568,7 +610,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
     }
     flush(cur_qb);
-    if (DBG && a.dbg && warp == 2 && lane == 0) { a.dbg[blockIdx.x * 16 + 5] = w_tfull; a.dbg[blockIdx.x * 16 + 6] = t_fold; a.dbg[blockIdx.x * 16 + 7] = tick<DBG>() - t_begin; a.dbg[blockIdx.x * 16 + 8] = t_ld; a.dbg[blockIdx.x * 16 + 9] = t_sm; a.dbg[blockIdx.x * 16 + 10] = t_app; }
+    if (dbg && warp == 2 && lane == 0) { a.dbg[blockIdx.x * 16 + 5] = w_tfull; a.dbg[blockIdx.x * 16 + 6] = t_fold; a.dbg[blockIdx.x * 16 + 7] = clock64() - t_begin; }
   }
 
   // no CTA of a pair may leave (or free TMEM) while its peer can still signal its barriers
@@ -615,10 +657,10 @@ inline int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int D,
   return 0;
 }
 
-template <int K, bool DBG, bool PAIR>
-inline int mma_launch_kdt(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
+template <int K, bool PAIR, bool TWO>
+inline int mma_launch_kpt(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
                           const MmaPlan& pl, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<K, DBG, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
+  cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<K, PAIR, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "smem attribute: %s", cudaGetErrorString(e)); return 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)pl.ctas);
@@ -630,7 +672,7 @@ inline int mma_launch_kdt(const CUtensorMap& mq, const CUtensorMap& m0, const CU
   attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, scan_mma_kernel<K, DBG, PAIR>, mq, m0, m1, ma);
+  e = cudaLaunchKernelEx(&cfg, scan_mma_kernel<K, PAIR, TWO>, mq, m0, m1, ma);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
@@ -638,8 +680,8 @@ inline int mma_launch_kdt(const CUtensorMap& mq, const CUtensorMap& m0, const CU
 template <int K>
 inline int mma_launch_k(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
                         const MmaPlan& pl, cudaStream_t st) {
-  if (pl.pair) return ma.dbg ? mma_launch_kdt<K, true, true>(mq, m0, m1, ma, pl, st) : mma_launch_kdt<K, false, true>(mq, m0, m1, ma, pl, st);
-  return ma.dbg ? mma_launch_kdt<K, true, false>(mq, m0, m1, ma, pl, st) : mma_launch_kdt<K, false, false>(mq, m0, m1, ma, pl, st);
+  if (pl.pair) return pl.two ? mma_launch_kpt<K, true, true>(mq, m0, m1, ma, pl, st) : mma_launch_kpt<K, true, false>(mq, m0, m1, ma, pl, st);
+  return pl.two ? mma_launch_kpt<K, false, true>(mq, m0, m1, ma, pl, st) : mma_launch_kpt<K, false, false>(mq, m0, m1, ma, pl, st);
 }
 
 inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
@@ -652,7 +694,8 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
   MmaArgs ma;
   ma.s = s;
   ma.n_tile = pl.n_tile; ma.n_qb = pl.n_qb; ma.n_t = pl.n_t; ma.stages = pl.stages; ma.kc = pl.kc;
-  ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.q_blk = pl.q_blk;
+  ma.merged = pl.merged; ma.kc_total = pl.merged ? 2 * pl.kc : pl.kc;
+  ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.q_blk = pl.q_blk; ma.upq = pl.upq;
   ma.W = (long long)pl.n_qb * pl.n_t;
   ma.dbg = nullptr;
   static const bool debug = getenv("KEMR_MMA_DEBUG") != nullptr;
@@ -685,9 +728,9 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
         if (t < tmin) { tmin = t; cmin = c; }
         if (t > tmax) { tmax = t; cmax = c; }
       }
-      fprintf(stderr, "[kemr mma dbg] pair=%d n_tile=%d K=%d ctas=%d tiles/unit=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f (min %lld @cta %d, max %lld @cta %d; max cta: wait_full=%lld wait_tempty=%lld) | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f ld=%.0f score+mask=%.0f append=%.0f cycles\n",
-              pl.pair, pl.n_tile, pl.K, pl.ctas, (double)ma.W / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
-              tmin, cmin, tmax, cmax, h[(size_t)cmax * 16 + 2], h[(size_t)cmax * 16 + 3], avg[5], avg[6], avg[7], avg[8], avg[9], avg[10]);
+      fprintf(stderr, "[kemr mma dbg] pair=%d merged=%d n_tile=%d K=%d ctas=%d tiles/unit=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f (min %lld @cta %d, max %lld @cta %d; max cta: wait_full=%lld wait_tempty=%lld) | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f  cycles\n",
+              pl.pair, pl.merged, pl.n_tile, pl.K, pl.ctas, (double)ma.W / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
+              tmin, cmin, tmax, cmax, h[(size_t)cmax * 16 + 2], h[(size_t)cmax * 16 + 3], avg[5], avg[6], avg[7]);
       if (getenv("KEMR_MMA_DEBUG_TRACE")) {
         std::vector<long long> tr((size_t)8 * kTraceLen);
         cudaMemcpy(tr.data(), ma.dbg + kTraceBase, tr.size() * 8, cudaMemcpyDeviceToHost);
