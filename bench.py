@@ -292,7 +292,7 @@ def run_ours(args, cfg):
                                "gallery resident in HBM", "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": 2 * args.steps, "roofline": roof, "clocks": clocks,
                 "uncertified_queries": n_uncert, "sm_count": info["sm_count"],
-                "scan_path": "tcgen05" if (info["has_tcgen05"] and Q >= 5) else "warp-dot"}
+                "scan_path": "tcgen05" if engine.scan_plan(Q, M, D, G, k_sel, wi == wt)["path"] == _lib.PATH_MMA else "warp-dot"}
         # CPU baseline beside it: bounded sample of the same workload on the host cores
         if world == 1 and not args.no_cpu_baseline:
             s2, Q2, M2 = cpu_sample(cfg, 1000)

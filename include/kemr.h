@@ -81,6 +81,12 @@ int kemr_quantize_rows(const float* src, uint16_t* dst, int64_t rows, int D, int
 int kemr_synth_rows(uint16_t* dst, int64_t rows, int D, uint64_t seed, int64_t row_base,
                     kemr_stream_t stream);
 
+/* ---- which scan kernel KEMR_PATH_AUTO would run for this shape on the current device
+ * (KEMR_PATH_WARP or KEMR_PATH_MMA; the tcgen05 kernel needs enough gallery tiles for the candidate
+ * lists k_sel asks for), and how many candidate lists ("parts") per query it would leave.
+ * galleries = 1 or 2; equal_weights != 0 when both fusion weights are the same number. */
+int kemr_scan_plan(int Q, int64_t M, int D, int galleries, int k_sel, int equal_weights, int* path, int* parts);
+
 /* ---- workspace sizing for kemr_scan_topk / kemr_rank_count / kemr_score_matrix */
 size_t kemr_workspace_bytes(int Q, int64_t M, int D, int k_sel, int64_t max_hits_per_query);
 

@@ -18,7 +18,7 @@ EXPORTS = (
     "kemr_workspace_bytes", "kemr_scan_topk", "kemr_score_pairs", "kemr_rank_count", "kemr_score_matrix",
     "kemr_matrix_rank", "kemr_matrix_topk", "kemr_matrix_fuse", "kemr_metrics_reduce",
     "kemr_metrics_reduce_host", "kemr_merge_topk", "kemr_index_create", "kemr_index_destroy",
-    "kemr_index_search_host", "kemr_set_scan_done_event",
+    "kemr_index_search_host", "kemr_set_scan_done_event", "kemr_scan_plan",
 )
 
 
@@ -38,6 +38,7 @@ def _declare(lib):
     lib.kemr_device_info.argtypes = [C.POINTER(i32)] * 4
     lib.kemr_quantize_rows.argtypes = [p, p, i64, i32, i32, p]
     lib.kemr_synth_rows.argtypes = [p, i64, i32, u64, i64, p]
+    lib.kemr_scan_plan.argtypes = [i32, i64, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.kemr_workspace_bytes.restype = sz
     lib.kemr_workspace_bytes.argtypes = [i32, i64, i32, i32, i64]
     lib.kemr_scan_topk.argtypes = [p, i32, p, p, i64, i32, f64, f64, f64, p, p, p, i64, i32, i32, f64, i64,

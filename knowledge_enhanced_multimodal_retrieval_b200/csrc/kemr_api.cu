@@ -135,15 +135,18 @@ static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, 
     pl->path = path;
   }
   if (path == KEMR_PATH_AUTO) {
-    // tensor-core kernel when there is a batch to amortise its prologue; warp-dot for the
-    // latency-bound tiny batches
-    pl->path = (dv.major == 10 && Q >= 5 && mma_supported(D, K)) ? KEMR_PATH_MMA : KEMR_PATH_WARP;
+    // tensor-core kernel when there is a batch to amortise its prologue and the shape can be planned
+    // (enough gallery tiles for the candidate lists k_sel needs); warp-dot for the latency-bound tiny
+    // batches and as the general fallback
+    pl->path = KEMR_PATH_WARP;
+    if (dv.major == 10 && Q >= 5 && mma_supported(D, K) && mma_make_plan(Q, M, D, G, K, mode, dv.sms, equal_weights, &pl->mma) == 0)
+      pl->path = KEMR_PATH_MMA;
   }
   if (pl->path == KEMR_PATH_MMA) {
     if (dv.major != 10) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path needs compute capability 10.x (have %d.%d)", dv.major, dv.minor);
     if (!mma_supported(D, K)) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path: unsupported D=%d / k_sel=%d", D, K);
     int rc = mma_make_plan(Q, M, D, G, K, mode, dv.sms, equal_weights, &pl->mma);
-    if (rc) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path: cannot plan this shape");
+    if (rc) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path: cannot plan this shape (k_sel=%d needs more gallery tiles than M=%lld offers)", K, (long long)M);
     pl->P = pl->mma.parts;
     pl->Kp = pl->mma.K;
     return KEMR_OK;
@@ -156,6 +159,19 @@ static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, 
   P = (int)std::min<int64_t>(P, std::max<int64_t>(1, (M + 15) / 16));
   pl->P = P;
   pl->Kp = K;
+  return KEMR_OK;
+}
+
+extern "C" int kemr_scan_plan(int Q, int64_t M, int D, int galleries, int k_sel, int equal_weights, int* path, int* parts) {
+  if (Q <= 0 || M <= 0 || D <= 0 || D % 8 || D > kMaxD || galleries < 1 || galleries > 2 || k_sel < 1 || k_sel > kMaxKSel)
+    return fail(KEMR_ERR_ARG, "scan_plan: bad argument");
+  DevInfo dv;
+  int rc = dev_info(&dv);
+  if (rc) return rc;
+  ScanPlan pl;
+  if ((rc = make_plan(Q, M, D, galleries, k_sel, kModeTopk, KEMR_PATH_AUTO, equal_weights != 0, dv, &pl))) return rc;
+  if (path) *path = pl.path;
+  if (parts) *parts = pl.P;
   return KEMR_OK;
 }
 
@@ -222,7 +238,7 @@ extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, c
   a.q = q; a.Q = Q; a.gal[0] = gal_a; a.gal[1] = gal_b; a.G = G; a.M = M; a.D = D;
   a.w[0] = (float)w_a; a.w[1] = (float)w_b; a.mode = kModeTopk; a.K = pl.Kp; a.part_keys = part_keys;
   if (pl.path == KEMR_PATH_MMA) {
-    CUDA_TRY(cudaMemsetAsync(part_keys, 0, need, st));
+    if (!pl.mma.all_slots) CUDA_TRY(cudaMemsetAsync(part_keys, 0, need, st));   // unwritten slots must read as empty
     if ((rc = mma_launch(a, pl.mma, st))) return fail(KEMR_ERR_CUDA, "tcgen05 scan launch failed: %s", mma_last_error());
   } else {
     if ((rc = launch_warp_scan(a, pl, st))) return rc;

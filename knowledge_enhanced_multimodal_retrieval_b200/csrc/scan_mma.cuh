@@ -66,6 +66,8 @@ struct MmaPlan {
   int K = 0;              // list length (8, 16, 24, 32)
   int pair = 0;           // 1: CTA pairs (cta_group::2), 256 queries per block
   int upq = 0;            // units (CTAs or pairs) per query block; 0 = flattened (block, tile) ranges
+  int vq = 1;             // virtual parts per query block: lists are flushed and restarted at these boundaries
+  int all_slots = 0;      // 1: every part slot of every query row is written (no memset needed)
   int two = 0;            // 1: two accumulators (T2I, T2T) with their own weights
   int merged = 0;         // 1: two galleries, equal weights: one accumulator over 2*kc K chunks
   int q_blk = 0;          // queries per block (128, or 256 for CTA pairs)
@@ -73,12 +75,12 @@ struct MmaPlan {
 };
 
 inline bool mma_built() { return true; }
-inline bool mma_supported(int D, int K) { return D % 8 == 0 && D >= 8 && D <= kMaxD && K >= 1 && K <= 32; }
+inline bool mma_supported(int D, int K) { return D % 8 == 0 && D >= 8 && D <= kMaxD && K >= 1 && K <= kMaxKSel; }
 
 static thread_local char g_mma_error[256] = "";
 inline const char* mma_last_error() { return g_mma_error; }
 
-inline int mma_round_k(int K) { return K <= 8 ? 8 : K <= 16 ? 16 : K <= 24 ? 24 : 32; }
+constexpr int kPlanMaxParts = 304;     // candidate lists per query any plan may use (workspace bound: 2*148 + 8)
 
 inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sms, bool equal_weights, MmaPlan* p) {
   (void)mode;
@@ -123,11 +125,47 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
     }
   }
   p->ctas = p->pair ? 2 * nu : nu;
-  p->parts = 2 * parts;
   p->a_rows = (p->pair || Q >= kBlockM) ? kBlockM : (Q + 7) / 8 * 8;
-  // Many parts per query: each keeps a short list (the global top-k spreads over the parts); the
-  // select kernel's certificate flags the rare query whose winners crowd into one part.
-  p->K = mma_round_k(p->parts >= 12 && K <= 24 ? std::min(K, 8) : K);
+  // Candidate lists.  A query's rows are cut into segments (unit boundaries, plus `vq` virtual
+  // boundaries per block when more are needed); every segment yields two K-entry lists (one per
+  // column half).  Each list keeps the exact top-K of its rows, so the K_sel best rows of the query
+  // survive unless K or more of them fall into one list.  With the winners spread at random over L
+  // lists that happens with probability <= L * P[Poisson(K_sel / L) >= K] per query; (K, L) is chosen
+  // so that this stays below 2e-6 (a list that does overflow is caught by the select kernel's
+  // certificate and the query is re-run), taking the cheapest of K = 8 and 16 (cost ~ keys L*K times
+  // the insert cost ~K), and K = 32 only when neither fits.  Large k (top-100) therefore runs with short register lists
+  // and MANY parts instead of long lists.
+  const int span = parts;                          // natural segments per query block
+  auto overflow_prob = [](int ksel, int L, int Kc) {
+    if (ksel < Kc) return 0.0;
+    const double m = (double)ksel / L;
+    double term = exp(-m);
+    for (int i = 1; i <= Kc; ++i) term *= m / i;
+    double sum = term;
+    for (int i = Kc + 1; i < Kc + 64; ++i) { term *= m / i; sum += term; }
+    return sum * L;
+  };
+  const int seg_cap = (int)std::min<int64_t>(std::max<int64_t>(span, (int64_t)p->n_t), kPlanMaxParts / 2 - span + 1);
+  int Ksel = 0, vq = 1;
+  long long best_keys = 1ll << 60;
+  for (int Kc = 8; Kc <= 32; Kc *= 2) {
+    if (Kc == 32 && Ksel) break;
+    for (int seg = span; seg <= std::max(span, seg_cap); ++seg) {
+      const int segs = seg == span ? span : seg + span - 1;            // list slots when virtual parts are added
+      if (2 * segs > kPlanMaxParts) break;
+      if (overflow_prob(K, 2 * seg, Kc) <= 2e-6) {
+        const long long keys = 2ll * segs * Kc * Kc;
+        if (keys < best_keys) { best_keys = keys; Ksel = Kc; vq = seg == span ? 1 : seg; }
+        break;
+      }
+      if (seg >= p->n_t) break;                    // cannot cut finer than one tile per segment
+    }
+  }
+  if (!Ksel) return 1;
+  p->K = Ksel;
+  p->vq = vq;
+  p->parts = 2 * (vq + span - 1);
+  p->all_slots = (vq == 1 && p->upq > 0) ? 1 : 0;
   const size_t stage = (size_t)kBlockM * 128 + (p->pair ? (size_t)128 * 128 : (size_t)256 * 128);
   const size_t epi = (size_t)kBufCap * kEpiThreads * 8;
   p->stages = (int)std::min<size_t>(kMaxStages, (kSmemBudget - 2048 - epi) / stage);
@@ -262,7 +300,7 @@ struct MmaArgs {
   ScanArgs s;
   int n_tile;       // gallery rows per tile (128 with two accumulators, else 256)
   int merged;       // both galleries accumulate into ONE accumulator (equal weights): 2*kc K chunks
-  int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, upq;
+  int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, upq, vq;
   long long W;
   long long* dbg;   // optional [ctas][16] cycle counters + stage trace (KEMR_MMA_DEBUG=1)
 };
@@ -467,7 +505,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     int bcnt = 0;                                        // entries in this thread's append buffer
     int32_t cnt = 0;
     float blo = 0.f, bhi = 0.f;
-    int cur_qb = -1;
+    int cur_qb = -1, cur_part = -1, c_first = 0, slot = 0;
     bool qvalid = false;
     int qg = 0;
     const long long Wt = a.W;
@@ -503,11 +541,9 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
     };
-    auto flush = [&](int qb) {
-      if (qb < 0) return;
-      const long long wq = (long long)qb * a.n_t;
-      const int c_first = (int)(((wq + 1) * units - 1) / Wt);
-      const int slot = (a.upq > 0 ? unit % a.upq : unit - c_first) * 2 + half;
+    // write the lists / count of the part that just ended into its slot
+    auto flush = [&]() {
+      if (cur_part < 0) return;
       if (mode == kModeTopk) {
         fold();
         uint64_t* dst = a.s.part_keys + ((size_t)slot * a.q_pad + qg) * a.s.K;
@@ -522,8 +558,16 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     for (long long w = w_lo; w < w_hi; ++w, ++it) {
       const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
       if (qb != cur_qb) {
-        flush(cur_qb);
         cur_qb = qb;
+        c_first = a.upq > 0 ? qb * a.upq : (int)((((long long)qb * a.n_t + 1) * units - 1) / Wt);   // first unit of this block
+      }
+      // segment ordinal inside the query block: virtual parts + unit boundaries passed so far
+      const int ord = (a.vq > 1 ? (int)(((long long)t * a.vq) / a.n_t) : 0) + (unit - c_first);
+      const int part = qb * 4096 + ord;
+      if (part != cur_part) {
+        flush();
+        cur_part = part;
+        slot = ord * 2 + half;
         qg = qb * a.q_blk + qrow;
         qvalid = qg < a.s.Q;
         list.reset();
@@ -609,7 +653,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         else ptx::mbar_arrive(&tempty_bar[buf]);
       }
     }
-    flush(cur_qb);
+    flush();
     if (dbg && warp == 2 && lane == 0) { a.dbg[blockIdx.x * 16 + 5] = w_tfull; a.dbg[blockIdx.x * 16 + 6] = t_fold; a.dbg[blockIdx.x * 16 + 7] = clock64() - t_begin; }
   }
 
@@ -695,7 +739,7 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
   ma.s = s;
   ma.n_tile = pl.n_tile; ma.n_qb = pl.n_qb; ma.n_t = pl.n_t; ma.stages = pl.stages; ma.kc = pl.kc;
   ma.merged = pl.merged; ma.kc_total = pl.merged ? 2 * pl.kc : pl.kc;
-  ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.q_blk = pl.q_blk; ma.upq = pl.upq;
+  ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.q_blk = pl.q_blk; ma.upq = pl.upq; ma.vq = pl.vq;
   ma.W = (long long)pl.n_qb * pl.n_t;
   ma.dbg = nullptr;
   static const bool debug = getenv("KEMR_MMA_DEBUG") != nullptr;
@@ -709,7 +753,6 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
   switch (pl.K) {
     case 8: rc_launch = mma_launch_k<8>(mq, m0, m1, ma, pl, st); break;
     case 16: rc_launch = mma_launch_k<16>(mq, m0, m1, ma, pl, st); break;
-    case 24: rc_launch = mma_launch_k<24>(mq, m0, m1, ma, pl, st); break;
     default: rc_launch = mma_launch_k<32>(mq, m0, m1, ma, pl, st); break;
   }
   if (debug && rc_launch == 0) {
@@ -728,8 +771,8 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
         if (t < tmin) { tmin = t; cmin = c; }
         if (t > tmax) { tmax = t; cmax = c; }
       }
-      fprintf(stderr, "[kemr mma dbg] pair=%d merged=%d n_tile=%d K=%d ctas=%d tiles/unit=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f (min %lld @cta %d, max %lld @cta %d; max cta: wait_full=%lld wait_tempty=%lld) | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f  cycles\n",
-              pl.pair, pl.merged, pl.n_tile, pl.K, pl.ctas, (double)ma.W / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
+      fprintf(stderr, "[kemr mma dbg] pair=%d merged=%d vq=%d parts=%d n_tile=%d K=%d ctas=%d tiles/unit=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f (min %lld @cta %d, max %lld @cta %d; max cta: wait_full=%lld wait_tempty=%lld) | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f  cycles\n",
+              pl.pair, pl.merged, pl.vq, pl.parts, pl.n_tile, pl.K, pl.ctas, (double)ma.W / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
               tmin, cmin, tmax, cmax, h[(size_t)cmax * 16 + 2], h[(size_t)cmax * 16 + 3], avg[5], avg[6], avg[7]);
       if (getenv("KEMR_MMA_DEBUG_TRACE")) {
         std::vector<long long> tr((size_t)8 * kTraceLen);

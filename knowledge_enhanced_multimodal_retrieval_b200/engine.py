@@ -44,6 +44,14 @@ def device_info() -> Dict[str, int]:
             "has_tcgen05": v[3].value}
 
 
+def scan_plan(Q: int, M: int, D: int, galleries: int = 1, k_sel: int = 16, equal_weights: bool = False) -> Dict[str, int]:
+    """Kernel KEMR_PATH_AUTO would run for this shape (PATH_WARP / PATH_MMA) and its part count."""
+    path, parts = C.c_int(), C.c_int()
+    _lib.check(_lib.load().kemr_scan_plan(int(Q), int(M), int(D), int(galleries), int(k_sel), int(bool(equal_weights)),
+                                          C.byref(path), C.byref(parts)))
+    return {"path": path.value, "parts": parts.value}
+
+
 # --------------------------------------------------------------------------- workspace
 class _Workspace:
     def __init__(self):

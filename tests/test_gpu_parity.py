@@ -20,11 +20,14 @@ def _need_gpu():
     _lib.load()
 
 
-def path_ok(path, D, k=10):
+def path_ok(path, D, k=10, Q=64, M=1 << 20, G=1, equal=False):
+    """The tcgen05 kernel needs cc 10.x and enough gallery tiles for the lists k asks for."""
     if path != _lib.PATH_MMA:
         return True
     info = engine.device_info()
-    return bool(info["has_tcgen05"]) and engine.default_k_sel(k) <= 32
+    if not info["has_tcgen05"]:
+        return False
+    return engine.scan_plan(max(Q, 5), M, D, G, engine.default_k_sel(k), equal)["path"] == _lib.PATH_MMA
 
 
 def dev(x):
@@ -79,14 +82,16 @@ SHAPES = [  # Q, M, D, fused, k
     (1, 1, 8, False, 1), (1, 7, 64, True, 10), (2, 100, 64, False, 10), (3, 1000, 512, True, 10),
     (5, 257, 128, True, 20), (17, 5000, 768, True, 10), (130, 2100, 768, False, 100), (64, 4099, 1024, True, 10),
     (96, 160, 64, True, 5), (300, 700, 192, True, 3),
+    # large k on the tensor path: short register lists, many (virtual) parts
+    (300, 20000, 128, True, 100), (64, 30000, 64, False, 50), (700, 9000, 256, False, 100),
 ]
 
 
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("Q,M,D,fused,k", SHAPES)
 def test_scan_topk_matches_canonical(path, Q, M, D, fused, k):
-    if not path_ok(path, D, k):
-        pytest.skip("tcgen05 path unavailable")
+    if not path_ok(path, D, k, Q, M, 2 if fused else 1):
+        pytest.skip("tcgen05 path unavailable for this shape")
     s = synth.make_retrieval_set(Q=Q, M=M, D=D, seed=100 + Q + M, fused=fused, lam=0.2, diagonal=False)
     w = (0.1, 0.9) if fused else (1.0, 0.0)
     idx, score = engine.scan_topk(dev(s.query), dev(s.image), dev(s.target) if fused else None, w[0], w[1],
