@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the retrieval-scoring hot path (BASELINE.json metric: queries/sec, top-k=10).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c1|big]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c1|b64|b4096|c4|c5_b64|c5_b8192]
 
 One "step" = one pass of the hot path over one batch of synthetic queries: similarity scan of
 both galleries + weighted T2I/T2T fusion + top-k selection + canonical re-scoring.  Default
@@ -33,6 +33,11 @@ WORKLOADS = {
     "c3": dict(Q=1, M=43000, D=768, fused=True, k=10, seed=1),
     "b64": dict(Q=64, M=2_000_000, D=768, fused=False, k=10, seed=5, device_synth=True),
     "b4096": dict(Q=4096, M=1_250_000, D=768, fused=False, k=100, seed=4, device_synth=True),
+    # row-sharded gallery (north_star multi-GPU path): M rows PER GPU, queries replicated, local top-k with
+    # global ids, one NCCL all-gather, merge.  At 8 GPUs: c4 = 10 M rows, c5 = 100 M rows (153.6 GB).
+    "c4": dict(Q=4096, M=1_250_000, D=768, fused=False, k=100, seed=4, sharded=True),
+    "c5_b64": dict(Q=64, M=12_500_000, D=768, fused=False, k=10, seed=5, sharded=True),
+    "c5_b8192": dict(Q=8192, M=12_500_000, D=768, fused=False, k=10, seed=5, sharded=True),
 }
 
 
@@ -149,6 +154,199 @@ def workload_config(args, cfg, world):
             "l2": "L2 flushed (512 MiB memset) before every timed step"}
 
 
+def capture_step(step, torch, dist, world):
+    """Capture one step (our kernels + the NCCL all-gather) into a CUDA graph so that a multi-rank step
+    is ONE launch: without it the ranks drift apart on Python launch overhead and the all-gather waits.
+    Returns None (eager fallback on every rank) if any rank cannot capture."""
+    g = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+    except Exception as e:                       # noqa: BLE001
+        print(f"[bench] CUDA graph capture failed, running eagerly: {e}", file=sys.stderr)
+        g = None
+    if world > 1:
+        ok = torch.tensor([1 if g is not None else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            g = None
+    return g
+
+
+def timed_steps(args, torch, dist, world, lib, step, flush, use_graph):
+    """W warm-up steps, a short eager pass that times the scan kernel alone (event hook in the library),
+    then EXACTLY K timed steps (CUDA events, L2 flushed before each).  Returns (step_ms list, scan_ms mean)."""
+    import ctypes as C
+    for _ in range(max(3, args.warmup)):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    n_probe = 3
+    s0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_probe)]
+    m0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_probe)]
+    for m_ in m0:
+        m_.record()                      # materialise the underlying cudaEvent_t
+    torch.cuda.synchronize()
+    for i in range(n_probe):
+        flush.zero_()
+        s0[i].record()
+        lib.kemr_set_scan_done_event(C.c_void_p(m0[i].cuda_event))
+        step()
+    lib.kemr_set_scan_done_event(None)
+    torch.cuda.synchronize()
+    scan_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(s0, m0))
+    graph = capture_step(step, torch, dist, world) if use_graph else None
+    run = graph.replay if graph is not None else step
+    for _ in range(2):
+        flush.zero_()
+        run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        run()
+        ends[i].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    return [a.elapsed_time(b) for a, b in zip(starts, ends)], scan_ms, graph is not None
+
+
+# ----------------------------------------------------------------------------- our arm, row-sharded gallery
+def run_sharded(args, cfg):
+    """Gallery rows sharded over the ranks (cfg['M'] rows per GPU, generated on the device from the global
+    row index), queries replicated; a step = local scan + top-k (global ids) -> ONE all-gather -> merge."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from knowledge_enhanced_multimodal_retrieval_b200 import _lib, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    lib = _lib.load()
+    pk = peaks()
+    Q, D, k = cfg["Q"], cfg["D"], cfg["k"]
+    M = int(args.rows_per_gpu or cfg["M"])
+    lo = rank * M
+    gal = engine.synth_rows(M, D, cfg["seed"], row_base=lo)
+    g = torch.Generator().manual_seed(1234)                       # identical queries on every rank
+    q_host = torch.nn.functional.normalize(torch.randn(Q, D, generator=g), dim=1).pin_memory()
+    q = engine.quantize(q_host.cuda())
+    k_sel = engine.default_k_sel(k)
+    ws = engine.workspace_for(Q, M, D, k_sel)
+    flags = torch.empty((Q,), dtype=torch.int32, device="cuda")
+    packed = torch.empty((2, Q, k), dtype=torch.float64, device="cuda")      # [score | idx bit-cast]: the NCCL send buffer
+    score, idx = packed[0], packed[1].view(torch.int64)                        # the select kernel writes straight into it
+    gathered = torch.empty((world, 2, Q, k), dtype=torch.float64, device="cuda")
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    res = {}
+    qcur = [q]
+
+    def step():
+        engine.scan_topk_raw(qcur[0], gal, None, 1.0, 0.0, 1.0, None, k, k_sel, engine.DEFAULT_EPS, lo, score, idx, flags, ws)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
+            res["idx"], res["score"] = engine.merge_topk(gathered[:, 0], gathered[:, 1].contiguous().view(torch.int64), k)
+        else:
+            res["idx"], res["score"] = idx, score
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    step_ms, scan_ms_mean, graphed = timed_steps(args, torch, dist, world, lib, step, flush, world > 1)
+    total_ms = sum(step_ms)
+    scan_total = scan_ms_mean * args.steps
+    if world > 1:
+        t = torch.tensor([total_ms, scan_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, scan_total = float(t[0].item()), float(t[1].item())
+    n_uncert = int((flags & 1).sum().item())
+    # end to end: pinned host queries -> device -> quantise -> scan -> gather -> merge -> host results
+    out_i = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+    out_s = torch.empty((Q, k), dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        qcur[0] = engine.quantize(q_host.cuda(non_blocking=True))
+        step()
+        out_i.copy_(res["idx"], non_blocking=True)
+        out_s.copy_(res["score"], non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        info = engine.device_info()
+        scan_t = scan_total / args.steps * 1e-3
+        flops = 2.0 * Q * M * D
+        bytes_ = float(M) * D * 2
+        ridge = pk["tensor_burst"] * 1e12 / (pk["hbm"] * 1e9)
+        long_kernel = scan_t > 2e-3          # sustained clocks apply to multi-millisecond kernels
+        tpeak = pk["tensor_sustained"] if long_kernel else pk["tensor_burst"]
+        if Q >= ridge:
+            roof = {"bound": "tensor", "achieved": flops / scan_t / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                    "peak_kind": "sustained" if long_kernel else "burst"}
+        else:
+            roof = {"bound": "hbm", "achieved": bytes_ / scan_t / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["traffic"] = None
+        roof["peak_source"] = pk["source"]
+        roof["kernel"] = "scan (first kernel of kemr_scan_topk), per GPU, max over ranks"
+        roof["kernel_ms"] = scan_t * 1e3
+        roof["kernel_share_of_step"] = scan_total / total_ms
+        qps = Q * args.steps / (total_ms * 1e-3)
+        line = {"metric": "queries_per_sec_top%d" % k, "value": qps, "unit": "queries/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {Q} queries x {M * world} gallery rows ({M} per GPU) x {D}-d, "
+                                       f"single gallery, top-{k}", "queries_per_step": Q, "gallery_rows": M * world,
+                           "gallery_rows_per_gpu": M, "dim": D, "galleries": 1, "k": k,
+                           "parallelism": "single GPU" if world == 1 else f"gallery row-sharded x{world}, queries "
+                                          "replicated, one NCCL all-gather of local top-k + merge",
+                           "l2": "L2 flushed (512 MiB memset) before every timed step",
+                           "launch": "one CUDA graph per step" if graphed else "eager launches",
+                           "note": "weak scaling in GALLERY SIZE: queries/s stays flat while scanned rows grow with N; "
+                                   "row_queries_per_sec is the scaled quantity"},
+                "row_queries_per_sec": qps * M * world,
+                "e2e": {"value": Q * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(Q * D * 4),
+                        "d2h_bytes_per_step": int(Q * k * 16), "ms_per_step": e2e_s / args.steps * 1e3,
+                        "api": "pinned fp32 host queries -> quantize -> kemr_scan_topk (global ids) -> all-gather -> "
+                               "kemr_merge_topk -> pinned host results; gallery shard resident in HBM"},
+                "gpu_launches": (2 + (3 if world > 1 else 0)) * args.steps, "roofline": roof, "clocks": clocks,
+                "uncertified_queries": n_uncert, "sm_count": info["sm_count"],
+                "scan_path": "tcgen05" if engine.scan_plan(Q, M, D, 1, k_sel, False)["path"] == _lib.PATH_MMA else "warp-dot"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------- our arm (GPU)
 def run_ours(args, cfg):
     import ctypes as C
@@ -188,50 +386,23 @@ def run_ours(args, cfg):
     q = engine.quantize(q_host)
     k_sel = engine.default_k_sel(k)
     ws = engine.workspace_for(Q, M, D, k_sel)
-    score = torch.empty((Q, k), dtype=torch.float64, device="cuda")
-    idx = torch.empty((Q, k), dtype=torch.int64, device="cuda")
     flags = torch.empty((Q,), dtype=torch.int32, device="cuda")
-    packed = torch.empty((Q, 2 * k), dtype=torch.float64, device="cuda")
-    gathered = torch.empty((world * Q, 2 * k), dtype=torch.float64, device="cuda") if world > 1 else None
+    packed = torch.empty((2, Q, k), dtype=torch.float64, device="cuda")      # [score | idx bit-cast]: the NCCL send buffer
+    score, idx = packed[0], packed[1].view(torch.int64)                        # the select kernel writes straight into it
+    gathered = torch.empty((world, 2, Q, k), dtype=torch.float64, device="cuda") if world > 1 else None
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
     def step():
         engine.scan_topk_raw(q, img, tgt, wi, wt, 1.0, None, k, k_sel, engine.DEFAULT_EPS, 0, score, idx, flags, ws)
         if world > 1:
-            packed[:, :k] = score
-            packed[:, k:] = idx.view(torch.float64)           # bit-cast, exact
-            dist.all_gather_into_tensor(gathered, packed)
-
-    ev_scan = torch.cuda.Event(enable_timing=True)
-    for _ in range(max(3, args.warmup)):
-        flush.zero_()
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+            dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     # ---- timed region: K steps, device-timed, L2 flushed before each step
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    for m_ in mids:
-        m_.record()                      # materialise the underlying cudaEvent_t
-    torch.cuda.synchronize()
-    for i in range(args.steps):
-        flush.zero_()
-        starts[i].record()
-        lib.kemr_set_scan_done_event(C.c_void_p(mids[i].cuda_event))
-        step()
-        ends[i].record()
-    lib.kemr_set_scan_done_event(None)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    step_ms = [s_.elapsed_time(e_) for s_, e_ in zip(starts, ends)]
-    scan_ms = [s_.elapsed_time(m_) for s_, m_ in zip(starts, mids)]
+    step_ms, scan_ms_mean, graphed = timed_steps(args, torch, dist, world, lib, step, flush, world > 1)
+    scan_ms = [scan_ms_mean] * args.steps
     total_ms = sum(step_ms)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -290,7 +461,8 @@ def run_ours(args, cfg):
                         "h2d_bytes_per_step": int(Q * D * 4), "d2h_bytes_per_step": int(Q * k * 16 + Q * 4),
                         "api": "kemr_index_search_host (HostIndex.search): fp32 host queries in, top-k host arrays out; "
                                "gallery resident in HBM", "ms_per_step": e2e_s / args.steps * 1e3},
-                "gpu_launches": 2 * args.steps, "roofline": roof, "clocks": clocks,
+                "gpu_launches": 2 * args.steps, "launch": "one CUDA graph per step" if graphed else "eager launches",
+                "roofline": roof, "clocks": clocks,
                 "uncertified_queries": n_uncert, "sm_count": info["sm_count"],
                 "scan_path": "tcgen05" if engine.scan_plan(Q, M, D, G, k_sel, wi == wt)["path"] == _lib.PATH_MMA else "warp-dot"}
         # CPU baseline beside it: bounded sample of the same workload on the host cores
@@ -318,10 +490,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rows-per-gpu", type=int, default=0, help="override the gallery shard size of the sharded workloads")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif cfg.get("sharded"):
+        run_sharded(args, cfg)
     else:
         run_ours(args, cfg)
 
