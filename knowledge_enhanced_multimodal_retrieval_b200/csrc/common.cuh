@@ -128,6 +128,38 @@ struct CanonQueryT {
     for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, o));
     return __shfl_sync(0xffffffffu, acc, 0);
   }
+  // canonical dots with TWO already-fetched rows (T2I and T2T row of one candidate), the two reduction
+  // chains interleaved; same operation order per row as dot().  Valid on lane 0 only.
+  __device__ __forceinline__ void dot2_lane0(const CanonRow<NP>& ra, const CanonRow<NP>& rb, int D, int lane,
+                                             double& out_a, double& out_b) const {
+    const int npiece = D >> 3;
+    double a[8], b[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a[e] = 0.0; b[e] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      if (lane + 32 * j < npiece) {
+        const uint4 x = ra.x[j], y = rb.x[j];
+        a[0] = fma(v[j][0], bf16_to_f64(x.x & 0xffffu), a[0]); b[0] = fma(v[j][0], bf16_to_f64(y.x & 0xffffu), b[0]);
+        a[1] = fma(v[j][1], bf16hi_to_f64(x.x), a[1]);         b[1] = fma(v[j][1], bf16hi_to_f64(y.x), b[1]);
+        a[2] = fma(v[j][2], bf16_to_f64(x.y & 0xffffu), a[2]); b[2] = fma(v[j][2], bf16_to_f64(y.y & 0xffffu), b[2]);
+        a[3] = fma(v[j][3], bf16hi_to_f64(x.y), a[3]);         b[3] = fma(v[j][3], bf16hi_to_f64(y.y), b[3]);
+        a[4] = fma(v[j][4], bf16_to_f64(x.z & 0xffffu), a[4]); b[4] = fma(v[j][4], bf16_to_f64(y.z & 0xffffu), b[4]);
+        a[5] = fma(v[j][5], bf16hi_to_f64(x.z), a[5]);         b[5] = fma(v[j][5], bf16hi_to_f64(y.z), b[5]);
+        a[6] = fma(v[j][6], bf16_to_f64(x.w & 0xffffu), a[6]); b[6] = fma(v[j][6], bf16_to_f64(y.w & 0xffffu), b[6]);
+        a[7] = fma(v[j][7], bf16hi_to_f64(x.w), a[7]);         b[7] = fma(v[j][7], bf16hi_to_f64(y.w), b[7]);
+      }
+    }
+    double sa = __dadd_rn(__dadd_rn(__dadd_rn(a[0], a[1]), __dadd_rn(a[2], a[3])), __dadd_rn(__dadd_rn(a[4], a[5]), __dadd_rn(a[6], a[7])));
+    double sb = __dadd_rn(__dadd_rn(__dadd_rn(b[0], b[1]), __dadd_rn(b[2], b[3])), __dadd_rn(__dadd_rn(b[4], b[5]), __dadd_rn(b[6], b[7])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ta = __shfl_down_sync(0xffffffffu, sa, o), tb = __shfl_down_sync(0xffffffffu, sb, o);
+      sa = __dadd_rn(sa, ta);
+      sb = __dadd_rn(sb, tb);
+    }
+    out_a = sa; out_b = sb;
+  }
 };
 using CanonQuery = CanonQueryT<kCanonPieces>;
 

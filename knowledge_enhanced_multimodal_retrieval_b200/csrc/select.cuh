@@ -390,6 +390,180 @@ __global__ void __launch_bounds__(kSelWarpWarps * 32) select_warp_kernel(SelectA
   }
 }
 
+// ------------------------------------------------------------------ fast path: one small CTA per query
+// Same contract and the same small-case limits as select_warp_kernel, but W warps share one query:
+// the merge of the part lists is done by all W*32 threads, and the candidates are dealt round-robin
+// to the warps, each keeping the rows of its NEXT candidate in flight while it accumulates the current
+// one.  select_warp_kernel walks a query's 16+ candidates one after another in a single warp, so a
+// 1000-query batch is one wave of 1000 warps whose duration is the length of that serial chain
+// (~34 us on C2, ncu); here the chain is W times shorter and W times as many row loads are in flight.
+template <int NP, int W>
+__global__ void __launch_bounds__(W * 32) select_query_kernel(SelectArgs a) {
+  constexpr int T = W * 32;
+  __shared__ uint64_t s_heads[kSelWarpMaxP];
+  __shared__ uint64_t s_keys[kSelWarpMaxKeys];
+  __shared__ uint64_t s_selk[32];
+  __shared__ int s_lid[32];
+  __shared__ int32_t s_row[kSelWarpMaxCand];
+  __shared__ double s_bonus[kSelWarpMaxCand];
+  __shared__ double s_score[kSelWarpMaxCand];
+  __shared__ unsigned char s_has[kSelWarpMaxCand];
+  __shared__ unsigned long long s_bound;
+  __shared__ int s_nlist, s_extra, s_nsurv;
+  __shared__ double s_kth;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qi = blockIdx.x;
+  const int K = a.K, Kp = a.Kp, P = a.P;
+
+  CanonQueryT<NP> cq;
+  cq.load(a.q + (size_t)qi * a.D, a.D, lane);
+
+  // A1. heads of the part lists -> the (at most K) lists that can hold a top-K key
+  for (int p = tid; p < P; p += T) s_heads[p] = a.part_keys[((size_t)p * a.Q + qi) * Kp];
+  if (tid < 32) { s_selk[tid] = 0; s_lid[tid] = -1; }
+  if (tid == 0) { s_bound = 0; s_nlist = 0; s_extra = 0; s_nsurv = 0; s_kth = -INFINITY; }
+  __syncthreads();
+  for (int p = tid; p < P; p += T) {
+    const uint64_t x = s_heads[p];
+    if (!x) continue;
+    int r = 0;
+    for (int j = 0; j < P; ++j) r += s_heads[j] > x ? 1 : 0;
+    if (r < K) { s_lid[r] = p; atomicAdd(&s_nlist, 1); }
+    else atomicMax(&s_bound, (unsigned long long)x);
+  }
+  __syncthreads();
+
+  // A2. K best keys among the selected lists.  When K lists were selected their heads alone are K keys
+  //     >= the K-th head, so anything below that head is out; only the survivors are ranked by counting.
+  const int nlist = s_nlist;
+  const uint64_t cut = nlist >= K ? s_heads[s_lid[K - 1]] : 0ull;
+  {
+    const int n2 = nlist * Kp;
+    unsigned long long rej = 0;                          // largest key this thread saw rejected
+    for (int i = tid; i < n2; i += T) {
+      const int l = i / Kp, j = i - l * Kp;
+      const uint64_t x = a.part_keys[((size_t)s_lid[l] * a.Q + qi) * Kp + j];
+      if (!x) continue;
+      if (x >= cut) s_keys[atomicAdd(&s_nsurv, 1)] = x;
+      else if (x > rej) rej = x;
+      if (j == Kp - 1 && x > rej) rej = x;               // a full part list rejected rows below its last key
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, rej, o);
+      rej = other > rej ? other : rej;
+    }
+    if (lane == 0 && rej) atomicMax(&s_bound, rej);
+  }
+  __syncthreads();
+  const int ns = s_nsurv;
+  for (int i = tid; i < ns; i += T) {
+    const uint64_t x = s_keys[i];
+    int r = 0;
+    for (int j = 0; j < ns; ++j) r += s_keys[j] > x ? 1 : 0;
+    if (r < K) s_selk[r] = x;                            // keys are distinct -> ranks are distinct
+    else atomicMax(&s_bound, (unsigned long long)x);
+  }
+  __syncthreads();
+  int nsel = __popc(__ballot_sync(0xffffffffu, s_selk[lane] != 0));          // keys fill s_selk[0..nsel), descending
+  // Candidates past the k-th whose fp32 score lies more than 2 eps below the k-th fp32 score cannot reach
+  // the top k (|fp32 - canonical| <= eps; a KG bonus only raises the k-th score): they are not re-scored
+  // and count as rejected for the certificate.  KG hits among them come back through the hit list.
+  if (nsel > a.k) {
+    const double kth32 = (double)key_score(s_selk[a.k - 1]) - 2.0 * a.eps * (1.0 + 1.0 / 64.0);
+    const bool drop = lane >= a.k && lane < nsel && (double)key_score(s_selk[lane]) < kth32;
+    const unsigned m = __ballot_sync(0xffffffffu, drop);
+    if (m) {
+      const int first = __ffs(m) - 1;                    // descending order: everything from `first` on drops
+      if (tid == 0) atomicMax(&s_bound, (unsigned long long)s_selk[first]);
+      nsel = first;
+    }
+  }
+
+  // B. candidate table = scan candidates U KG hits
+  if (tid < nsel) { s_row[tid] = (int32_t)key_row(s_selk[tid]); s_bonus[tid] = 0.0; s_has[tid] = 0; }
+  __syncthreads();
+  if (a.hit_rowptr) {
+    const int64_t h0 = a.hit_rowptr[qi], h1 = a.hit_rowptr[qi + 1];
+    for (int64_t h = h0 + tid; h < h1; h += T) {
+      const int32_t col = a.hit_col[h];
+      if (col < 0 || (int64_t)col >= a.M) continue;
+      int found = -1;
+      for (int i = 0; i < nsel; ++i) if (s_row[i] == col) { found = i; break; }
+      if (found < 0) {
+        found = nsel + atomicAdd(&s_extra, 1);
+        if (found >= kSelWarpMaxCand) continue;      // cannot happen when max_hits_per_query is honest
+        s_row[found] = col;
+      }
+      s_bonus[found] = a.hit_bonus[h];
+      s_has[found] = 1;
+    }
+    __syncthreads();
+  }
+  const int n = min(nsel + s_extra, kSelWarpMaxCand);
+
+  // C. canonical re-scoring: warp w takes candidates w, w+W, ...; the rows of its next candidate are in
+  //    flight while the current one is accumulated (two register sets, roles alternate)
+  {
+    CanonRow<NP> ra[2], rb[2];
+    auto fetch = [&](int set, int c) {
+      const size_t off = (size_t)s_row[c] * a.D;
+      ra[set].load(a.gal[0] + off, a.D, lane);
+      if (a.G > 1) rb[set].load(a.gal[1] + off, a.D, lane);
+    };
+    auto score = [&](int set, int c) {
+      double sa, sb = 0.0;
+      if (a.G > 1) cq.dot2_lane0(ra[set], rb[set], a.D, lane, sa, sb);
+      else sa = cq.dot(ra[set], a.D, lane);
+      if (lane == 0) s_score[c] = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, s_bonus[c], s_has[c] != 0);
+    };
+    int c = warp;
+    if (c < n) fetch(0, c);
+    while (c < n) {
+      if (c + W < n) fetch(1, c + W);
+      score(0, c);
+      c += W;
+      if (c >= n) break;
+      if (c + W < n) fetch(0, c + W);
+      score(1, c);
+      c += W;
+    }
+  }
+  __syncthreads();
+
+  // D. order by (score desc, row asc) by counting; write the first k
+  for (int c = tid; c < n; c += T) {
+    const double sc = s_score[c];
+    const int32_t rc = s_row[c];
+    int r = 0;
+    for (int j = 0; j < n; ++j) r += ahead64(s_score[j], s_row[j], sc, rc) ? 1 : 0;
+    if (r < a.k) {
+      const size_t o = (size_t)qi * a.k + r;
+      a.out_score64[o] = sc;
+      if (a.out_score32) a.out_score32[o] = (float)sc;
+      a.out_idx[o] = a.idx_base + rc;
+      if (r == a.k - 1) s_kth = sc;
+    }
+  }
+  for (int r = n + tid; r < a.k; r += T) {
+    const size_t o = (size_t)qi * a.k + r;
+    a.out_score64[o] = -INFINITY;
+    if (a.out_score32) a.out_score32[o] = -INFINITY;
+    a.out_idx[o] = -1;
+  }
+  __syncthreads();
+
+  // E. certificate
+  if (tid == 0) {
+    int flag = 0;
+    if (s_bound) {
+      const double b = (double)key_score((uint64_t)s_bound) + a.eps * (1.0 + 1.0 / 64.0);
+      const double reach = a.alpha * b + 1e-300;
+      if (!(n >= a.k && s_kth > reach)) flag = 1;
+    }
+    a.out_flags[qi] = flag;
+  }
+}
+
 // ------------------------------------------------------------------ canonical pair scores
 __global__ void score_pairs_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ ga,
                                    const uint16_t* __restrict__ gb, int D, double wa, double wb,
