@@ -56,7 +56,7 @@ extern "C" int kemr_set_scan_done_event(void* cuda_event) {
 }
 extern "C" int kemr_abi_version(void) { return KEMR_ABI_VERSION; }
 
-struct DevInfo { int ok = 0, dev = -1, sms = 0, major = 0, minor = 0; };
+struct DevInfo { int ok = 0, dev = -1, sms = 0, major = 0, minor = 0, quads = 0; };
 static int dev_info(DevInfo* out) {
   static thread_local DevInfo cache;
   int dev = 0;
@@ -66,6 +66,7 @@ static int dev_info(DevInfo* out) {
     CUDA_TRY(cudaDeviceGetAttribute(&cache.sms, cudaDevAttrMultiProcessorCount, dev));
     CUDA_TRY(cudaDeviceGetAttribute(&cache.major, cudaDevAttrComputeCapabilityMajor, dev));
     CUDA_TRY(cudaDeviceGetAttribute(&cache.minor, cudaDevAttrComputeCapabilityMinor, dev));
+    cache.quads = cache.major == 10 ? mma_max_quads() : 0;
     cache.ok = 1;
   }
   *out = cache;
@@ -139,13 +140,13 @@ static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, 
     // (enough gallery tiles for the candidate lists k_sel needs); warp-dot for the latency-bound tiny
     // batches and as the general fallback
     pl->path = KEMR_PATH_WARP;
-    if (dv.major == 10 && Q >= 5 && mma_supported(D, K) && mma_make_plan(Q, M, D, G, K, mode, dv.sms, equal_weights, &pl->mma) == 0)
+    if (dv.major == 10 && Q >= 5 && mma_supported(D, K) && mma_make_plan(Q, M, D, G, K, mode, dv.sms, dv.quads, equal_weights, &pl->mma) == 0)
       pl->path = KEMR_PATH_MMA;
   }
   if (pl->path == KEMR_PATH_MMA) {
     if (dv.major != 10) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path needs compute capability 10.x (have %d.%d)", dv.major, dv.minor);
     if (!mma_supported(D, K)) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path: unsupported D=%d / k_sel=%d", D, K);
-    int rc = mma_make_plan(Q, M, D, G, K, mode, dv.sms, equal_weights, &pl->mma);
+    int rc = mma_make_plan(Q, M, D, G, K, mode, dv.sms, dv.quads, equal_weights, &pl->mma);
     if (rc) return fail(KEMR_ERR_UNSUPPORTED, "tcgen05 path: cannot plan this shape (k_sel=%d needs more gallery tiles than M=%lld offers)", K, (long long)M);
     pl->P = pl->mma.parts;
     pl->Kp = pl->mma.K;
@@ -184,7 +185,7 @@ extern "C" size_t kemr_workspace_bytes(int Q, int64_t M, int D, int k_sel, int64
   if (dev_info(&dv) == KEMR_OK && dv.sms > 0) sms = dv.sms;
   const int P = 2 * sms + 8;                    // upper bound of any plan's part count
   const int K = std::max(1, std::min(k_sel, kMaxKSel));
-  const int Qp = (Q + 255) / 256 * 256;       // query rows padded to a CTA pair's block
+  const int Qp = (Q + 511) / 512 * 512;       // query rows padded to a cluster's block (two CTA pairs)
   size_t topk = parts_bytes(P, Qp, K);
   size_t count = align_up((size_t)Q * 8) + align_up((size_t)Q * 8) + align_up((size_t)P * Qp * 4) + 256 +
                  align_up(((size_t)1 << 20) * 8 + (size_t)Q * 256 * 8);

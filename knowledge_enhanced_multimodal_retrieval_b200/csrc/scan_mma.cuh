@@ -65,6 +65,7 @@ struct MmaPlan {
   int a_rows = 0;         // query rows actually loaded per block
   int K = 0;              // list length (8, 16, 24, 32)
   int pair = 0;           // 1: CTA pairs (cta_group::2), 256 queries per block
+  int cl = 1;             // CTAs per cluster: 1, 2 (one pair) or 4 (two pairs on adjacent query blocks sharing the gallery tile by TMA multicast)
   int upq = 0;            // units (CTAs or pairs) per query block; 0 = flattened (block, tile) ranges
   int vq = 1;             // virtual parts per query block: lists are flushed and restarted at these boundaries
   int all_slots = 0;      // 1: every part slot of every query row is written (no memset needed)
@@ -82,7 +83,7 @@ inline const char* mma_last_error() { return g_mma_error; }
 
 constexpr int kPlanMaxParts = 304;     // candidate lists per query any plan may use (workspace bound: 2*148 + 8)
 
-inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sms, bool equal_weights, MmaPlan* p) {
+inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sms, int quads, bool equal_weights, MmaPlan* p) {
   (void)mode;
   p->kc = (D + kBlockK - 1) / kBlockK;
   // Two galleries with EQUAL fusion weights: w*(q.a) + w*(q.b) = w*(q.a + q.b), so both galleries'
@@ -96,7 +97,18 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
   static const char* force_pair = getenv("KEMR_MMA_PAIR");          // experiments: 0 = never, 1 = always
   p->pair = force_pair ? (force_pair[0] == '1') : (Q > kBlockM);
   if (sms < 2) p->pair = 0;
-  p->q_blk = p->pair ? 2 * kBlockM : kBlockM;
+  // Clusters of FOUR CTAs (two pairs): the pairs take adjacent 256-query blocks and the same gallery tiles, and
+  // every CTA fetches only a quarter of the tile chunk, multicast to the CTA of the other pair that needs the same
+  // half -> 24 KB instead of 32 KB through L2 per CTA and stage (the pair kernel runs at the L2 slice limit of
+  // ~1 sector/clk/slice: ncu 0.87 sectors/clk/slice at 64 % tensor-pipe activity).  `quads` = clusters of four the
+  // device can hold at once (33 on a B200: GPC shapes leave 16 SMs unusable), so this pays only when the batch is
+  // L2-bound (>= 2 blocks) and an odd block count does not waste too much on the phantom block.
+  const int n_qb256 = p->pair ? (Q + 2 * kBlockM - 1) / (2 * kBlockM) : 0;
+  static const char* force_cl = getenv("KEMR_MMA_CL");              // experiments: 2 = pairs only, 4 = always quads
+  bool quad = p->pair && quads >= 1 && n_qb256 >= 2 && (n_qb256 % 2 == 0 || n_qb256 >= 7);
+  if (force_cl && p->pair && quads >= 1) quad = force_cl[0] == '4';
+  p->cl = quad ? 4 : (p->pair ? 2 : 1);
+  p->q_blk = quad ? 4 * kBlockM : (p->pair ? 2 * kBlockM : kBlockM);     // queries per scheduling block (per cluster)
   p->n_tile = p->two ? 128 : 256;
   p->n_qb = (Q + p->q_blk - 1) / p->q_blk;
   p->q_pad = p->n_qb * p->q_blk;
@@ -104,7 +116,7 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
   if (nt > (1ll << 30)) return 1;
   p->n_t = (int)nt;
   const int64_t W = (int64_t)p->n_qb * p->n_t;
-  const int units = p->pair ? sms / 2 : sms;       // persistent CTAs, or CTA pairs
+  const int units = quad ? quads : (p->pair ? sms / 2 : sms);       // persistent CTAs, pairs or quads
   int nu, parts = 1;
   const int upq_try = (int)std::min<int64_t>(units / std::max(1, p->n_qb), nt);
   if (upq_try >= 1 && ((int64_t)upq_try * p->n_qb * 10 >= (int64_t)std::min<int64_t>(units, W) * 9)) {
@@ -124,7 +136,7 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
       parts = std::max(parts, c1 - c0 + 1);
     }
   }
-  p->ctas = p->pair ? 2 * nu : nu;
+  p->ctas = p->cl * nu;
   p->a_rows = (p->pair || Q >= kBlockM) ? kBlockM : (Q + 7) / 8 * 8;
   // Candidate lists.  A query's rows are cut into segments (unit boundaries, plus `vq` virtual
   // boundaries per block when more are needed); every segment yields two K-entry lists (one per
@@ -201,6 +213,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
+// one lane of the (converged) warp; always the same lane for a full mask
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -250,6 +268,13 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
 }
+// the same, multicast: the box lands at the same offset in every CTA of `mask`, and each destination's bytes are
+// signalled on the barrier at `leader_bar`'s offset in that destination's pair leader (CUTLASS SM100_TMA_2SM_LOAD_MULTICAST)
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -263,10 +288,10 @@ __device__ __forceinline__ void mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, u
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair when the MMAs retire
-__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+// arrives on the barrier at this shared-memory offset in every CTA of `mask` when the MMAs retire
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -303,6 +328,7 @@ struct MmaArgs {
   int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, upq, vq;
   long long W;
   long long* dbg;   // optional [ctas][16] cycle counters + stage trace (KEMR_MMA_DEBUG=1)
+  int dbg_skip;     // timing experiments only (results invalid): after a unit's first tile skip the TMA loads of bit0 = queries, bit1 = gallery
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -363,16 +389,18 @@ __device__ __forceinline__ void ld_shared_v2(uint32_t addr, float& s, uint32_t& 
 // accumulators (T2I, T2T) of 128 columns each, fused in the epilogue with their own weights
 // (otherwise ONE accumulator of 256 gallery rows: single gallery, or both galleries with equal
 // weights accumulated over 2*kc K chunks).
-template <int K, bool PAIR, bool TWO>
+template <int K, int CL, bool TWO>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g0,
                 const __grid_constant__ CUtensorMap map_g1, MmaArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_mma_raw[];
   // identical shared-memory layout in both CTAs of a pair (the MMA addresses the peer by offset)
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_mma_raw + 1023) & ~(uintptr_t)1023);
+  constexpr bool PAIR = CL >= 2;                                // CTA pairs (cta_group::2)
+  constexpr bool QUAD = CL == 4;                                // two pairs per cluster sharing the gallery tile
   constexpr int n_tile = TWO ? 128 : 256;                       // gallery rows per tile
   constexpr uint32_t a_bytes = (uint32_t)kBlockM * 128u;
-  constexpr uint32_t b_box = PAIR ? 128u : (uint32_t)n_tile;     // gallery rows per TMA box
+  constexpr uint32_t b_box = PAIR ? 128u : (uint32_t)n_tile;     // gallery rows per CTA and stage
   constexpr uint32_t b_bytes = b_box * 128u;
   constexpr uint32_t stage_bytes = a_bytes + (PAIR ? b_bytes : 256u * 128u);
   const uint32_t buf_u32 = ptx::smem_u32(smem + (size_t)a.stages * stage_bytes);      // [kBufCap][kEpiThreads] x 8 B
@@ -383,9 +411,12 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
-  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // persistent CTA or CTA pair
-  const int units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t crank = PAIR ? ptx::cluster_ctarank() : 0u;    // rank in the cluster
+  const uint32_t rank = crank & 1u;                             // rank in the pair; 0 = leader (issues the MMAs)
+  const uint32_t pc = crank >> 1;                               // which pair of a quad (its 256-query block)
+  const uint32_t lead = crank & ~1u;                            // cluster rank of this pair's leader
+  const int unit = (int)(blockIdx.x / CL);                      // persistent CTA, pair or quad
+  const int units = (int)(gridDim.x / CL);
   const bool dbg = a.dbg != nullptr;
   long long w_lo, w_hi;                      // this unit's range of the flattened (query block, tile) grid
   if (a.upq > 0) {
@@ -399,7 +430,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (threadIdx.x == 0) {
     // full: one arrival (the leader's expect_tx covers both CTAs' bytes; the peer's TMA loads complete
     // on the leader's barrier); tempty: epilogue warps of both CTAs
-    for (int i = 0; i < a.stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    // empty: one arrival per pair of the cluster (a quad's CTAs write into each other's stages)
+    for (int i = 0; i < a.stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], QUAD ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiWarps : kEpiWarps); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&map_q); ptx::prefetch_tmap(&map_g0);
@@ -413,7 +445,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
   if (warp == 0) {
     // ================================================================= TMA producer
-    if (lane == 0) {
+    // (whole warp in the loop, one elected lane issues -- see the MMA issuer below)
+    {
       int stage = 0; uint32_t phase = 0;
       long long w_empty = 0; const long long t_begin = dbg ? clock64() : 0;
       int tr = 0;
@@ -424,15 +457,36 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const int g = kcc >= a.kc ? 1 : 0;              // merged mode: second gallery's chunks follow the first's
           const int kx = (kcc - g * a.kc) * kBlockK;
           mbar_wait_dbg(&empty_bar[stage], phase ^ 1, dbg, w_empty);
-          if (dbg && blockIdx.x < 2 && tr < kTraceLen) a.dbg[kTraceBase + (blockIdx.x * 4 + 0) * kTraceLen + tr] = clock64();
+          if (dbg && blockIdx.x < 2 && lane == 0 && tr < kTraceLen) a.dbg[kTraceBase + (blockIdx.x * 4 + 0) * kTraceLen + tr] = clock64();
           unsigned char* sa = smem + (size_t)stage * stage_bytes;
-          if (PAIR) {
+          if (ptx::elect_one()) {
+          if (a.dbg_skip && w > w_lo) {
+            // ingress experiment: the stage keeps whatever it held; only the selected operand is fetched
+            const bool la = !(a.dbg_skip & 1), lb = !(a.dbg_skip & 2);
+            const uint32_t lbar = PAIR ? ptx::map_to_cta(ptx::smem_u32(&full_bar[stage]), lead) : 0u;
+            const uint32_t txs = (la ? a_bytes : 0u) + (lb ? (PAIR ? b_bytes : 256u * 128u) : 0u);
+            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], PAIR ? 2u * txs : txs);
+            if (PAIR) {
+              if (la) ptx::tma_load_2d_pair(sa, &map_q, lbar, kx, qb * a.q_blk + (int)crank * kBlockM);
+              if (lb) ptx::tma_load_2d_pair(sa + a_bytes, g ? &map_g1 : &map_g0, lbar, kx, t * n_tile + (int)rank * 128);
+            } else {
+              if (la) ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kx, qb * kBlockM);
+              if (lb) ptx::tma_load_2d(sa + a_bytes, g ? &map_g1 : &map_g0, &full_bar[stage], kx, t * n_tile);
+            }
+          } else if (PAIR) {
             // this CTA's 128 query rows + its half of the gallery chunk; bytes land on the leader's barrier
-            const uint32_t lbar = ptx::map_to_cta(ptx::smem_u32(&full_bar[stage]), 0);
+            const uint32_t lbar = ptx::map_to_cta(ptx::smem_u32(&full_bar[stage]), lead);
             if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], tx);
-            ptx::tma_load_2d_pair(sa, &map_q, lbar, kx, qb * (2 * kBlockM) + (int)rank * kBlockM);
+            ptx::tma_load_2d_pair(sa, &map_q, lbar, kx, qb * a.q_blk + (int)crank * kBlockM);
             const CUtensorMap* mb = TWO ? (rank ? &map_g1 : &map_g0) : (g ? &map_g1 : &map_g0);
-            ptx::tma_load_2d_pair(sa + a_bytes, mb, lbar, kx, t * n_tile + (TWO ? 0 : (int)rank * 128));
+            const int brow = t * n_tile + (TWO ? 0 : (int)rank * 128);
+            if (QUAD) {
+              // this CTA's quarter of the chunk (64 rows), multicast to the CTA of the other pair holding the same half
+              ptx::tma_load_2d_pair_mc(sa + a_bytes + pc * (64u * 128u), mb, lbar, kx, brow + (int)pc * 64,
+                                       (uint16_t)((1u << rank) | (4u << rank)));
+            } else {
+              ptx::tma_load_2d_pair(sa + a_bytes, mb, lbar, kx, brow);
+            }
           } else {
             ptx::mbar_expect_tx(&full_bar[stage], tx);
             ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kx, qb * kBlockM);
@@ -443,20 +497,30 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               ptx::tma_load_2d(sa + a_bytes, g ? &map_g1 : &map_g0, &full_bar[stage], kx, t * n_tile);
             }
           }
-          if (dbg && blockIdx.x < 2 && tr < kTraceLen) { a.dbg[kTraceBase + (blockIdx.x * 4 + 1) * kTraceLen + tr] = clock64(); ++tr; }
+          }
+          __syncwarp();
+          if (dbg && blockIdx.x < 2 && lane == 0 && tr < kTraceLen) a.dbg[kTraceBase + (blockIdx.x * 4 + 1) * kTraceLen + tr] = clock64();
+          if (dbg && blockIdx.x < 2 && tr < kTraceLen) ++tr;
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (dbg) { a.dbg[blockIdx.x * 16 + 0] = w_empty; a.dbg[blockIdx.x * 16 + 1] = clock64() - t_begin; }
+      if (dbg && lane == 0) { a.dbg[blockIdx.x * 16 + 0] = w_empty; a.dbg[blockIdx.x * 16 + 1] = clock64() - t_begin; }
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    // The WHOLE warp walks the loop (warp-uniform control flow and addresses, so descriptors live in uniform
+    // registers); one elected lane issues the MMAs and commits.  Issued from a single divergent lane, every MMA
+    // sat behind a ~60-cycle register->uniform-register waterfall and the tensor pipe idled between MMAs
+    // (ncu: 64 % tensor-pipe activity with all loads and the epilogue switched off).
+    if (rank == 0) {
       int stage = 0; uint32_t phase = 0;
       // The gallery chunk(s) of a stage form ONE K-major tile of 256 rows (T2I rows then T2T rows, or
       // 256 rows of one gallery; split across the two CTAs in pair mode): a single MMA with N = 256
       // fills the whole accumulator buffer and reads the query chunk once.
       const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, 256);
+      const uint64_t adesc0 = umma_desc_sw128(ptx::smem_u32(smem));
+      const uint64_t bdesc0 = umma_desc_sw128(ptx::smem_u32(smem) + a_bytes);
+      constexpr uint64_t stage_step = (uint64_t)(stage_bytes >> 4);      // descriptor start-address units (16 B)
       long long it = 0;
       long long w_full = 0, w_tempty = 0; const long long t_begin = dbg ? clock64() : 0;
       int tr = 0;
@@ -468,32 +532,38 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
         for (int kcc = 0; kcc < a.kc_total; ++kcc) {
           mbar_wait_dbg(&full_bar[stage], phase, dbg, w_full);
-          if (dbg && blockIdx.x == 0 && tr < kTraceLen) a.dbg[kTraceBase + 2 * kTraceLen + tr] = clock64();
+          if (dbg && blockIdx.x == 0 && lane == 0 && tr < kTraceLen) a.dbg[kTraceBase + 2 * kTraceLen + tr] = clock64();
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + a_bytes);
+          const uint64_t adesc = adesc0 + (uint64_t)stage * stage_step;
+          const uint64_t bdesc = bdesc0 + (uint64_t)stage * stage_step;
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            if (PAIR) ptx::mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kcc | k) ? 1u : 0u);
-            else ptx::mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kcc | k) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              if (PAIR) ptx::mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kcc | k) ? 1u : 0u);
+              else ptx::mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kcc | k) ? 1u : 0u);
+            }
+            // frees the smem stage (in every CTA of the cluster) when these MMAs retire
+            if (PAIR) ptx::mma_commit_pair(&empty_bar[stage], QUAD ? (uint16_t)0xF : (uint16_t)0x3); else ptx::mma_commit(&empty_bar[stage]);
           }
-          // frees the smem stage (in both CTAs) when these MMAs retire
-          if (PAIR) ptx::mma_commit_pair(&empty_bar[stage]); else ptx::mma_commit(&empty_bar[stage]);
-          if (dbg && blockIdx.x == 0 && tr < kTraceLen) { a.dbg[kTraceBase + 3 * kTraceLen + tr] = clock64(); ++tr; }
+          __syncwarp();
+          if (dbg && blockIdx.x == 0 && lane == 0 && tr < kTraceLen) { a.dbg[kTraceBase + 3 * kTraceLen + tr] = clock64(); }
+          if (dbg && blockIdx.x == 0 && tr < kTraceLen) ++tr;
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         // accumulators of this tile are complete
-        if (PAIR) ptx::mma_commit_pair(&tfull_bar[buf]); else ptx::mma_commit(&tfull_bar[buf]);
+        if (ptx::elect_one()) {
+          if (PAIR) ptx::mma_commit_pair(&tfull_bar[buf], (uint16_t)(3u << lead)); else ptx::mma_commit(&tfull_bar[buf]);
+        }
+        __syncwarp();
       }
-      if (dbg) { a.dbg[blockIdx.x * 16 + 2] = w_full; a.dbg[blockIdx.x * 16 + 3] = w_tempty; a.dbg[blockIdx.x * 16 + 4] = clock64() - t_begin; }
+      if (dbg && lane == 0) { a.dbg[blockIdx.x * 16 + 2] = w_full; a.dbg[blockIdx.x * 16 + 3] = w_tempty; a.dbg[blockIdx.x * 16 + 4] = clock64() - t_begin; }
     }
   } else {
     // ================================================================= epilogue (warps 2..9)
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
     const int half = (warp - 2) >> 2;                    // which half of the tile's score columns
     const int et = (warp - 2) * 32 + lane;               // epilogue thread id, 0..255
-    const int qrow = (int)rank * kBlockM + quad * 32 + lane;     // query row inside the block
+    const int qrow = (int)crank * kBlockM + quad * 32 + lane;    // query row inside the (cluster's) block
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t my_buf = buf_u32 + (uint32_t)et * 8u;  // append-buffer entry i of this thread: + i * kEpiThreads * 8
     const float w0 = a.s.w[0], w1 = a.s.w[1];
@@ -511,8 +581,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const long long Wt = a.W;
     long long it = 0;
     long long w_tfull = 0, t_fold = 0; const long long t_begin = dbg ? clock64() : 0;
-    const uint32_t tempty0 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
-    const uint32_t tempty1 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tempty_bar[1]), 0) : 0u;
+    const uint32_t tempty0 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tempty_bar[0]), lead) : 0u;
+    const uint32_t tempty1 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tempty_bar[1]), lead) : 0u;
 
     // fold every lane's append buffer into its register list, in lock-step
     auto fold = [&]() {
@@ -634,15 +704,17 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
       // double-buffered TMEM reads: chunk i+1 is in flight while chunk i is processed
       uint32_t ra0[16], rb0[16], ra1[16], rb1[16];
-      if (nch > 0) load(cbeg, ra0, rb0);
-      for (int i = 0; i < nch; i += 2) {
+      const int nch_run = (a.dbg_skip & 4) ? 0 : nch;          // timing experiment: epilogue reads nothing
+      const bool no_proc = (a.dbg_skip & 8) != 0;              // timing experiment: TMEM reads only
+      if (nch_run > 0) load(cbeg, ra0, rb0);
+      for (int i = 0; i < nch_run; i += 2) {
         ptx::tmem_ld_wait();
         if (i + 1 < nch) load(cbeg + (i + 1) * 16, ra1, rb1);
-        process(cbeg + i * 16, ra0, rb0);
+        if (!no_proc) process(cbeg + i * 16, ra0, rb0); else cnt += (int32_t)ra0[3];
         if (i + 1 < nch) {
           ptx::tmem_ld_wait();
           if (i + 2 < nch) load(cbeg + (i + 2) * 16, ra0, rb0);
-          process(cbeg + (i + 1) * 16, ra1, rb1);
+          if (!no_proc) process(cbeg + (i + 1) * 16, ra1, rb1); else cnt += (int32_t)ra1[3];
         }
       }
       // release this accumulator buffer to the (leader's) MMA warp
@@ -701,10 +773,10 @@ inline int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int D,
   return 0;
 }
 
-template <int K, bool PAIR, bool TWO>
+template <int K, int CL, bool TWO>
 inline int mma_launch_kpt(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
                           const MmaPlan& pl, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<K, PAIR, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
+  cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<K, CL, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "smem attribute: %s", cudaGetErrorString(e)); return 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)pl.ctas);
@@ -713,10 +785,10 @@ inline int mma_launch_kpt(const CUtensorMap& mq, const CUtensorMap& m0, const CU
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, scan_mma_kernel<K, PAIR, TWO>, mq, m0, m1, ma);
+  e = cudaLaunchKernelEx(&cfg, scan_mma_kernel<K, CL, TWO>, mq, m0, m1, ma);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
@@ -724,14 +796,32 @@ inline int mma_launch_kpt(const CUtensorMap& mq, const CUtensorMap& m0, const CU
 template <int K>
 inline int mma_launch_k(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
                         const MmaPlan& pl, cudaStream_t st) {
-  if (pl.pair) return pl.two ? mma_launch_kpt<K, true, true>(mq, m0, m1, ma, pl, st) : mma_launch_kpt<K, true, false>(mq, m0, m1, ma, pl, st);
-  return pl.two ? mma_launch_kpt<K, false, true>(mq, m0, m1, ma, pl, st) : mma_launch_kpt<K, false, false>(mq, m0, m1, ma, pl, st);
+  if (pl.cl == 4) return pl.two ? mma_launch_kpt<K, 4, true>(mq, m0, m1, ma, pl, st) : mma_launch_kpt<K, 4, false>(mq, m0, m1, ma, pl, st);
+  if (pl.cl == 2) return pl.two ? mma_launch_kpt<K, 2, true>(mq, m0, m1, ma, pl, st) : mma_launch_kpt<K, 2, false>(mq, m0, m1, ma, pl, st);
+  return pl.two ? mma_launch_kpt<K, 1, true>(mq, m0, m1, ma, pl, st) : mma_launch_kpt<K, 1, false>(mq, m0, m1, ma, pl, st);
+}
+
+// clusters of four CTAs (one 227 KB CTA per SM) the current device can hold at once
+inline int mma_max_quads() {
+  cudaFuncSetAttribute(scan_mma_kernel<8, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(4 * 64);
+  cfg.blockDim = dim3(kMmaThreads);
+  cfg.dynamicSmemBytes = kSmemBudget;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, scan_mma_kernel<8, 4, false>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
 }
 
 inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
   CUtensorMap mq, m0, m1;
   if (make_tmap_2d(&mq, s.q, s.Q, s.D, pl.a_rows)) return 1;
-  const int b_box = pl.pair ? 128 : pl.n_tile;     // gallery rows per TMA box
+  const int b_box = pl.cl == 4 ? 64 : (pl.pair ? 128 : pl.n_tile);     // gallery rows per TMA box
   if (make_tmap_2d(&m0, s.gal[0], s.M, s.D, b_box)) return 1;
   if (s.G > 1) { if (make_tmap_2d(&m1, s.gal[1], s.M, s.D, b_box)) return 1; }
   else m1 = m0;
@@ -742,6 +832,8 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
   ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.q_blk = pl.q_blk; ma.upq = pl.upq; ma.vq = pl.vq;
   ma.W = (long long)pl.n_qb * pl.n_t;
   ma.dbg = nullptr;
+  static const char* skip_env = getenv("KEMR_MMA_DEBUG_SKIP");
+  ma.dbg_skip = skip_env ? atoi(skip_env) : 0;
   static const bool debug = getenv("KEMR_MMA_DEBUG") != nullptr;
   if (debug) {
     static long long* dbuf = nullptr;
@@ -762,7 +854,7 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
       std::vector<long long> h((size_t)pl.ctas * 16);
       cudaMemcpy(h.data(), ma.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
       double avg[16] = {0};
-      const int stride = pl.pair ? 2 : 1;        // the MMA role runs in the leader CTA of a pair
+      const int stride = pl.pair ? 2 : 1;        // the MMA role runs in the leader CTA of every pair
       const int nu = pl.ctas / stride;
       for (int c = 0; c < pl.ctas; c += stride) for (int i = 0; i < 16; ++i) avg[i] += (double)h[(size_t)c * 16 + i] / nu;
       long long tmin = 1ll << 62, tmax = 0; int cmin = 0, cmax = 0;
@@ -771,8 +863,8 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
         if (t < tmin) { tmin = t; cmin = c; }
         if (t > tmax) { tmax = t; cmax = c; }
       }
-      fprintf(stderr, "[kemr mma dbg] pair=%d merged=%d vq=%d parts=%d n_tile=%d K=%d ctas=%d tiles/unit=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f (min %lld @cta %d, max %lld @cta %d; max cta: wait_full=%lld wait_tempty=%lld) | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f  cycles\n",
-              pl.pair, pl.merged, pl.vq, pl.parts, pl.n_tile, pl.K, pl.ctas, (double)ma.W / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
+      fprintf(stderr, "[kemr mma dbg] cl=%d merged=%d vq=%d parts=%d n_tile=%d K=%d ctas=%d tiles/unit=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f (min %lld @cta %d, max %lld @cta %d; max cta: wait_full=%lld wait_tempty=%lld) | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f  cycles\n",
+              pl.cl, pl.merged, pl.vq, pl.parts, pl.n_tile, pl.K, pl.ctas, (double)ma.W / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
               tmin, cmin, tmax, cmax, h[(size_t)cmax * 16 + 2], h[(size_t)cmax * 16 + 3], avg[5], avg[6], avg[7]);
       if (getenv("KEMR_MMA_DEBUG_TRACE")) {
         std::vector<long long> tr((size_t)8 * kTraceLen);
