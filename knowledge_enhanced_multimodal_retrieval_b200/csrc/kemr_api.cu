@@ -254,39 +254,25 @@ extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, c
   s.k = k; s.eps = eps; s.idx_base = idx_base;
   s.out_score64 = out_score64; s.out_score32 = out_score32; s.out_idx = out_idx; s.out_flags = out_flags;
   s.max_cand = k_sel + (int)max_hits_per_query;
-  if (select_warp_ok(pl.P, pl.Kp, k_sel, s.max_cand)) {
-    // small case (few parts, short lists, <= 64 candidates): one CTA of W warps per query; W = 0 runs the
-    // older warp-per-query kernel (KEMR_SELECT_WARPS, experiments)
-    static const char* wenv = getenv("KEMR_SELECT_WARPS");
-    const int W = wenv ? atoi(wenv) : 4;
-    const int np = (D + 255) / 256;
-    if (W == 0) {
-      const dim3 grid((Q + kSelWarpWarps - 1) / kSelWarpWarps), block(kSelWarpWarps * 32);
-      switch (np) {
-        case 1: select_warp_kernel<1><<<grid, block, 0, st>>>(s, Q); break;
-        case 2: select_warp_kernel<2><<<grid, block, 0, st>>>(s, Q); break;
-        case 3: select_warp_kernel<3><<<grid, block, 0, st>>>(s, Q); break;
-        default: select_warp_kernel<4><<<grid, block, 0, st>>>(s, Q); break;
-      }
-      LAUNCH_CHECK("select_warp_kernel");
-      return KEMR_OK;
-    }
-#define KEMR_SELQ(NPV, WV) select_query_kernel<NPV, WV><<<Q, WV * 32, 0, st>>>(s)
-#define KEMR_SELQ_W(WV) switch (np) { case 1: KEMR_SELQ(1, WV); break; case 2: KEMR_SELQ(2, WV); break; \
-                                      case 3: KEMR_SELQ(3, WV); break; default: KEMR_SELQ(4, WV); break; }
-    if (W == 2) { KEMR_SELQ_W(2) } else if (W == 8) { KEMR_SELQ_W(8) } else { KEMR_SELQ_W(4) }
-#undef KEMR_SELQ_W
-#undef KEMR_SELQ
-    LAUNCH_CHECK("select_query_kernel");
-    return KEMR_OK;
-  }
+  s.key_slots = (int)select_key_slots(pl.Kp, k_sel);
   if (pl.P > kMaxParts) return fail(KEMR_ERR_UNSUPPORTED, "too many part lists per query (%d)", pl.P);
-  const size_t smem = select_smem_bytes(pl.P, pl.Kp, k_sel, s.max_cand, G, D);
+  const size_t smem = select_smem_bytes(pl.P, pl.Kp, k_sel, s.max_cand);
   if (smem > 200 * 1024) return fail(KEMR_ERR_UNSUPPORTED, "select kernel needs %zu bytes of shared memory", smem);
-  if (smem > 48 * 1024)
-    CUDA_TRY(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  select_rescore_kernel<<<Q, kSelectThreads, smem, st>>>(s);
-  LAUNCH_CHECK("select_rescore_kernel");
+  // one CTA per query: 4 warps for the common small case, 8 when there are many candidates to re-score
+  const int np = (D + 255) / 256;
+  const bool small = s.max_cand <= kSelSmallCand;
+#define KEMR_SEL(NPV, WV)                                                                                         \
+  do {                                                                                                            \
+    if (smem > 48 * 1024)                                                                                         \
+      CUDA_TRY(cudaFuncSetAttribute(select_kernel<NPV, WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    select_kernel<NPV, WV><<<Q, WV * 32, smem, st>>>(s);                                                          \
+  } while (0)
+#define KEMR_SEL_NP(WV) switch (np) { case 1: KEMR_SEL(1, WV); break; case 2: KEMR_SEL(2, WV); break; \
+                                      case 3: KEMR_SEL(3, WV); break; default: KEMR_SEL(4, WV); break; }
+  if (small) { KEMR_SEL_NP(4) } else { KEMR_SEL_NP(8) }
+#undef KEMR_SEL_NP
+#undef KEMR_SEL
+  LAUNCH_CHECK("select_kernel");
   return KEMR_OK;
 }
 

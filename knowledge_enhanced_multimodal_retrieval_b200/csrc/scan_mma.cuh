@@ -71,6 +71,7 @@ struct MmaPlan {
   int all_slots = 0;      // 1: every part slot of every query row is written (no memset needed)
   int two = 0;            // 1: two accumulators (T2I, T2T) with their own weights
   int merged = 0;         // 1: two galleries, equal weights: one accumulator over 2*kc K chunks
+  int ds = 0;             // 1: merged + CTA pairs: query chunk staged once per K step for both galleries
   int q_blk = 0;          // queries per block (128, or 256 for CTA pairs)
   size_t smem = 0;
 };
@@ -99,14 +100,15 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
   if (sms < 2) p->pair = 0;
   // Clusters of FOUR CTAs (two pairs): the pairs take adjacent 256-query blocks and the same gallery tiles, and
   // every CTA fetches only a quarter of the tile chunk, multicast to the CTA of the other pair that needs the same
-  // half -> 24 KB instead of 32 KB through L2 per CTA and stage (the pair kernel runs at the L2 slice limit of
-  // ~1 sector/clk/slice: ncu 0.87 sectors/clk/slice at 64 % tensor-pipe activity).  `quads` = clusters of four the
-  // device can hold at once (33 on a B200: GPC shapes leave 16 SMs unusable), so this pays only when the batch is
-  // L2-bound (>= 2 blocks) and an odd block count does not waste too much on the phantom block.
+  // half -> 24 KB instead of 32 KB through L2 per CTA and stage (the pair kernel reaches the L2 slice limit of
+  // ~1 sector/clk/slice, ncu).  `quads` = clusters of four the device can hold at once (33 on a B200: GPC shapes
+  // leave 16 SMs unusable), so this pays only for long L2-bound scans: measured +7 % on 4096 q x 1.25 M rows,
+  // -7 % on 1000 q x 43 k rows x 2 galleries (fewer SMs, 11 instead of 10 tiles per unit).
   const int n_qb256 = p->pair ? (Q + 2 * kBlockM - 1) / (2 * kBlockM) : 0;
+  const int64_t nt256 = (M + (p->two ? 128 : 256) - 1) / (p->two ? 128 : 256);
   static const char* force_cl = getenv("KEMR_MMA_CL");              // experiments: 2 = pairs only, 4 = always quads
-  bool quad = p->pair && quads >= 1 && n_qb256 >= 2 && (n_qb256 % 2 == 0 || n_qb256 >= 7);
-  if (force_cl && p->pair && quads >= 1) quad = force_cl[0] == '4';
+  bool quad = p->pair && quads >= 1 && n_qb256 >= 4 && n_qb256 % 2 == 0 && nt256 >= 1024;
+  if (force_cl && p->pair && quads >= 1 && n_qb256 >= 2) quad = force_cl[0] == '4';
   p->cl = quad ? 4 : (p->pair ? 2 : 1);
   p->q_blk = quad ? 4 * kBlockM : (p->pair ? 2 * kBlockM : kBlockM);     // queries per scheduling block (per cluster)
   p->n_tile = p->two ? 128 : 256;
@@ -178,7 +180,9 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
   p->vq = vq;
   p->parts = 2 * (vq + span - 1);
   p->all_slots = (vq == 1 && p->upq > 0) ? 1 : 0;
-  const size_t stage = (size_t)kBlockM * 128 + (p->pair ? (size_t)128 * 128 : (size_t)256 * 128);
+  static const bool no_ds = getenv("KEMR_MMA_NO_DS") != nullptr;
+  p->ds = (p->merged && p->pair && !no_ds) ? 1 : 0;
+  const size_t stage = (size_t)kBlockM * 128 + (p->pair ? (size_t)128 * 128 * (p->ds ? 2 : 1) : (size_t)256 * 128);
   const size_t epi = (size_t)kBufCap * kEpiThreads * 8;
   p->stages = (int)std::min<size_t>(kMaxStages, (kSmemBudget - 2048 - epi) / stage);
   p->smem = (size_t)p->stages * stage + epi + 1024;
@@ -325,6 +329,7 @@ struct MmaArgs {
   ScanArgs s;
   int n_tile;       // gallery rows per tile (128 with two accumulators, else 256)
   int merged;       // both galleries accumulate into ONE accumulator (equal weights): 2*kc K chunks
+  int ds;           // merged, CTA pairs: a stage holds the query chunk ONCE plus the matching chunk of BOTH galleries (8 MMAs)
   int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, upq, vq;
   long long W;
   long long* dbg;   // optional [ctas][16] cycle counters + stage trace (KEMR_MMA_DEBUG=1)
@@ -402,7 +407,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   constexpr uint32_t a_bytes = (uint32_t)kBlockM * 128u;
   constexpr uint32_t b_box = PAIR ? 128u : (uint32_t)n_tile;     // gallery rows per CTA and stage
   constexpr uint32_t b_bytes = b_box * 128u;
-  constexpr uint32_t stage_bytes = a_bytes + (PAIR ? b_bytes : 256u * 128u);
+  const bool ds = PAIR && !TWO && a.ds != 0;                    // merged double stage: A + B(T2I) + B(T2T)
+  const uint32_t stage_bytes = a_bytes + (PAIR ? (ds ? 2u * b_bytes : b_bytes) : 256u * 128u);
   const uint32_t buf_u32 = ptx::smem_u32(smem + (size_t)a.stages * stage_bytes);      // [kBufCap][kEpiThreads] x 8 B
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes + (size_t)kBufCap * kEpiThreads * 8);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -464,11 +470,12 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             // ingress experiment: the stage keeps whatever it held; only the selected operand is fetched
             const bool la = !(a.dbg_skip & 1), lb = !(a.dbg_skip & 2);
             const uint32_t lbar = PAIR ? ptx::map_to_cta(ptx::smem_u32(&full_bar[stage]), lead) : 0u;
-            const uint32_t txs = (la ? a_bytes : 0u) + (lb ? (PAIR ? b_bytes : 256u * 128u) : 0u);
+            const uint32_t txs = (la ? a_bytes : 0u) + (lb ? (PAIR ? (ds ? 2u * b_bytes : b_bytes) : 256u * 128u) : 0u);
             if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], PAIR ? 2u * txs : txs);
             if (PAIR) {
               if (la) ptx::tma_load_2d_pair(sa, &map_q, lbar, kx, qb * a.q_blk + (int)crank * kBlockM);
-              if (lb) ptx::tma_load_2d_pair(sa + a_bytes, g ? &map_g1 : &map_g0, lbar, kx, t * n_tile + (int)rank * 128);
+              if (lb) ptx::tma_load_2d_pair(sa + a_bytes, (!ds && g) ? &map_g1 : &map_g0, lbar, kx, t * n_tile + (int)rank * 128);
+              if (lb && ds) ptx::tma_load_2d_pair(sa + a_bytes + b_bytes, &map_g1, lbar, kx, t * n_tile + (int)rank * 128);
             } else {
               if (la) ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kx, qb * kBlockM);
               if (lb) ptx::tma_load_2d(sa + a_bytes, g ? &map_g1 : &map_g0, &full_bar[stage], kx, t * n_tile);
@@ -478,14 +485,17 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const uint32_t lbar = ptx::map_to_cta(ptx::smem_u32(&full_bar[stage]), lead);
             if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], tx);
             ptx::tma_load_2d_pair(sa, &map_q, lbar, kx, qb * a.q_blk + (int)crank * kBlockM);
-            const CUtensorMap* mb = TWO ? (rank ? &map_g1 : &map_g0) : (g ? &map_g1 : &map_g0);
             const int brow = t * n_tile + (TWO ? 0 : (int)rank * 128);
-            if (QUAD) {
-              // this CTA's quarter of the chunk (64 rows), multicast to the CTA of the other pair holding the same half
-              ptx::tma_load_2d_pair_mc(sa + a_bytes + pc * (64u * 128u), mb, lbar, kx, brow + (int)pc * 64,
-                                       (uint16_t)((1u << rank) | (4u << rank)));
-            } else {
-              ptx::tma_load_2d_pair(sa + a_bytes, mb, lbar, kx, brow);
+            for (int gi = 0; gi < (ds ? 2 : 1); ++gi) {
+              const CUtensorMap* mb = TWO ? (rank ? &map_g1 : &map_g0) : ((ds ? gi : g) ? &map_g1 : &map_g0);
+              unsigned char* sb = sa + a_bytes + (uint32_t)gi * b_bytes;
+              if (QUAD) {
+                // this CTA's quarter of the chunk (64 rows), multicast to the CTA of the other pair holding the same half
+                ptx::tma_load_2d_pair_mc(sb + pc * (64u * 128u), mb, lbar, kx, brow + (int)pc * 64,
+                                         (uint16_t)((1u << rank) | (4u << rank)));
+              } else {
+                ptx::tma_load_2d_pair(sb, mb, lbar, kx, brow);
+              }
             }
           } else {
             ptx::mbar_expect_tx(&full_bar[stage], tx);
@@ -520,7 +530,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, 256);
       const uint64_t adesc0 = umma_desc_sw128(ptx::smem_u32(smem));
       const uint64_t bdesc0 = umma_desc_sw128(ptx::smem_u32(smem) + a_bytes);
-      constexpr uint64_t stage_step = (uint64_t)(stage_bytes >> 4);      // descriptor start-address units (16 B)
+      const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);          // descriptor start-address units (16 B)
       long long it = 0;
       long long w_full = 0, w_tempty = 0; const long long t_begin = dbg ? clock64() : 0;
       int tr = 0;
@@ -541,6 +551,13 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             for (int k = 0; k < kBlockK / 16; ++k) {
               if (PAIR) ptx::mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kcc | k) ? 1u : 0u);
               else ptx::mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kcc | k) ? 1u : 0u);
+            }
+            if (PAIR && ds) {
+              // same query chunk against the second gallery's chunk, same accumulator
+              const uint64_t bdesc1 = bdesc + (uint64_t)(b_bytes >> 4);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                ptx::mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc1 + (uint64_t)(k * 2), idesc, 1u);
             }
             // frees the smem stage (in every CTA of the cluster) when these MMAs retire
             if (PAIR) ptx::mma_commit_pair(&empty_bar[stage], QUAD ? (uint16_t)0xF : (uint16_t)0x3); else ptx::mma_commit(&empty_bar[stage]);
@@ -828,7 +845,7 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
   MmaArgs ma;
   ma.s = s;
   ma.n_tile = pl.n_tile; ma.n_qb = pl.n_qb; ma.n_t = pl.n_t; ma.stages = pl.stages; ma.kc = pl.kc;
-  ma.merged = pl.merged; ma.kc_total = pl.merged ? 2 * pl.kc : pl.kc;
+  ma.merged = pl.merged; ma.ds = pl.ds; ma.kc_total = (pl.merged && !pl.ds) ? 2 * pl.kc : pl.kc;
   ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.q_blk = pl.q_blk; ma.upq = pl.upq; ma.vq = pl.vq;
   ma.W = (long long)pl.n_qb * pl.n_t;
   ma.dbg = nullptr;

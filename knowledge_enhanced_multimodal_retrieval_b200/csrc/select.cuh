@@ -30,398 +30,64 @@ struct SelectArgs {
   int64_t* out_idx;            // [Q][k]
   int32_t* out_flags;          // [Q]
   int max_cand;                // K + max hits per query
+  int key_slots;               // select_key_slots(Kp, K)
 };
 
-constexpr int kSelectThreads = 256;
-constexpr int kSelectWarps = kSelectThreads / 32;
-constexpr int kCountMax = 1024;          // up to this many gathered keys are ranked by counting
 constexpr int kMaxParts = 4096;          // part lists per query the head pass can hold
+constexpr int kSelSmallCand = 64;        // up to this many candidates a query is handled by a 4-warp CTA
 
-// dynamic smem (16-byte aligned pieces first):
-//   heads[P] u64 | keys[max(K*Kp, kSelectWarps*K)] u64 |
-//   cand_score[max_cand] f64 | cand_bonus[max_cand] f64 | cand_row[max_cand] i32 | cand_has[max_cand] u8
-inline size_t select_key_slots(int Kp, int K) {
-  const size_t gathered = (size_t)K * Kp, per_warp = (size_t)kSelectWarps * K;
-  return gathered > per_warp ? gathered : per_warp;
+// dynamic shared memory of select_kernel (8-byte pieces first):
+//   heads[P] u64 | keys[pow2 >= K*Kp] u64 | selk[K] u64 | score[max_cand] f64 | bonus[max_cand] f64 |
+//   lid[K] i32 | row[max_cand] i32 | has[max_cand] u8
+inline size_t select_key_slots(int Kp, int K) {      // gathered keys, rounded up to a power of two (bitonic sort)
+  size_t n = 32;
+  while (n < (size_t)K * Kp) n <<= 1;
+  return n;
 }
-inline size_t select_smem_bytes(int P, int Kp, int K, int max_cand, int G, int D) {
-  (void)G; (void)D;
-  size_t b = (size_t)P * 8 + select_key_slots(Kp, K) * 8 + (size_t)max_cand * (8 + 8 + 4);
-  b += ((size_t)max_cand + 15) & ~(size_t)15;
+constexpr int kSelCountMax = 256;        // more surviving keys than this are sorted instead of ranked by counting
+inline size_t select_smem_bytes(int P, int Kp, int K, int max_cand) {
+  size_t b = ((size_t)P + select_key_slots(Kp, K) + (size_t)K + 2 * (size_t)max_cand) * 8 + ((size_t)K + (size_t)max_cand) * 4;
+  b += (size_t)max_cand;
   return (b + 15) & ~(size_t)15;
 }
 
-__global__ void __launch_bounds__(kSelectThreads) select_rescore_kernel(SelectArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int K = a.K, Kp = a.Kp, P = a.P;
-  uint64_t* heads = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* lists = heads + P;
-  const size_t gathered = (size_t)K * Kp, per_warp = (size_t)kSelectWarps * K;
-  double* cand_score = reinterpret_cast<double*>(lists + (gathered > per_warp ? gathered : per_warp));
-  double* cand_bonus = cand_score + a.max_cand;
-  int32_t* cand_row = reinterpret_cast<int32_t*>(cand_bonus + a.max_cand);
-  unsigned char* cand_has = reinterpret_cast<unsigned char*>(cand_row + a.max_cand);
-  __shared__ int s_nsel, s_extra, s_nlist;
-  __shared__ uint64_t s_sel[kMaxKSel];
-  __shared__ int s_listid[kMaxKSel];
-  __shared__ unsigned long long s_bound;     // largest key any stage rejected (0 = nothing rejected)
-
-  const int qi = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  // this lane's share of the query row, widened to binary64 once
-  CanonQuery cq;
-  cq.load(a.q + (size_t)qi * a.D, a.D, lane);
-
-  // ---- A1. heads of all part lists; only the K lists with the largest heads can hold a top-K key
-  for (int i = threadIdx.x; i < K; i += blockDim.x) { s_sel[i] = 0; s_listid[i] = -1; }
-  if (threadIdx.x == 0) { s_bound = 0; s_nlist = 0; s_extra = 0; }
-  for (int p = threadIdx.x; p < P; p += blockDim.x) heads[p] = a.part_keys[((size_t)p * a.Q + qi) * Kp];
-  __syncthreads();
-  for (int p = threadIdx.x; p < P; p += blockDim.x) {
-    const uint64_t x = heads[p];
-    if (!x) continue;
-    int r = 0;
-    for (int j = 0; j < P; ++j) r += heads[j] > x ? 1 : 0;
-    if (r < K) { s_listid[r] = p; atomicAdd(&s_nlist, 1); }
-    else atomicMax(&s_bound, (unsigned long long)x);       // whole list rejected: nothing in it beats its head
-  }
-  __syncthreads();
-  const int nlist = s_nlist;                                // selected lists occupy s_listid[0..nlist)
-
-  // ---- A2. the K best keys among the selected lists
-  const int n2 = nlist * Kp;
-  if (n2 <= kCountMax) {
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-      const int l = i / Kp, j = i - l * Kp;
-      lists[i] = a.part_keys[((size_t)s_listid[l] * a.Q + qi) * Kp + j];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-      const uint64_t x = lists[i];
-      if (!x) continue;
-      int r = 0;
-      for (int j = 0; j < n2; ++j) r += lists[j] > x ? 1 : 0;
-      if (r < K) s_sel[r] = x;                              // keys are distinct -> ranks are distinct
-      // rejected here, or last entry of a full part list (that part rejected rows below it)
-      if (r >= K || (i % Kp) == Kp - 1) atomicMax(&s_bound, (unsigned long long)x);
-    }
-    __syncthreads();
-  } else {
-    uint64_t* mine = lists + (size_t)warp * K;
-    for (int i = lane; i < K; i += 32) mine[i] = 0;
-    __syncwarp();
-    uint64_t thr = 0;
-    unsigned long long bnd = 0;
-    for (int l = warp; l < nlist; l += kSelectWarps) {
-      const uint64_t* src = a.part_keys + ((size_t)s_listid[l] * a.Q + qi) * Kp;
-      const uint64_t last = src[Kp - 1];
-      if (last > bnd) bnd = last;                 // a full part list rejected rows below its last key
-      for (int i = 0; i < Kp; ++i) {
-        const uint64_t x = src[i];
-        if (x <= thr) { if (x > bnd) bnd = x; break; }   // sorted: this and the rest are rejected here
-        warp_list_insert(mine, K, x, lane);
-        thr = mine[K - 1];
-      }
-    }
-    if (lane == 0 && bnd) atomicMax(&s_bound, bnd);
-    __syncthreads();
-    if (warp == 0) {
-      thr = mine[K - 1];
-      for (int w2 = 1; w2 < kSelectWarps; ++w2) {
-        const uint64_t* other = lists + (size_t)w2 * K;
-        for (int i = 0; i < K; ++i) {
-          const uint64_t x = other[i];
-          if (x <= thr) { if (lane == 0 && x) atomicMax(&s_bound, (unsigned long long)x); break; }
-          warp_list_insert(mine, K, x, lane);
-          thr = mine[K - 1];
-        }
-      }
-      // keys displaced from the final list are bounded by its last key
-      if (lane == 0 && mine[K - 1]) atomicMax(&s_bound, (unsigned long long)mine[K - 1]);
-      for (int i = lane; i < K; i += 32) s_sel[i] = mine[i];
-    }
-    __syncthreads();
-  }
-  if (warp == 0) {
-    int n = 0;
-    for (int i = lane; i < K; i += 32) n += (s_sel[i] != 0);
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-    if (lane == 0) s_nsel = n;
-  }
-  __syncthreads();
-  const int nsel = s_nsel;
-  const uint64_t* sel = s_sel;
-
-  // ---- B. candidate table = scan candidates U KG hits
-  for (int i = threadIdx.x; i < nsel; i += blockDim.x) {
-    cand_row[i] = (int32_t)key_row(sel[i]);
-    cand_bonus[i] = 0.0;
-    cand_has[i] = 0;
-  }
-  __syncthreads();
-  if (a.hit_rowptr) {
-    const int64_t h0 = a.hit_rowptr[qi], h1 = a.hit_rowptr[qi + 1];
-    for (int64_t h = h0 + threadIdx.x; h < h1; h += blockDim.x) {
-      const int32_t col = a.hit_col[h];
-      if (col < 0 || (int64_t)col >= a.M) continue;
-      int found = -1;
-      for (int i = 0; i < nsel; ++i) if (cand_row[i] == col) { found = i; break; }
-      if (found < 0) {
-        found = nsel + atomicAdd(&s_extra, 1);
-        if (found >= a.max_cand) continue;      // cannot happen when max_hits_per_query is honest
-        cand_row[found] = col;
-      }
-      cand_bonus[found] = a.hit_bonus[h];
-      cand_has[found] = 1;
-    }
-  }
-  __syncthreads();
-  const int n = min(nsel + s_extra, a.max_cand);
-
-  // ---- C. canonical re-scoring, one warp per candidate, straight from coalesced 16-byte loads
-  for (int c = warp; c < n; c += kSelectWarps) {
-    const size_t off = (size_t)cand_row[c] * a.D;
-    const double sa = canon_dot_q(cq, a.gal[0] + off, a.D, lane);
-    const double sb = a.G > 1 ? canon_dot_q(cq, a.gal[1] + off, a.D, lane) : 0.0;
-    if (lane == 0)
-      cand_score[c] = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, cand_bonus[c], cand_has[c] != 0);
-  }
-  __syncthreads();
-
-  // ---- D. order by (score desc, row asc) by counting; write the first k
-  __shared__ double s_kth;
-  if (threadIdx.x == 0) s_kth = -INFINITY;
-  __syncthreads();
-  for (int c = threadIdx.x; c < n; c += blockDim.x) {
-    const double sc = cand_score[c];
-    const int32_t rc = cand_row[c];
-    int r = 0;
-    for (int j = 0; j < n; ++j) r += ahead64(cand_score[j], cand_row[j], sc, rc) ? 1 : 0;
-    if (r < a.k) {
-      const size_t o = (size_t)qi * a.k + r;
-      a.out_score64[o] = sc;
-      if (a.out_score32) a.out_score32[o] = (float)sc;
-      a.out_idx[o] = a.idx_base + rc;
-      if (r == a.k - 1) s_kth = sc;
-    }
-  }
-  for (int r = n + threadIdx.x; r < a.k; r += blockDim.x) {
-    const size_t o = (size_t)qi * a.k + r;
-    a.out_score64[o] = -INFINITY;
-    if (a.out_score32) a.out_score32[o] = -INFINITY;
-    a.out_idx[o] = -1;
-  }
-  __syncthreads();
-
-  // ---- E. certificate: nothing the scan rejected can reach the k-th canonical score
-  if (threadIdx.x == 0) {
-    int flag = 0;
-    if (s_bound) {                              // something was rejected on its fp32 score
-      const double bound = (double)key_score((uint64_t)s_bound) + a.eps * (1.0 + 1.0 / 64.0);
-      const double reach = a.alpha * bound + 1e-300;
-      if (!(n >= a.k && s_kth > reach)) flag = 1;
-    }
-    a.out_flags[qi] = flag;
-  }
-}
-
-// ------------------------------------------------------------------ fast path: one WARP per query
-// Same contract as select_rescore_kernel for the common small case (few parts, short lists, at
-// most 64 candidates): no block barriers, 4 independent queries per CTA, so a 1000-query batch
-// fits the GPU in a single wave and the re-scoring loads of different queries overlap.
-constexpr int kSelWarpWarps = 4;
-constexpr int kSelWarpMaxP = 64;
-constexpr int kSelWarpMaxKeys = 256;
-constexpr int kSelWarpMaxCand = 64;
-
-inline bool select_warp_ok(int P, int Kp, int K, int max_cand) {
-  const int nl = P < K ? P : K;
-  return P <= kSelWarpMaxP && K <= 32 && nl * Kp <= kSelWarpMaxKeys && max_cand <= kSelWarpMaxCand;
-}
-
-template <int NP>
-__global__ void __launch_bounds__(kSelWarpWarps * 32) select_warp_kernel(SelectArgs a, int nq) {
-  __shared__ uint64_t s_heads[kSelWarpWarps][kSelWarpMaxP];
-  __shared__ uint64_t s_keys[kSelWarpWarps][kSelWarpMaxKeys];
-  __shared__ uint64_t s_selk[kSelWarpWarps][32];
-  __shared__ int s_lid[kSelWarpWarps][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int qi = blockIdx.x * kSelWarpWarps + warp;
-  if (qi >= nq) return;
-  const int K = a.K, Kp = a.Kp, P = a.P;
-  uint64_t* heads = s_heads[warp];
-  uint64_t* keys = s_keys[warp];
-  uint64_t* selk = s_selk[warp];
-  int* lid = s_lid[warp];
-  unsigned long long bound = 0;                    // per-lane partial, max-reduced at the end
-
-  CanonQueryT<NP> cq;
-  cq.load(a.q + (size_t)qi * a.D, a.D, lane);
-
-  // A1. heads of the part lists -> the (at most K) lists that can hold a top-K key
-  for (int p = lane; p < P; p += 32) heads[p] = a.part_keys[((size_t)p * a.Q + qi) * Kp];
-  selk[lane] = 0; lid[lane] = -1;
-  __syncwarp();
-  int nlist = 0;
-  for (int p = lane; p < P; p += 32) {
-    const uint64_t x = heads[p];
-    if (!x) continue;
-    int r = 0;
-    for (int j = 0; j < P; ++j) r += heads[j] > x ? 1 : 0;
-    if (r < K) { lid[r] = p; ++nlist; }
-    else if (x > bound) bound = x;
-  }
-  for (int o = 16; o > 0; o >>= 1) nlist += __shfl_xor_sync(0xffffffffu, nlist, o);
-  __syncwarp();
-
-  // A2. K best keys among the selected lists
-  const int n2 = nlist * Kp;
-  for (int i = lane; i < n2; i += 32) {
-    const int l = i / Kp, j = i - l * Kp;
-    keys[i] = a.part_keys[((size_t)lid[l] * a.Q + qi) * Kp + j];
-  }
-  __syncwarp();
-  for (int i = lane; i < n2; i += 32) {
-    const uint64_t x = keys[i];
-    if (!x) continue;
-    int r = 0;
-    for (int j = 0; j < n2; ++j) r += keys[j] > x ? 1 : 0;
-    if (r < K) selk[r] = x;
-    if ((r >= K || (i % Kp) == Kp - 1) && x > bound) bound = x;
-  }
-  __syncwarp();
-  const uint64_t mykey = selk[lane];                // lane i <-> candidate i (K <= 32)
-  const int nsel = __popc(__ballot_sync(0xffffffffu, mykey != 0));
-
-  // B. candidates: lane holds candidate `lane` and (KG hits) candidate `32+lane`
-  int32_t row0 = mykey ? (int32_t)key_row(mykey) : -1, row1 = -1;
-  double bon0 = 0.0, bon1 = 0.0;
-  bool has0 = false, has1 = false;
-  int n = nsel;
-  if (a.hit_rowptr) {
-    const int64_t h0 = a.hit_rowptr[qi], h1 = a.hit_rowptr[qi + 1];
-    for (int64_t h = h0; h < h1; ++h) {             // few dozen hits: walk them warp-uniformly
-      const int32_t col = a.hit_col[h];
-      if (col < 0 || (int64_t)col >= a.M) continue;
-      const double b = a.hit_bonus[h];
-      const unsigned m0 = __ballot_sync(0xffffffffu, row0 == col);
-      const unsigned m1 = __ballot_sync(0xffffffffu, row1 == col);
-      if (m0) { if (row0 == col) { bon0 = b; has0 = true; } }
-      else if (m1) { if (row1 == col) { bon1 = b; has1 = true; } }
-      else if (n < kSelWarpMaxCand) {
-        if (n < 32) { if (lane == n) { row0 = col; bon0 = b; has0 = true; } }
-        else if (lane == n - 32) { row1 = col; bon1 = b; has1 = true; }
-        ++n;
-      }
-    }
-  }
-
-  // C. canonical re-scoring; the whole warp works on one candidate at a time, and the rows of
-  //    candidate c+1 (both galleries) are already in flight while candidate c is accumulated
-  double sc0 = 0.0, sc1 = 0.0;
-  CanonRow<NP> cur[2], nxt[2];
-  if (n > 0) {
-    const size_t off = (size_t)__shfl_sync(0xffffffffu, row0, 0) * a.D;
-    cur[0].load(a.gal[0] + off, a.D, lane);
-    if (a.G > 1) cur[1].load(a.gal[1] + off, a.D, lane);
-  }
-  for (int c = 0; c < n; ++c) {
-    if (c + 1 < n) {
-      const int32_t rown = __shfl_sync(0xffffffffu, c + 1 < 32 ? row0 : row1, (c + 1) & 31);
-      const size_t off = (size_t)rown * a.D;
-      nxt[0].load(a.gal[0] + off, a.D, lane);
-      if (a.G > 1) nxt[1].load(a.gal[1] + off, a.D, lane);
-    }
-    const double sa = cq.dot(cur[0], a.D, lane);
-    const double sb = a.G > 1 ? cq.dot(cur[1], a.D, lane) : 0.0;
-    if (lane == (c & 31)) {
-      if (c < 32) sc0 = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, bon0, has0);
-      else sc1 = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, bon1, has1);
-    }
-    cur[0] = nxt[0];
-    cur[1] = nxt[1];
-  }
-
-  // D. order by (score desc, row asc) by counting over shuffled copies; write the first k
-  int r0 = 0, r1 = 0;
-  for (int j = 0; j < n; ++j) {
-    const double sj = __shfl_sync(0xffffffffu, j < 32 ? sc0 : sc1, j & 31);
-    const int32_t rj = __shfl_sync(0xffffffffu, j < 32 ? row0 : row1, j & 31);
-    r0 += ahead64(sj, rj, sc0, row0) ? 1 : 0;
-    r1 += ahead64(sj, rj, sc1, row1) ? 1 : 0;
-  }
-  double kth = -INFINITY;
-  if (lane < n && r0 < a.k) {
-    const size_t o = (size_t)qi * a.k + r0;
-    a.out_score64[o] = sc0;
-    if (a.out_score32) a.out_score32[o] = (float)sc0;
-    a.out_idx[o] = a.idx_base + row0;
-    if (r0 == a.k - 1) kth = sc0;
-  }
-  if (32 + lane < n && r1 < a.k) {
-    const size_t o = (size_t)qi * a.k + r1;
-    a.out_score64[o] = sc1;
-    if (a.out_score32) a.out_score32[o] = (float)sc1;
-    a.out_idx[o] = a.idx_base + row1;
-    if (r1 == a.k - 1) kth = sc1;
-  }
-  for (int r = n + lane; r < a.k; r += 32) {
-    const size_t o = (size_t)qi * a.k + r;
-    a.out_score64[o] = -INFINITY;
-    if (a.out_score32) a.out_score32[o] = -INFINITY;
-    a.out_idx[o] = -1;
-  }
-
-  // E. certificate
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bound, o);
-    bound = ob > bound ? ob : bound;
-    kth = fmax(kth, __shfl_xor_sync(0xffffffffu, kth, o));
-  }
-  if (lane == 0) {
-    int flag = 0;
-    if (bound) {
-      const double b = (double)key_score((uint64_t)bound) + a.eps * (1.0 + 1.0 / 64.0);
-      const double reach = a.alpha * b + 1e-300;
-      if (!(n >= a.k && kth > reach)) flag = 1;
-    }
-    a.out_flags[qi] = flag;
-  }
-}
-
-// ------------------------------------------------------------------ fast path: one small CTA per query
-// Same contract and the same small-case limits as select_warp_kernel, but W warps share one query:
-// the merge of the part lists is done by all W*32 threads, and the candidates are dealt round-robin
-// to the warps, each keeping the rows of its NEXT candidate in flight while it accumulates the current
-// one.  select_warp_kernel walks a query's 16+ candidates one after another in a single warp, so a
-// 1000-query batch is one wave of 1000 warps whose duration is the length of that serial chain
-// (~34 us on C2, ncu); here the chain is W times shorter and W times as many row loads are in flight.
+// One CTA of W warps per query.  Merges the query's P part lists into the K best fp32-scored candidates,
+// adds the KG hits, re-scores every candidate canonically (binary64), orders them and emits the certificate.
+//   A1  heads of the P lists: only the K lists with the largest heads can hold a top-K key;
+//   A2  keys of those lists that are not below the K-th head (K keys are already >= it) are ranked by counting;
+//   A3  candidates past the k-th whose fp32 score is more than 2 eps below the k-th fp32 score cannot reach the
+//       top k (|fp32 - canonical| <= eps, a KG bonus only raises the k-th score): not re-scored, counted as
+//       rejected for the certificate; KG hits among them come back through the hit list;
+//   B   candidate table = scan candidates U KG hits;
+//   C   warp w re-scores candidates w, w+W, ...; the rows of its next candidate are in flight meanwhile;
+//   D   order by (score desc, row asc) by counting, write the first k;   E  certificate.
 template <int NP, int W>
-__global__ void __launch_bounds__(W * 32) select_query_kernel(SelectArgs a) {
+__global__ void __launch_bounds__(W * 32) select_kernel(SelectArgs a) {
   constexpr int T = W * 32;
-  __shared__ uint64_t s_heads[kSelWarpMaxP];
-  __shared__ uint64_t s_keys[kSelWarpMaxKeys];
-  __shared__ uint64_t s_selk[32];
-  __shared__ int s_lid[32];
-  __shared__ int32_t s_row[kSelWarpMaxCand];
-  __shared__ double s_bonus[kSelWarpMaxCand];
-  __shared__ double s_score[kSelWarpMaxCand];
-  __shared__ unsigned char s_has[kSelWarpMaxCand];
-  __shared__ unsigned long long s_bound;
-  __shared__ int s_nlist, s_extra, s_nsurv;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = a.K, Kp = a.Kp, P = a.P, MC = a.max_cand;
+  uint64_t* s_heads = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* s_keys = s_heads + P;
+  uint64_t* s_selk = s_keys + a.key_slots;
+  double* s_score = reinterpret_cast<double*>(s_selk + K);
+  double* s_bonus = s_score + MC;
+  int* s_lid = reinterpret_cast<int*>(s_bonus + MC);
+  int32_t* s_row = s_lid + K;
+  unsigned char* s_has = reinterpret_cast<unsigned char*>(s_row + MC);
+  __shared__ unsigned long long s_bound;     // largest key any stage rejected (0 = nothing rejected)
+  __shared__ unsigned long long s_cut;
+  __shared__ int s_nlist, s_extra, s_nsurv, s_nsel, s_first;
   __shared__ double s_kth;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int qi = blockIdx.x;
-  const int K = a.K, Kp = a.Kp, P = a.P;
 
   CanonQueryT<NP> cq;
   cq.load(a.q + (size_t)qi * a.D, a.D, lane);
 
-  // A1. heads of the part lists -> the (at most K) lists that can hold a top-K key
+  // A1
   for (int p = tid; p < P; p += T) s_heads[p] = a.part_keys[((size_t)p * a.Q + qi) * Kp];
-  if (tid < 32) { s_selk[tid] = 0; s_lid[tid] = -1; }
-  if (tid == 0) { s_bound = 0; s_nlist = 0; s_extra = 0; s_nsurv = 0; s_kth = -INFINITY; }
+  for (int i = tid; i < K; i += T) { s_selk[i] = 0; s_lid[i] = -1; }
+  if (tid == 0) { s_bound = 0; s_cut = 0; s_nlist = 0; s_extra = 0; s_nsurv = 0; s_nsel = 0; s_first = K; s_kth = -INFINITY; }
   __syncthreads();
   for (int p = tid; p < P; p += T) {
     const uint64_t x = s_heads[p];
@@ -429,24 +95,45 @@ __global__ void __launch_bounds__(W * 32) select_query_kernel(SelectArgs a) {
     int r = 0;
     for (int j = 0; j < P; ++j) r += s_heads[j] > x ? 1 : 0;
     if (r < K) { s_lid[r] = p; atomicAdd(&s_nlist, 1); }
-    else atomicMax(&s_bound, (unsigned long long)x);
+    else atomicMax(&s_bound, (unsigned long long)x);       // whole list rejected: nothing in it beats its head
   }
   __syncthreads();
 
-  // A2. K best keys among the selected lists.  When K lists were selected their heads alone are K keys
-  //     >= the K-th head, so anything below that head is out; only the survivors are ranked by counting.
-  const int nlist = s_nlist;
-  const uint64_t cut = nlist >= K ? s_heads[s_lid[K - 1]] : 0ull;
+  // A2
+  const int nlist = s_nlist;                                // selected lists occupy s_lid[0..nlist), by head rank
+  // A lower bound of the K-th best key: the first jc entries of every selected list are jc*nlist >= K keys, so the
+  // K-th largest of them (jc = 1: the K-th head) is at most the K-th best overall; anything below it is out.
+  uint64_t cut = 0;
+  if (nlist >= K) {
+    cut = s_heads[s_lid[K - 1]];
+  } else if (nlist > 0) {
+    const int jc = min(Kp, (K + nlist - 1) / nlist);
+    const int nsub = nlist * jc;                            // <= K + nlist - 1 < 2K <= key slots
+    for (int i = tid; i < nsub; i += T) {
+      const int l = i / jc, j = i - l * jc;
+      s_keys[i] = a.part_keys[((size_t)s_lid[l] * a.Q + qi) * Kp + j];
+    }
+    __syncthreads();
+    for (int i = tid; i < nsub; i += T) {
+      const uint64_t x = s_keys[i];
+      if (!x) continue;
+      int r = 0;
+      for (int j = 0; j < nsub; ++j) r += s_keys[j] > x ? 1 : 0;
+      if (r == K - 1) s_cut = x;                            // exists only if the subset holds K non-empty keys
+    }
+    __syncthreads();
+    cut = s_cut;
+  }
   {
     const int n2 = nlist * Kp;
-    unsigned long long rej = 0;                          // largest key this thread saw rejected
+    unsigned long long rej = 0;                             // largest key this thread saw rejected
     for (int i = tid; i < n2; i += T) {
       const int l = i / Kp, j = i - l * Kp;
       const uint64_t x = a.part_keys[((size_t)s_lid[l] * a.Q + qi) * Kp + j];
       if (!x) continue;
       if (x >= cut) s_keys[atomicAdd(&s_nsurv, 1)] = x;
       else if (x > rej) rej = x;
-      if (j == Kp - 1 && x > rej) rej = x;               // a full part list rejected rows below its last key
+      if (j == Kp - 1 && x > rej) rej = x;                  // a full part list rejected rows below its last key
     }
     for (int o = 16; o > 0; o >>= 1) {
       const unsigned long long other = __shfl_xor_sync(0xffffffffu, rej, o);
@@ -456,31 +143,56 @@ __global__ void __launch_bounds__(W * 32) select_query_kernel(SelectArgs a) {
   }
   __syncthreads();
   const int ns = s_nsurv;
-  for (int i = tid; i < ns; i += T) {
-    const uint64_t x = s_keys[i];
-    int r = 0;
-    for (int j = 0; j < ns; ++j) r += s_keys[j] > x ? 1 : 0;
-    if (r < K) s_selk[r] = x;                            // keys are distinct -> ranks are distinct
-    else atomicMax(&s_bound, (unsigned long long)x);
+  if (ns <= kSelCountMax) {
+    for (int i = tid; i < ns; i += T) {
+      const uint64_t x = s_keys[i];
+      int r = 0;
+      for (int j = 0; j < ns; ++j) r += s_keys[j] > x ? 1 : 0;
+      if (r < K) { s_selk[r] = x; atomicAdd(&s_nsel, 1); }  // keys are distinct -> ranks are distinct
+      else atomicMax(&s_bound, (unsigned long long)x);
+    }
+  } else {
+    // few lists with long tails (fewer lists than K: nothing could be pruned): bitonic sort, descending
+    int n2p = 32;
+    while (n2p < ns) n2p <<= 1;
+    for (int i = ns + tid; i < n2p; i += T) s_keys[i] = 0;
+    __syncthreads();
+    for (int kk = 2; kk <= n2p; kk <<= 1) {
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < n2p; i += T) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const uint64_t x = s_keys[i], y = s_keys[ixj];
+            const bool desc = (i & kk) == 0;
+            if (desc ? (x < y) : (x > y)) { s_keys[i] = y; s_keys[ixj] = x; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = tid; i < K && i < ns; i += T) s_selk[i] = s_keys[i];
+    if (tid == 0) {
+      s_nsel = ns < K ? ns : K;
+      if (ns > K) atomicMax(&s_bound, (unsigned long long)s_keys[K]);     // largest key rejected here
+    }
   }
   __syncthreads();
-  int nsel = __popc(__ballot_sync(0xffffffffu, s_selk[lane] != 0));          // keys fill s_selk[0..nsel), descending
-  // Candidates past the k-th whose fp32 score lies more than 2 eps below the k-th fp32 score cannot reach
-  // the top k (|fp32 - canonical| <= eps; a KG bonus only raises the k-th score): they are not re-scored
-  // and count as rejected for the certificate.  KG hits among them come back through the hit list.
+
+  // A3 (keys fill s_selk[0..nsel) in descending order, so everything from the first dropped key on drops)
+  int nsel = s_nsel;
   if (nsel > a.k) {
     const double kth32 = (double)key_score(s_selk[a.k - 1]) - 2.0 * a.eps * (1.0 + 1.0 / 64.0);
-    const bool drop = lane >= a.k && lane < nsel && (double)key_score(s_selk[lane]) < kth32;
-    const unsigned m = __ballot_sync(0xffffffffu, drop);
-    if (m) {
-      const int first = __ffs(m) - 1;                    // descending order: everything from `first` on drops
-      if (tid == 0) atomicMax(&s_bound, (unsigned long long)s_selk[first]);
-      nsel = first;
+    for (int i = a.k + tid; i < nsel; i += T)
+      if ((double)key_score(s_selk[i]) < kth32) atomicMin(&s_first, i);
+    __syncthreads();
+    if (s_first < nsel) {
+      nsel = s_first;
+      if (tid == 0) atomicMax(&s_bound, (unsigned long long)s_selk[nsel]);
     }
   }
 
-  // B. candidate table = scan candidates U KG hits
-  if (tid < nsel) { s_row[tid] = (int32_t)key_row(s_selk[tid]); s_bonus[tid] = 0.0; s_has[tid] = 0; }
+  // B
+  for (int i = tid; i < nsel; i += T) { s_row[i] = (int32_t)key_row(s_selk[i]); s_bonus[i] = 0.0; s_has[i] = 0; }
   __syncthreads();
   if (a.hit_rowptr) {
     const int64_t h0 = a.hit_rowptr[qi], h1 = a.hit_rowptr[qi + 1];
@@ -491,7 +203,7 @@ __global__ void __launch_bounds__(W * 32) select_query_kernel(SelectArgs a) {
       for (int i = 0; i < nsel; ++i) if (s_row[i] == col) { found = i; break; }
       if (found < 0) {
         found = nsel + atomicAdd(&s_extra, 1);
-        if (found >= kSelWarpMaxCand) continue;      // cannot happen when max_hits_per_query is honest
+        if (found >= MC) continue;                          // cannot happen when max_hits_per_query is honest
         s_row[found] = col;
       }
       s_bonus[found] = a.hit_bonus[h];
@@ -499,38 +211,47 @@ __global__ void __launch_bounds__(W * 32) select_query_kernel(SelectArgs a) {
     }
     __syncthreads();
   }
-  const int n = min(nsel + s_extra, kSelWarpMaxCand);
+  const int n = min(nsel + s_extra, MC);
 
-  // C. canonical re-scoring: warp w takes candidates w, w+W, ...; the rows of its next candidate are in
-  //    flight while the current one is accumulated (two register sets, roles alternate)
+  // C (two register sets, roles alternate).  An item is two rows re-scored together with interleaved reduction
+  //   chains: the T2I and T2T row of one candidate, or -- single gallery -- the rows of two candidates.
   {
     CanonRow<NP> ra[2], rb[2];
+    const bool two = a.G > 1;
+    const int step = two ? W : 2 * W;                       // candidates consumed per round of the CTA
     auto fetch = [&](int set, int c) {
       const size_t off = (size_t)s_row[c] * a.D;
       ra[set].load(a.gal[0] + off, a.D, lane);
-      if (a.G > 1) rb[set].load(a.gal[1] + off, a.D, lane);
+      if (two) rb[set].load(a.gal[1] + off, a.D, lane);
+      else rb[set].load(a.gal[0] + (size_t)s_row[min(c + W, n - 1)] * a.D, a.D, lane);
     };
     auto score = [&](int set, int c) {
-      double sa, sb = 0.0;
-      if (a.G > 1) cq.dot2_lane0(ra[set], rb[set], a.D, lane, sa, sb);
-      else sa = cq.dot(ra[set], a.D, lane);
-      if (lane == 0) s_score[c] = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, s_bonus[c], s_has[c] != 0);
+      double sa, sb;
+      cq.dot2_lane0(ra[set], rb[set], a.D, lane, sa, sb);
+      if (lane == 0) {
+        if (two) {
+          s_score[c] = canon_fuse(sa, sb, true, a.w[0], a.w[1], a.alpha, s_bonus[c], s_has[c] != 0);
+        } else {
+          s_score[c] = canon_fuse(sa, 0.0, false, a.w[0], a.w[1], a.alpha, s_bonus[c], s_has[c] != 0);
+          if (c + W < n) s_score[c + W] = canon_fuse(sb, 0.0, false, a.w[0], a.w[1], a.alpha, s_bonus[c + W], s_has[c + W] != 0);
+        }
+      }
     };
     int c = warp;
     if (c < n) fetch(0, c);
     while (c < n) {
-      if (c + W < n) fetch(1, c + W);
+      if (c + step < n) fetch(1, c + step);
       score(0, c);
-      c += W;
+      c += step;
       if (c >= n) break;
-      if (c + W < n) fetch(0, c + W);
+      if (c + step < n) fetch(0, c + step);
       score(1, c);
-      c += W;
+      c += step;
     }
   }
   __syncthreads();
 
-  // D. order by (score desc, row asc) by counting; write the first k
+  // D
   for (int c = tid; c < n; c += T) {
     const double sc = s_score[c];
     const int32_t rc = s_row[c];
@@ -552,7 +273,7 @@ __global__ void __launch_bounds__(W * 32) select_query_kernel(SelectArgs a) {
   }
   __syncthreads();
 
-  // E. certificate
+  // E: nothing the scan or the stages above rejected can reach the k-th canonical score
   if (tid == 0) {
     int flag = 0;
     if (s_bound) {
