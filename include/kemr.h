@@ -127,6 +127,35 @@ int kemr_rank_count(const uint16_t* q, int Q,
                     int64_t* out_count, int32_t* out_flags,
                     void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream);
 
+/* ---- per-query fusion weights: the gated fusion heads of the reference (fusion_model.py:9-23 SimpleGatedFusionWithBias,
+ * :136-180 GatedFusionHead, :182-196 SimpleGatedFusion: scores = gate(q)*T2I + (1-gate(q))*T2T, evaluated there
+ * block by block into an (N,N) host matrix, evaluator_fusion.py:76-121).  Same contract as the scalar calls with
+ *     clip(q,j) = fl(fl(w_a_q[q]*S_a) + fl(w_b_q[q]*S_b)),   w_*_q: DEVICE arrays of Q binary64 weights;
+ * both galleries are required.  The weights ride in the epilogue of the scan (one TMEM lane = one query). */
+int kemr_scan_topk_gated(const uint16_t* q, int Q,
+                         const uint16_t* gal_a, const uint16_t* gal_b, int64_t M, int D,
+                         const double* w_a_q, const double* w_b_q, double alpha,
+                         const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
+                         int64_t max_hits_per_query,
+                         int k, int k_sel, double eps, int64_t idx_base,
+                         double* out_score64, float* out_score32, int64_t* out_idx, int32_t* out_flags,
+                         void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream);
+int kemr_rank_count_gated(const uint16_t* q, int Q,
+                          const uint16_t* gal_a, const uint16_t* gal_b, int64_t M, int D,
+                          const double* w_a_q, const double* w_b_q, double alpha,
+                          const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
+                          const double* t_score64, const int64_t* t_gidx, double eps, int64_t idx_base,
+                          int64_t* out_count, int32_t* out_flags,
+                          void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream);
+int kemr_score_pairs_gated(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
+                           const double* w_a_q, const double* w_b_q, double alpha,
+                           const int32_t* pair_q, const int64_t* pair_row, const double* pair_bonus,
+                           int64_t n_pairs, double* out_score64, kemr_stream_t stream);
+/* gate of the linear gated heads in fp32: gate[q] = sigmoid(sum_d q[q][d]*weight[d] + bias)
+ * (fusion_model.py:18-19, :190-191); writes w_a_q = gate, w_b_q = fl32(1 - gate) widened to binary64. */
+int kemr_gate_linear(const uint16_t* q, int Q, int D, const float* weight, float bias,
+                     double* out_w_a_q, double* out_w_b_q, kemr_stream_t stream);
+
 /* ---- dense fp32 fused similarity matrix out[q*ld + j] = fl32(w_a*S_a + w_b*S_b) as the scan
  * kernels compute it (compatibility with callers that want the matrix: metrics.py:102,145-148). */
 int kemr_score_matrix(const uint16_t* q, int Q,

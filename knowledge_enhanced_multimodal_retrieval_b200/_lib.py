@@ -19,6 +19,7 @@ EXPORTS = (
     "kemr_matrix_rank", "kemr_matrix_topk", "kemr_matrix_fuse", "kemr_metrics_reduce",
     "kemr_metrics_reduce_host", "kemr_merge_topk", "kemr_index_create", "kemr_index_destroy",
     "kemr_index_search_host", "kemr_set_scan_done_event", "kemr_scan_plan",
+    "kemr_scan_topk_gated", "kemr_rank_count_gated", "kemr_score_pairs_gated", "kemr_gate_linear",
 )
 
 
@@ -44,6 +45,12 @@ def _declare(lib):
     lib.kemr_scan_topk.argtypes = [p, i32, p, p, i64, i32, f64, f64, f64, p, p, p, i64, i32, i32, f64, i64,
                                    p, p, p, p, p, sz, i32, p]
     lib.kemr_score_pairs.argtypes = [p, p, p, i32, f64, f64, f64, p, p, p, i64, p, p]
+    lib.kemr_scan_topk_gated.argtypes = [p, i32, p, p, i64, i32, p, p, f64, p, p, p, i64, i32, i32, f64, i64,
+                                         p, p, p, p, p, sz, i32, p]
+    lib.kemr_rank_count_gated.argtypes = [p, i32, p, p, i64, i32, p, p, f64, p, p, p, p, p, f64, i64,
+                                          p, p, p, sz, i32, p]
+    lib.kemr_score_pairs_gated.argtypes = [p, p, p, i32, p, p, f64, p, p, p, i64, p, p]
+    lib.kemr_gate_linear.argtypes = [p, i32, i32, p, f32, p, p, p]
     lib.kemr_rank_count.argtypes = [p, i32, p, p, i64, i32, f64, f64, f64, p, p, p, p, p, f64, i64,
                                     p, p, p, sz, i32, p]
     lib.kemr_score_matrix.argtypes = [p, i32, p, p, i64, i32, f32, f32, p, i64, p, sz, i32, p]

@@ -190,7 +190,7 @@ extern "C" size_t kemr_workspace_bytes(int Q, int64_t M, int D, int k_sel, int64
   size_t count = align_up((size_t)Q * 8) + align_up((size_t)Q * 8) + align_up((size_t)P * Qp * 4) + 256 +
                  align_up(((size_t)1 << 20) * 8 + (size_t)Q * 256 * 8);
   (void)M; (void)D;
-  return std::max(topk, count) + 4096;
+  return std::max(topk, count) + 2 * align_up((size_t)Q * 4) + 4096;
 }
 
 template <int QB, int CH>
@@ -210,14 +210,23 @@ static int launch_warp_scan(const ScanArgs& a, const ScanPlan& pl, cudaStream_t 
 }
 
 // ----------------------------------------------------------------------------- scan + top-k
-extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
-                              int64_t M, int D, double w_a, double w_b, double alpha,
-                              const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
-                              int64_t max_hits_per_query, int k, int k_sel, double eps, int64_t idx_base,
-                              double* out_score64, float* out_score32, int64_t* out_idx, int32_t* out_flags,
-                              void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream) {
+// per-query weights for the fp32 scan kernels: binary64 [Q] -> fp32 [Q]
+__global__ void weights_to_f32_kernel(const double* __restrict__ wa, const double* __restrict__ wb, int Q,
+                                      float* __restrict__ oa, float* __restrict__ ob) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Q) { oa[i] = (float)wa[i]; ob[i] = (float)wb[i]; }
+}
+
+static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
+                          int64_t M, int D, double w_a, double w_b, const double* wq_a, const double* wq_b, double alpha,
+                          const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
+                          int64_t max_hits_per_query, int k, int k_sel, double eps, int64_t idx_base,
+                          double* out_score64, float* out_score32, int64_t* out_idx, int32_t* out_flags,
+                          void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream) {
   int rc = check_common(q, Q, gal_a, M, D);
   if (rc) return rc;
+  if ((wq_a != nullptr) != (wq_b != nullptr)) return fail(KEMR_ERR_ARG, "per-query weights need both arrays");
+  if (wq_a && !gal_b) return fail(KEMR_ERR_ARG, "per-query weights need two galleries");
   if (k <= 0 || k_sel < k || k_sel > kMaxKSel) return fail(KEMR_ERR_ARG, "need 0 < k <= k_sel <= %d (k=%d, k_sel=%d)", kMaxKSel, k, k_sel);
   if (!(alpha > 0.0)) return fail(KEMR_ERR_ARG, "alpha must be > 0 for the sparse KG-boost path (alpha=%g)", alpha);
   if (!out_score64 || !out_idx || !out_flags) return fail(KEMR_ERR_ARG, "null output pointer");
@@ -228,16 +237,25 @@ extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, c
   if ((rc = dev_info(&dv))) return rc;
   const int G = gal_b ? 2 : 1;
   ScanPlan pl;
-  if ((rc = make_plan(Q, M, D, G, k_sel, kModeTopk, path, (float)w_a == (float)w_b, dv, &pl))) return rc;
+  if ((rc = make_plan(Q, M, D, G, k_sel, kModeTopk, path, !wq_a && (float)w_a == (float)w_b, dv, &pl))) return rc;
   const int Qrows = pl.path == KEMR_PATH_MMA ? pl.mma.q_pad : Q;
   const size_t need = parts_bytes(pl.P, Qrows, pl.Kp);
-  if (!workspace || workspace_bytes < need) return fail(KEMR_ERR_WORKSPACE, "scan_topk needs %zu workspace bytes, got %zu", need, workspace_bytes);
+  const size_t need_w = wq_a ? 2 * align_up((size_t)Q * 4) : 0;
+  if (!workspace || workspace_bytes < need + need_w) return fail(KEMR_ERR_WORKSPACE, "scan_topk needs %zu workspace bytes, got %zu", need + need_w, workspace_bytes);
   cudaStream_t st = S(stream);
   uint64_t* part_keys = reinterpret_cast<uint64_t*>(workspace);
+  float* wq32[2] = {nullptr, nullptr};
+  if (wq_a) {
+    wq32[0] = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + need);
+    wq32[1] = wq32[0] + align_up((size_t)Q * 4) / 4;
+    weights_to_f32_kernel<<<(Q + 255) / 256, 256, 0, st>>>(wq_a, wq_b, Q, wq32[0], wq32[1]);
+    LAUNCH_CHECK("weights_to_f32_kernel");
+  }
 
   ScanArgs a{};
   a.q = q; a.Q = Q; a.gal[0] = gal_a; a.gal[1] = gal_b; a.G = G; a.M = M; a.D = D;
-  a.w[0] = (float)w_a; a.w[1] = (float)w_b; a.mode = kModeTopk; a.K = pl.Kp; a.part_keys = part_keys;
+  a.w[0] = (float)w_a; a.w[1] = (float)w_b; a.wq[0] = wq32[0]; a.wq[1] = wq32[1];
+  a.mode = kModeTopk; a.K = pl.Kp; a.part_keys = part_keys;
   if (pl.path == KEMR_PATH_MMA) {
     if (!pl.mma.all_slots) CUDA_TRY(cudaMemsetAsync(part_keys, 0, need, st));   // unwritten slots must read as empty
     if ((rc = mma_launch(a, pl.mma, st))) return fail(KEMR_ERR_CUDA, "tcgen05 scan launch failed: %s", mma_last_error());
@@ -249,7 +267,7 @@ extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, c
   SelectArgs s{};
   s.part_keys = part_keys; s.P = pl.P; s.Q = Qrows; s.K = k_sel; s.Kp = pl.Kp;
   s.q = q; s.gal[0] = gal_a; s.gal[1] = gal_b; s.G = G; s.D = D; s.M = M;
-  s.w[0] = w_a; s.w[1] = w_b; s.alpha = alpha;
+  s.w[0] = w_a; s.w[1] = w_b; s.wq[0] = wq_a; s.wq[1] = wq_b; s.alpha = alpha;
   s.hit_rowptr = hit_rowptr; s.hit_col = hit_col; s.hit_bonus = hit_bonus;
   s.k = k; s.eps = eps; s.idx_base = idx_base;
   s.out_score64 = out_score64; s.out_score32 = out_score32; s.out_idx = out_idx; s.out_flags = out_flags;
@@ -276,23 +294,63 @@ extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, c
   return KEMR_OK;
 }
 
-extern "C" int kemr_score_pairs(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
-                                double w_a, double w_b, double alpha, const int32_t* pair_q,
-                                const int64_t* pair_row, const double* pair_bonus, int64_t n_pairs,
-                                double* out_score64, kemr_stream_t stream) {
+extern "C" int kemr_scan_topk(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
+                              int64_t M, int D, double w_a, double w_b, double alpha,
+                              const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
+                              int64_t max_hits_per_query, int k, int k_sel, double eps, int64_t idx_base,
+                              double* out_score64, float* out_score32, int64_t* out_idx, int32_t* out_flags,
+                              void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream) {
+  return scan_topk_impl(q, Q, gal_a, gal_b, M, D, w_a, w_b, nullptr, nullptr, alpha, hit_rowptr, hit_col, hit_bonus,
+                        max_hits_per_query, k, k_sel, eps, idx_base, out_score64, out_score32, out_idx, out_flags,
+                        workspace, workspace_bytes, path, stream);
+}
+
+extern "C" int kemr_scan_topk_gated(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
+                                    int64_t M, int D, const double* w_a_q, const double* w_b_q, double alpha,
+                                    const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
+                                    int64_t max_hits_per_query, int k, int k_sel, double eps, int64_t idx_base,
+                                    double* out_score64, float* out_score32, int64_t* out_idx, int32_t* out_flags,
+                                    void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream) {
+  if (!w_a_q || !w_b_q) return fail(KEMR_ERR_ARG, "scan_topk_gated: null weight array");
+  return scan_topk_impl(q, Q, gal_a, gal_b, M, D, 0.0, 0.0, w_a_q, w_b_q, alpha, hit_rowptr, hit_col, hit_bonus,
+                        max_hits_per_query, k, k_sel, eps, idx_base, out_score64, out_score32, out_idx, out_flags,
+                        workspace, workspace_bytes, path, stream);
+}
+
+static int score_pairs_impl(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
+                            double w_a, double w_b, const double* wq_a, const double* wq_b, double alpha,
+                            const int32_t* pair_q, const int64_t* pair_row, const double* pair_bonus, int64_t n_pairs,
+                            double* out_score64, kemr_stream_t stream) {
   if (!q || !gal_a || !pair_q || !pair_row || !out_score64) return fail(KEMR_ERR_ARG, "score_pairs: null pointer");
   if (D <= 0 || D > kMaxD) return fail(KEMR_ERR_ARG, "score_pairs: bad D");
   if (n_pairs <= 0) return KEMR_OK;
   const int64_t blocks = std::min<int64_t>((n_pairs + 7) / 8, 148 * 8);
-  score_pairs_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(q, gal_a, gal_b, D, w_a, w_b, alpha, pair_q,
+  score_pairs_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(q, gal_a, gal_b, D, w_a, w_b, wq_a, wq_b, alpha, pair_q,
                                                               pair_row, pair_bonus, n_pairs, out_score64);
   LAUNCH_CHECK("score_pairs_kernel");
   return KEMR_OK;
 }
 
+extern "C" int kemr_score_pairs(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
+                                double w_a, double w_b, double alpha, const int32_t* pair_q,
+                                const int64_t* pair_row, const double* pair_bonus, int64_t n_pairs,
+                                double* out_score64, kemr_stream_t stream) {
+  return score_pairs_impl(q, gal_a, gal_b, D, w_a, w_b, nullptr, nullptr, alpha, pair_q, pair_row, pair_bonus, n_pairs,
+                          out_score64, stream);
+}
+
+extern "C" int kemr_score_pairs_gated(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
+                                      const double* w_a_q, const double* w_b_q, double alpha, const int32_t* pair_q,
+                                      const int64_t* pair_row, const double* pair_bonus, int64_t n_pairs,
+                                      double* out_score64, kemr_stream_t stream) {
+  if (!w_a_q || !w_b_q || !gal_b) return fail(KEMR_ERR_ARG, "score_pairs_gated: needs both weight arrays and two galleries");
+  return score_pairs_impl(q, gal_a, gal_b, D, 0.0, 0.0, w_a_q, w_b_q, alpha, pair_q, pair_row, pair_bonus, n_pairs,
+                          out_score64, stream);
+}
+
 // ----------------------------------------------------------------------------- rank counting
-extern "C" int kemr_rank_count(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
-                               int64_t M, int D, double w_a, double w_b, double alpha,
+static int rank_count_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
+                               int64_t M, int D, double w_a, double w_b, const double* wq_a, const double* wq_b, double alpha,
                                const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
                                const double* t_score64, const int64_t* t_gidx, double eps, int64_t idx_base,
                                int64_t* out_count, int32_t* out_flags, void* workspace,
@@ -306,7 +364,8 @@ extern "C" int kemr_rank_count(const uint16_t* q, int Q, const uint16_t* gal_a, 
   if ((rc = dev_info(&dv))) return rc;
   const int G = gal_b ? 2 : 1;
   ScanPlan pl;
-  if ((rc = make_plan(Q, M, D, G, 16, kModeCount, path, (float)w_a == (float)w_b, dv, &pl))) return rc;
+  if ((wq_a != nullptr) != (wq_b != nullptr) || (wq_a && !gal_b)) return fail(KEMR_ERR_ARG, "per-query weights need both arrays and two galleries");
+  if ((rc = make_plan(Q, M, D, G, 16, kModeCount, path, !wq_a && (float)w_a == (float)w_b, dv, &pl))) return rc;
   const int Qrows = pl.path == KEMR_PATH_MMA ? pl.mma.q_pad : Q;
 
   // carve: band_lo | band_hi | part_count | amb_counter | amb_q | amb_row
@@ -315,6 +374,7 @@ extern "C" int kemr_rank_count(const uint16_t* q, int Q, const uint16_t* gal_a, 
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
   const size_t o_lo = take((size_t)Qrows * 4), o_hi = take((size_t)Qrows * 4);
   const size_t o_pc = take((size_t)pl.P * Qrows * 4), o_ctr = take(256);
+  const size_t o_w0 = take(wq_a ? (size_t)Q * 4 : 0), o_w1 = take(wq_a ? (size_t)Q * 4 : 0);
   if (!workspace || workspace_bytes < off + 2 * 4096) return fail(KEMR_ERR_WORKSPACE, "rank_count needs at least %zu workspace bytes, got %zu", off + 2 * 4096, workspace_bytes);
   const size_t left = workspace_bytes - off;
   const unsigned int amb_cap = (unsigned int)std::min<size_t>((left - 512) / 8, 0x7fffffffu);
@@ -327,6 +387,12 @@ extern "C" int kemr_rank_count(const uint16_t* q, int Q, const uint16_t* gal_a, 
   uint32_t* amb_row = reinterpret_cast<uint32_t*>(p + o_ar);
   cudaStream_t st = S(stream);
 
+  float* wq32[2] = {nullptr, nullptr};
+  if (wq_a) {
+    wq32[0] = reinterpret_cast<float*>(p + o_w0); wq32[1] = reinterpret_cast<float*>(p + o_w1);
+    weights_to_f32_kernel<<<(Q + 255) / 256, 256, 0, st>>>(wq_a, wq_b, Q, wq32[0], wq32[1]);
+    LAUNCH_CHECK("weights_to_f32_kernel");
+  }
   CUDA_TRY(cudaMemsetAsync(amb_counter, 0, 256, st));
   if (Qrows > Q) {   // padded query rows of the tensor path never count
     CUDA_TRY(cudaMemsetAsync(band_lo, 0x7f, (size_t)Qrows * 4, st));   // ~3.4e38
@@ -337,7 +403,7 @@ extern "C" int kemr_rank_count(const uint16_t* q, int Q, const uint16_t* gal_a, 
 
   ScanArgs a{};
   a.q = q; a.Q = Q; a.gal[0] = gal_a; a.gal[1] = gal_b; a.G = G; a.M = M; a.D = D;
-  a.w[0] = (float)w_a; a.w[1] = (float)w_b; a.mode = kModeCount; a.K = 16;
+  a.w[0] = (float)w_a; a.w[1] = (float)w_b; a.wq[0] = wq32[0]; a.wq[1] = wq32[1]; a.mode = kModeCount; a.K = 16;
   a.band_lo = band_lo; a.band_hi = band_hi; a.part_count = part_count;
   a.amb_q = amb_q; a.amb_row = amb_row; a.amb_counter = amb_counter; a.amb_cap = amb_cap;
   if (pl.path == KEMR_PATH_MMA) {
@@ -352,7 +418,7 @@ extern "C" int kemr_rank_count(const uint16_t* q, int Q, const uint16_t* gal_a, 
   rank_sum_parts_kernel<<<(Q + 255) / 256, 256, 0, st>>>(part_count, pl.P, Q, Qrows, amb_counter, amb_cap, count, out_flags);
   LAUNCH_CHECK("rank_sum_parts_kernel");
   RankFixArgs f{};
-  f.q = q; f.gal[0] = gal_a; f.gal[1] = gal_b; f.G = G; f.D = D; f.w[0] = w_a; f.w[1] = w_b; f.alpha = alpha;
+  f.q = q; f.gal[0] = gal_a; f.gal[1] = gal_b; f.G = G; f.D = D; f.w[0] = w_a; f.w[1] = w_b; f.wq[0] = wq_a; f.wq[1] = wq_b; f.alpha = alpha;
   f.t = t_score64; f.t_gidx = t_gidx; f.idx_base = idx_base; f.count = count;
   rank_amb_kernel<<<dv.sms * 4, 256, 0, st>>>(f, amb_q, amb_row, amb_counter, amb_cap);
   LAUNCH_CHECK("rank_amb_kernel");
@@ -360,6 +426,55 @@ extern "C" int kemr_rank_count(const uint16_t* q, int Q, const uint16_t* gal_a, 
     rank_hits_kernel<<<std::min(Q, dv.sms * 8), 128, 0, st>>>(f, Q, M, hit_rowptr, hit_col, hit_bonus);
     LAUNCH_CHECK("rank_hits_kernel");
   }
+  return KEMR_OK;
+}
+
+extern "C" int kemr_rank_count(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
+                               int64_t M, int D, double w_a, double w_b, double alpha,
+                               const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
+                               const double* t_score64, const int64_t* t_gidx, double eps, int64_t idx_base,
+                               int64_t* out_count, int32_t* out_flags, void* workspace,
+                               size_t workspace_bytes, int path, kemr_stream_t stream) {
+  return rank_count_impl(q, Q, gal_a, gal_b, M, D, w_a, w_b, nullptr, nullptr, alpha, hit_rowptr, hit_col, hit_bonus,
+                         t_score64, t_gidx, eps, idx_base, out_count, out_flags, workspace, workspace_bytes, path, stream);
+}
+
+extern "C" int kemr_rank_count_gated(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
+                                     int64_t M, int D, const double* w_a_q, const double* w_b_q, double alpha,
+                                     const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
+                                     const double* t_score64, const int64_t* t_gidx, double eps, int64_t idx_base,
+                                     int64_t* out_count, int32_t* out_flags, void* workspace,
+                                     size_t workspace_bytes, int path, kemr_stream_t stream) {
+  if (!w_a_q || !w_b_q) return fail(KEMR_ERR_ARG, "rank_count_gated: null weight array");
+  return rank_count_impl(q, Q, gal_a, gal_b, M, D, 0.0, 0.0, w_a_q, w_b_q, alpha, hit_rowptr, hit_col, hit_bonus,
+                         t_score64, t_gidx, eps, idx_base, out_count, out_flags, workspace, workspace_bytes, path, stream);
+}
+
+// ----------------------------------------------------------------------------- gate of the simple gated heads
+// gate[q] = sigmoid(sum_d q[q][d] * weight[d] + bias) in fp32 (fusion_model.py:18-19, :190-191); one warp per query,
+// lane-strided partial sums then a 16-8-4-2-1 fold.  w_a = gate, w_b = fl32(1 - gate), both widened to binary64.
+__global__ void gate_linear_kernel(const uint16_t* __restrict__ q, int Q, int D, const float* __restrict__ weight,
+                                   float bias, double* __restrict__ wa, double* __restrict__ wb) {
+  const int lane = threadIdx.x & 31;
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (qi >= Q) return;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) acc = fmaf(bf16_to_f32(q[(size_t)qi * D + d]), weight[d], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const float logit = acc + bias;
+    const float gate = 1.0f / (1.0f + expf(-logit));
+    wa[qi] = (double)gate;
+    wb[qi] = (double)(1.0f - gate);
+  }
+}
+
+extern "C" int kemr_gate_linear(const uint16_t* q, int Q, int D, const float* weight, float bias,
+                                double* out_w_a_q, double* out_w_b_q, kemr_stream_t stream) {
+  if (!q || !weight || !out_w_a_q || !out_w_b_q || Q <= 0 || D <= 0) return fail(KEMR_ERR_ARG, "gate_linear: bad argument");
+  gate_linear_kernel<<<(Q + 7) / 8, 256, 0, S(stream)>>>(q, Q, D, weight, bias, out_w_a_q, out_w_b_q);
+  LAUNCH_CHECK("gate_linear_kernel");
   return KEMR_OK;
 }
 
@@ -378,7 +493,7 @@ extern "C" int kemr_score_matrix(const uint16_t* q, int Q, const uint16_t* gal_a
   if ((rc = make_plan(Q, M, D, G, 16, kModeDense, path, w_a == w_b, dv, &pl))) return rc;
   ScanArgs a{};
   a.q = q; a.Q = Q; a.gal[0] = gal_a; a.gal[1] = gal_b; a.G = G; a.M = M; a.D = D;
-  a.w[0] = w_a; a.w[1] = w_b; a.mode = kModeDense; a.K = 16; a.dense = out; a.ld = ld;
+  a.w[0] = w_a; a.w[1] = w_b; a.wq[0] = nullptr; a.wq[1] = nullptr; a.mode = kModeDense; a.K = 16; a.dense = out; a.ld = ld;
   if (pl.path == KEMR_PATH_MMA) {
     if ((rc = mma_launch(a, pl.mma, S(stream)))) return fail(KEMR_ERR_CUDA, "tcgen05 scan launch failed: %s", mma_last_error());
     return KEMR_OK;

@@ -583,7 +583,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int qrow = (int)crank * kBlockM + quad * 32 + lane;    // query row inside the (cluster's) block
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t my_buf = buf_u32 + (uint32_t)et * 8u;  // append-buffer entry i of this thread: + i * kEpiThreads * 8
-    const float w0 = a.s.w[0], w1 = a.s.w[1];
+    float w0 = a.s.w[0], w1 = a.s.w[1];
     const int mode = a.s.mode;
     constexpr int kHalfCols = n_tile / 2;                // score columns per warp and tile
     RegList<K> list;
@@ -659,6 +659,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         qvalid = qg < a.s.Q;
         list.reset();
         thr = qvalid ? -INFINITY : INFINITY;             // padded query rows never collect candidates
+        if (a.s.wq[0] && qvalid) { w0 = a.s.wq[0][qg]; w1 = a.s.wq[1][qg]; }   // per-query gate (two accumulators)
         cnt = 0;
         if (mode == kModeCount) { blo = a.s.band_lo[qg]; bhi = a.s.band_hi[qg]; }   // padded rows hold +huge: never count
       }

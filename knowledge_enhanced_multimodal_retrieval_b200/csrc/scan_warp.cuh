@@ -27,6 +27,7 @@ struct ScanArgs {
   int64_t M;
   int D;
   float w[2];
+  const float* wq[2];       // optional per-query fusion weights [Q] (gated fusion heads); null = the scalars w[]
   int mode;
   // TOPK
   int K;
@@ -78,6 +79,12 @@ __global__ void __launch_bounds__(kWarpScanThreads, 2) scan_warp_kernel(ScanArgs
     }
   }
 
+  float wg[QB][2];
+#pragma unroll
+  for (int qq = 0; qq < QB; ++qq) {
+    wg[qq][0] = a.w[0]; wg[qq][1] = a.w[1];
+    if (a.wq[0] && qq < nq) { wg[qq][0] = a.wq[0][q0 + qq]; wg[qq][1] = a.wq[1][q0 + qq]; }
+  }
   const int K = a.K;
   uint64_t thr[QB];
   int32_t cnt[QB];
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(kWarpScanThreads, 2) scan_warp_kernel(ScanArgs
             }
           }
 #pragma unroll
-          for (int qq = 0; qq < QB; ++qq) s[qq] = fmaf(a.w[g], acc[qq], s[qq]);
+          for (int qq = 0; qq < QB; ++qq) s[qq] = fmaf(wg[qq][g], acc[qq], s[qq]);
         }
       }
 #pragma unroll

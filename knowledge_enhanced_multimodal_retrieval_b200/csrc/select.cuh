@@ -18,6 +18,7 @@ struct SelectArgs {
   int G, D;
   int64_t M;
   double w[2];
+  const double* wq[2];         // optional per-query fusion weights [Q]; null = the scalars w[]
   double alpha;
   const int64_t* hit_rowptr;   // [Q+1] or null
   const int32_t* hit_col;
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(W * 32) select_kernel(SelectArgs a) {
   {
     CanonRow<NP> ra[2], rb[2];
     const bool two = a.G > 1;
+    const double wa = a.wq[0] ? a.wq[0][qi] : a.w[0], wb = a.wq[0] ? a.wq[1][qi] : a.w[1];
     const int step = two ? W : 2 * W;                       // candidates consumed per round of the CTA
     auto fetch = [&](int set, int c) {
       const size_t off = (size_t)s_row[c] * a.D;
@@ -230,10 +232,10 @@ __global__ void __launch_bounds__(W * 32) select_kernel(SelectArgs a) {
       cq.dot2_lane0(ra[set], rb[set], a.D, lane, sa, sb);
       if (lane == 0) {
         if (two) {
-          s_score[c] = canon_fuse(sa, sb, true, a.w[0], a.w[1], a.alpha, s_bonus[c], s_has[c] != 0);
+          s_score[c] = canon_fuse(sa, sb, true, wa, wb, a.alpha, s_bonus[c], s_has[c] != 0);
         } else {
-          s_score[c] = canon_fuse(sa, 0.0, false, a.w[0], a.w[1], a.alpha, s_bonus[c], s_has[c] != 0);
-          if (c + W < n) s_score[c + W] = canon_fuse(sb, 0.0, false, a.w[0], a.w[1], a.alpha, s_bonus[c + W], s_has[c + W] != 0);
+          s_score[c] = canon_fuse(sa, 0.0, false, wa, wb, a.alpha, s_bonus[c], s_has[c] != 0);
+          if (c + W < n) s_score[c + W] = canon_fuse(sb, 0.0, false, wa, wb, a.alpha, s_bonus[c + W], s_has[c + W] != 0);
         }
       }
     };
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(W * 32) select_kernel(SelectArgs a) {
 // ------------------------------------------------------------------ canonical pair scores
 __global__ void score_pairs_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ ga,
                                    const uint16_t* __restrict__ gb, int D, double wa, double wb,
+                                   const double* __restrict__ wqa, const double* __restrict__ wqb,
                                    double alpha, const int32_t* __restrict__ pq,
                                    const int64_t* __restrict__ prow, const double* __restrict__ pbonus,
                                    int64_t n, double* __restrict__ out) {
@@ -300,7 +303,8 @@ __global__ void score_pairs_kernel(const uint16_t* __restrict__ q, const uint16_
     const double sa = canon_dot_warp(qrow, ga + off, D, lane);
     const double sb = gb ? canon_dot_warp(qrow, gb + off, D, lane) : 0.0;
     if (lane == 0)
-      out[i] = canon_fuse(sa, sb, gb != nullptr, wa, wb, alpha, pbonus ? pbonus[i] : 0.0, pbonus != nullptr);
+      out[i] = canon_fuse(sa, sb, gb != nullptr, wqa ? wqa[pq[i]] : wa, wqa ? wqb[pq[i]] : wb, alpha, pbonus ? pbonus[i] : 0.0,
+                          pbonus != nullptr);
   }
 }
 
@@ -333,6 +337,7 @@ struct RankFixArgs {
   const uint16_t* gal[2];
   int G, D;
   double w[2];
+  const double* wq[2];        // optional per-query weights [Q]
   double alpha;
   const double* t;            // [Q]
   const int64_t* t_gidx;      // [Q]
@@ -357,7 +362,8 @@ __global__ void rank_amb_kernel(RankFixArgs a, const uint32_t* __restrict__ amb_
     const double sa = canon_dot_warp(qrow, a.gal[0] + off, a.D, lane);
     const double sb = a.G > 1 ? canon_dot_warp(qrow, a.gal[1] + off, a.D, lane) : 0.0;
     if (lane == 0) {
-      const double f = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, 0.0, false);
+      const double wa = a.wq[0] ? a.wq[0][qi] : a.w[0], wb = a.wq[0] ? a.wq[1][qi] : a.w[1];
+      const double f = canon_fuse(sa, sb, a.G > 1, wa, wb, a.alpha, 0.0, false);
       if (ahead64(f, a.idx_base + row, a.t[qi], a.t_gidx[qi])) atomicAdd(&a.count[qi], 1ull);
     }
   }
@@ -377,8 +383,9 @@ __global__ void rank_hits_kernel(RankFixArgs a, int Q, int64_t M, const int64_t*
       const double sa = canon_dot_warp(qrow, a.gal[0] + off, a.D, lane);
       const double sb = a.G > 1 ? canon_dot_warp(qrow, a.gal[1] + off, a.D, lane) : 0.0;
       if (lane == 0) {
-        const double f0 = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, 0.0, false);
-        const double f1 = canon_fuse(sa, sb, a.G > 1, a.w[0], a.w[1], a.alpha, bonus[h], true);
+        const double wa = a.wq[0] ? a.wq[0][qi] : a.w[0], wb = a.wq[0] ? a.wq[1][qi] : a.w[1];
+        const double f0 = canon_fuse(sa, sb, a.G > 1, wa, wb, a.alpha, 0.0, false);
+        const double f1 = canon_fuse(sa, sb, a.G > 1, wa, wb, a.alpha, bonus[h], true);
         const int d = (int)ahead64(f1, a.idx_base + row, a.t[qi], a.t_gidx[qi]) -
                       (int)ahead64(f0, a.idx_base + row, a.t[qi], a.t_gidx[qi]);
         if (d) atomicAdd(&a.count[qi], (unsigned long long)(long long)d);

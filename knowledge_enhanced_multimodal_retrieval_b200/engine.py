@@ -192,11 +192,48 @@ def default_k_sel(k: int) -> int:
     return min(MAX_K_SEL, (k + 6 + 7) // 8 * 8)
 
 
+def _per_query(w) -> bool:
+    return isinstance(w, (torch.Tensor, np.ndarray))
+
+
+def query_weights(w_a, w_b, Q: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-query fusion weights (gated heads) as contiguous binary64 device arrays [Q]."""
+    out = []
+    for w in (w_a, w_b):
+        t = torch.as_tensor(w).to(device=device, dtype=torch.float64).reshape(-1).contiguous()
+        if t.numel() != Q:
+            raise KemrError(f"per-query weights need {Q} entries, got {t.numel()}")
+        out.append(t)
+    return out[0], out[1]
+
+
+def gate_linear(q: torch.Tensor, weight: ArrayLike, bias: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(gate, 1 - gate) of the linear gated heads, gate = sigmoid(q . weight + bias) in fp32
+    (reference `fusion_model.py:18-19,190-191`), as binary64 per-query weights for scan_topk / rank_targets."""
+    Q, D = q.shape
+    w = torch.as_tensor(weight).to(device=q.device, dtype=torch.float32).reshape(-1).contiguous()
+    if w.numel() != D:
+        raise KemrError(f"gate weight needs {D} entries, got {w.numel()}")
+    wa = torch.empty((Q,), dtype=torch.float64, device=q.device)
+    wb = torch.empty((Q,), dtype=torch.float64, device=q.device)
+    _lib.check(_lib.load().kemr_gate_linear(_ptr(q), Q, D, _ptr(w), float(bias), _ptr(wa), _ptr(wb), _stream()))
+    return wa, wb
+
+
 def scan_topk_raw(q, gal_a, gal_b, w_a, w_b, alpha, hits: Optional[KGHits], k, k_sel, eps, idx_base,
                   out_score, out_idx, out_flags, ws, path=PATH_AUTO, out_score32=None):
-    """One kemr_scan_topk call; no host synchronisation."""
+    """One kemr_scan_topk call (kemr_scan_topk_gated when w_a / w_b are per-query arrays); no host synchronisation."""
     Q, D = q.shape
     M = gal_a.shape[0]
+    if _per_query(w_a) or _per_query(w_b):
+        wa, wb = query_weights(w_a, w_b, Q, q.device)
+        _lib.check(_lib.load().kemr_scan_topk_gated(
+            _ptr(q), Q, _ptr(gal_a), _ptr(gal_b), M, D, _ptr(wa), _ptr(wb), float(alpha),
+            _ptr(hits.rowptr) if hits else None, _ptr(hits.col) if hits else None,
+            _ptr(hits.bonus) if hits else None, hits.max_per_query if hits else 0,
+            k, k_sel, float(eps), int(idx_base), _ptr(out_score), _ptr(out_score32), _ptr(out_idx),
+            _ptr(out_flags), _ptr(ws), ws.numel(), path, _stream()))
+        return
     _lib.check(_lib.load().kemr_scan_topk(
         _ptr(q), Q, _ptr(gal_a), _ptr(gal_b), M, D, float(w_a), float(w_b), float(alpha),
         _ptr(hits.rowptr) if hits else None, _ptr(hits.col) if hits else None,
@@ -221,6 +258,9 @@ def scan_topk(q: torch.Tensor, gal_a: torch.Tensor, gal_b: Optional[torch.Tensor
     M = gal_a.shape[0]
     k_sel = default_k_sel(k) if k_sel is None else k_sel
     mh = hits.max_per_query if hits else 0
+    gated = _per_query(w_a) or _per_query(w_b)               # per-query weights (gated fusion heads)
+    if gated:
+        w_a, w_b = query_weights(w_a, w_b, Q, q.device)
     ws = workspace_for(Q, M, D, k_sel, mh)
     score = torch.empty((Q, k), dtype=torch.float64, device=q.device)
     idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
@@ -236,11 +276,12 @@ def scan_topk(q: torch.Tensor, gal_a: torch.Tensor, gal_b: Optional[torch.Tensor
             sub_hits = hits.subset(bad) if hits is not None else None
             qs = q[bad].contiguous()
             n = qs.shape[0]
+            wa_sub, wb_sub = (w_a[bad].contiguous(), w_b[bad].contiguous()) if gated else (w_a, w_b)
             s2 = torch.empty((n, k), dtype=torch.float64, device=q.device)
             i2 = torch.empty((n, k), dtype=torch.int64, device=q.device)
             f2 = torch.empty((n,), dtype=torch.int32, device=q.device)
             ws2 = workspace_for(n, M, D, ks, sub_hits.max_per_query if sub_hits else 0)
-            scan_topk_raw(qs, gal_a, gal_b, w_a, w_b, alpha, sub_hits, k, ks, eps, idx_base, s2, i2, f2, ws2, path)
+            scan_topk_raw(qs, gal_a, gal_b, wa_sub, wb_sub, alpha, sub_hits, k, ks, eps, idx_base, s2, i2, f2, ws2, path)
             score[bad] = s2
             idx[bad] = i2
             flags[bad] = f2
@@ -276,6 +317,11 @@ def score_pairs(q, gal_a, gal_b, pair_q: torch.Tensor, pair_row: torch.Tensor, w
     pq = pair_q.to(device=q.device, dtype=torch.int32).contiguous()
     pr = pair_row.to(device=q.device, dtype=torch.int64).contiguous()
     pb = None if pair_bonus is None else pair_bonus.to(device=q.device, dtype=torch.float64).contiguous()
+    if _per_query(w_a) or _per_query(w_b):
+        wa, wb = query_weights(w_a, w_b, q.shape[0], q.device)
+        _lib.check(_lib.load().kemr_score_pairs_gated(_ptr(q), _ptr(gal_a), _ptr(gal_b), q.shape[1], _ptr(wa), _ptr(wb),
+                                                      float(alpha), _ptr(pq), _ptr(pr), _ptr(pb), n, _ptr(out), _stream()))
+        return out
     _lib.check(_lib.load().kemr_score_pairs(_ptr(q), _ptr(gal_a), _ptr(gal_b), q.shape[1], float(w_a),
                                             float(w_b), float(alpha), _ptr(pq), _ptr(pr), _ptr(pb), n,
                                             _ptr(out), _stream()))
@@ -311,11 +357,16 @@ def rank_count(q, gal_a, gal_b, t_score: torch.Tensor, t_gidx: torch.Tensor, w_a
         ws = workspace_for(Q, M, D, 16, 0, scale)
         count = torch.empty((Q,), dtype=torch.int64, device=q.device)
         flags = torch.empty((Q,), dtype=torch.int32, device=q.device)
-        _lib.check(_lib.load().kemr_rank_count(
-            _ptr(q), Q, _ptr(gal_a), _ptr(gal_b), M, D, float(w_a), float(w_b), float(alpha),
-            _ptr(hits.rowptr) if hits else None, _ptr(hits.col) if hits else None,
-            _ptr(hits.bonus) if hits else None, _ptr(t_score), _ptr(t_gidx), float(eps), int(idx_base),
-            _ptr(count), _ptr(flags), _ptr(ws), ws.numel(), path, _stream()))
+        tail = (_ptr(hits.rowptr) if hits else None, _ptr(hits.col) if hits else None,
+                _ptr(hits.bonus) if hits else None, _ptr(t_score), _ptr(t_gidx), float(eps), int(idx_base),
+                _ptr(count), _ptr(flags), _ptr(ws), ws.numel(), path, _stream())
+        if _per_query(w_a) or _per_query(w_b):
+            wa, wb = query_weights(w_a, w_b, Q, q.device)
+            _lib.check(_lib.load().kemr_rank_count_gated(_ptr(q), Q, _ptr(gal_a), _ptr(gal_b), M, D, _ptr(wa), _ptr(wb),
+                                                         float(alpha), *tail))
+        else:
+            _lib.check(_lib.load().kemr_rank_count(_ptr(q), Q, _ptr(gal_a), _ptr(gal_b), M, D, float(w_a), float(w_b),
+                                                   float(alpha), *tail))
         if not bool((flags & FLAG_OVERFLOW).any()):
             return count
         if scale >= 64:

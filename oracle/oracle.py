@@ -268,10 +268,15 @@ def canon_dot64(query: np.ndarray, gallery: np.ndarray) -> np.ndarray:
 
 def canon_fused64(s_a: np.ndarray, s_b: Optional[np.ndarray], w_a: float = 1.0, w_b: float = 0.0,
                   alpha: float = 1.0, bonus: Optional[np.ndarray] = None) -> np.ndarray:
-    """fl(fl(alpha * fl(fl(w_a*S_a) + fl(w_b*S_b))) + bonus), all binary64."""
-    clip = np.float64(w_a) * s_a
+    """fl(fl(alpha * fl(fl(w_a*S_a) + fl(w_b*S_b))) + bonus), all binary64.  w_a / w_b may be per-query arrays [Q]
+    (gated fusion heads, fusion_model.py:21,178,194: gate*t2i + (1-gate)*t2t)."""
+    wa = np.asarray(w_a, dtype=np.float64)
+    wb = np.asarray(w_b, dtype=np.float64)
+    wa = wa.reshape(-1, 1) if wa.ndim else wa
+    wb = wb.reshape(-1, 1) if wb.ndim else wb
+    clip = wa * s_a
     if s_b is not None:
-        clip = clip + np.float64(w_b) * s_b
+        clip = clip + wb * s_b
     out = np.float64(alpha) * clip
     if bonus is not None:
         out = out + bonus
@@ -333,3 +338,18 @@ def near_tie_audit(scores: np.ndarray, target_idx: Optional[np.ndarray], k: int,
         close = np.abs(scores - t) <= tol
         rank_risky = int((close.sum(axis=1) > 1).sum())
     return topk_risky, rank_risky
+
+
+def ref_gate_linear(query: np.ndarray, weight: np.ndarray, bias: float) -> np.ndarray:
+    """Reference `fusion_model.py:18-19` / `:190-191`: gate = sigmoid((q * w).sum(1) + b), fp32 (numpy restatement of
+    the torch ops; the summation order of torch's reduction is not pinned, so compare with a tolerance)."""
+    q = np.asarray(query, dtype=np.float32)
+    logit = (q * np.asarray(weight, dtype=np.float32)).sum(axis=1, dtype=np.float32) + np.float32(bias)
+    return (np.float32(1.0) / (np.float32(1.0) + np.exp(-logit, dtype=np.float32))).astype(np.float32)
+
+
+def ref_gated_scores(query, image, target, gate: np.ndarray) -> np.ndarray:
+    """Reference `fusion_model.py:16-22`: gate * (q @ img.T) + (1 - gate) * (q @ tgt.T) in fp32, gate (N,) fp32."""
+    q = np.asarray(query, dtype=np.float32)
+    g = np.asarray(gate, dtype=np.float32).reshape(-1, 1)
+    return g * (q @ np.asarray(image, dtype=np.float32).T) + (np.float32(1.0) - g) * (q @ np.asarray(target, dtype=np.float32).T)

@@ -355,3 +355,59 @@ def test_retrieval_engine_end_to_end(small_set):
         fused = eng.retrieve_text(f"text {i}", threshold=-1)
         want = O.ref_fuse_clip_sparql_linear(plain, T2S().retrieval(""), 0.8, 0.2)
         assert fused == want
+
+
+# --------------------------------------------------------------------------- per-query gated fusion (§8f)
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("Q,M,D,k", [(130, 2000, 128, 10), (300, 3000, 768, 20), (7, 900, 64, 5)])
+def test_gated_per_query_weights_match_canonical(path, Q, M, D, k):
+    if not path_ok(path, D, k, Q, M, 2):
+        pytest.skip("tcgen05 path unavailable for this shape")
+    s = synth.make_retrieval_set(Q=Q, M=M, D=D, seed=500 + Q, fused=True, lam=0.2, diagonal=True)
+    rng = np.random.default_rng(Q)
+    gate = rng.uniform(0.02, 0.98, Q).astype(np.float32)
+    wa, wb = gate.astype(np.float64), (np.float32(1.0) - gate).astype(np.float64)
+    q, img, tgt = dev(s.query), dev(s.image), dev(s.target)
+    idx, score = engine.scan_topk(q, img, tgt, wa, wb, k=k, path=path)
+    can = O.canon_fused64(O.canon_dot64(s.query, s.image), O.canon_dot64(s.query, s.target), wa, wb)
+    widx, wscore = O.canon_topk(can, k)
+    assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(score.cpu().numpy(), wscore)
+    assert int((engine.last_flags() != 0).sum()) == 0
+    ranks = engine.rank_targets(q, img, tgt, torch.from_numpy(s.target_idx).cuda(), wa, wb, path=path)
+    assert np.array_equal(ranks.cpu().numpy(), O.canon_rank(can, s.target_idx))
+
+
+def test_gated_heads_follow_the_reference_formula():
+    from knowledge_enhanced_multimodal_retrieval_b200 import fusion_heads as FH
+    s = synth.make_retrieval_set(Q=200, M=200, D=256, seed=77, fused=True, lam=0.3, diagonal=True)
+    rng = np.random.default_rng(5)
+    w = rng.normal(0, 0.5, 256).astype(np.float32)
+    head = FH.SimpleGatedFusion(w, bias=0.25, embed_dim=256)
+    q = dev(s.query)
+    wa, wb = head.gate_weights(q)
+    gate_ref = O.ref_gate_linear(s.query, w, 0.25)
+    assert np.abs(wa.cpu().numpy() - gate_ref).max() < 2e-6                     # fp32 sum order differs, not more
+    assert np.array_equal(wb.cpu().numpy(), (np.float32(1) - wa.cpu().numpy().astype(np.float32)).astype(np.float64))
+    # metrics of the head == metrics of the reference's (N, N) fp32 score matrix (fusion_model.py:16-22 + metrics)
+    got = head.evaluate(s.query, s.image, s.target)
+    ref = O.ref_gated_scores(s.query, s.image, s.target, wa.cpu().numpy().astype(np.float32))
+    want = O.ref_metrics_from_matrix(ref)
+    can = O.canon_fused64(O.canon_dot64(s.query, s.image), O.canon_dot64(s.query, s.target),
+                          wa.cpu().numpy(), wb.cpu().numpy())
+    same_dict(got, O.metrics_from_ranks(O.canon_rank(can, s.target_idx)))
+    assert np.abs(ref - can).max() < 1e-5                                        # canonical == reference formula
+    for key in want:                                                             # at most one near-tie may flip
+        assert abs(float(got[key]) - float(want[key])) <= 0.51, (key, got[key], want[key])
+    # defaults of the two simple heads: gate = sigmoid(sum(q)) and sigmoid(-2)
+    g0, _ = FH.SimpleGatedFusionWithBias(embed_dim=256).gate_weights(q)
+    assert np.allclose(g0.cpu().numpy(), 1.0 / (1.0 + np.exp(2.0)), atol=1e-7)
+    # MLP gate and bilinear head run end to end and agree with a direct evaluation of their formulas
+    mlp = FH.GatedFusionHead(rng.normal(0, 0.1, (128, 256)), rng.normal(0, 0.1, 128), rng.normal(0, 0.1, (1, 128)), 0.1)
+    idx, sc = mlp.search(s.query, s.image, s.target, k=5)
+    ga, gb = mlp.gate_weights(q)
+    can2 = O.canon_fused64(O.canon_dot64(s.query, s.image), O.canon_dot64(s.query, s.target), ga.cpu().numpy(), gb.cpu().numpy())
+    widx, wsc = O.canon_topk(can2, 5)
+    assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(sc.cpu().numpy(), wsc)
+    bil = FH.BilinearFusionHead(np.eye(256, dtype=np.float32), np.eye(256, dtype=np.float32), alpha=0.0)
+    bil.project(s.image, s.target)
+    same_dict(bil.evaluate(s.query), metrics.compute_retrieval_metrics_final(s.query, s.target, s.image))
