@@ -211,6 +211,36 @@ int kemr_index_search_host(kemr_index_t* index, const float* q_host, int Q, int 
                            int k, int64_t* out_idx_host, double* out_score64_host,
                            int32_t* out_flags_host);
 
+/* ---- the data path either side of the scan ------------------------------------
+
+ * KG-hit CSR builder on the device.  Input: per query the LIST of gallery rows the knowledge graph returned, in
+ * list order, as GLOBAL row ids (-1 = unknown artefact), CSR-shaped (list_rowptr int64[Q+1], list_rows int64[nnz]),
+ * plus the bonus of ONE listing per query (w, delta or delta*omega(|R(q)|): fusion.py:83,130,202).  Output: the
+ * CSR kemr_scan_topk / kemr_rank_count take for the shard of rows [row_lo, row_hi): unique LOCAL columns per query
+ * in order of first listing; sum_repeats = 0 keeps one bonus per row (indicator, fusion.py:80), 1 adds it once per
+ * listing (fusion.py:130).  out_col / out_bonus need room for nnz entries; out_max_per_query is a device int64. */
+size_t kemr_hits_workspace_bytes(int Q);
+int kemr_hits_build_csr(const int64_t* list_rowptr, const int64_t* list_rows, const double* bonus_per_query,
+                        int Q, int64_t row_lo, int64_t row_hi, int sum_repeats,
+                        int64_t* out_rowptr, int32_t* out_col, double* out_bonus, int64_t* out_max_per_query,
+                        void* workspace, size_t workspace_bytes, kemr_stream_t stream);
+
+/* uuid -> gallery row map on the HOST (fusion.py:62 artefact_uuid_to_idx).  Keys are passed as one byte blob plus
+ * n+1 offsets.  A repeated uuid keeps its last row, like the reference's dict.  Lookup returns -1 for unknown keys;
+ * normalize_uri != 0 first cuts the key to its last '/' segment (fusion.py:76, text2sparql_retrieval.py:57). */
+typedef struct kemr_idmap kemr_idmap_t;
+int kemr_idmap_create(const char* blob_host, const int64_t* offsets_host, int64_t n, kemr_idmap_t** out);
+int kemr_idmap_destroy(kemr_idmap_t* map);
+int kemr_idmap_lookup(const kemr_idmap_t* map, const char* blob_host, const int64_t* offsets_host, int64_t n,
+                      int normalize_uri, int64_t* out_rows_host);
+
+/* persisted bf16 embedding store (replaces the reference's data/embeddings directory, clip_retrieval.py:28,35):
+ * one file = 64-byte header + M*D bf16, row-major, so a rank reads its shard as a byte range.  kemr_store_load
+ * streams rows [row_lo, row_hi) into DEVICE memory through two page-locked buffers and synchronises `stream`. */
+int kemr_store_write(const char* path, const uint16_t* rows_host, int64_t M, int D);
+int kemr_store_info(const char* path, int64_t* rows, int* dim);
+int kemr_store_load(const char* path, int64_t row_lo, int64_t row_hi, uint16_t* dst_device, kemr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

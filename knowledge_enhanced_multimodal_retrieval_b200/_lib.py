@@ -20,6 +20,8 @@ EXPORTS = (
     "kemr_metrics_reduce_host", "kemr_merge_topk", "kemr_index_create", "kemr_index_destroy",
     "kemr_index_search_host", "kemr_set_scan_done_event", "kemr_scan_plan",
     "kemr_scan_topk_gated", "kemr_rank_count_gated", "kemr_score_pairs_gated", "kemr_gate_linear",
+    "kemr_hits_workspace_bytes", "kemr_hits_build_csr", "kemr_idmap_create", "kemr_idmap_destroy", "kemr_idmap_lookup",
+    "kemr_store_write", "kemr_store_info", "kemr_store_load",
 )
 
 
@@ -51,6 +53,15 @@ def _declare(lib):
                                           p, p, p, sz, i32, p]
     lib.kemr_score_pairs_gated.argtypes = [p, p, p, i32, p, p, f64, p, p, p, i64, p, p]
     lib.kemr_gate_linear.argtypes = [p, i32, i32, p, f32, p, p, p]
+    lib.kemr_hits_workspace_bytes.restype = sz
+    lib.kemr_hits_workspace_bytes.argtypes = [i32]
+    lib.kemr_hits_build_csr.argtypes = [p, p, p, i32, i64, i64, i32, p, p, p, p, p, sz, p]
+    lib.kemr_idmap_create.argtypes = [p, p, i64, C.POINTER(p)]
+    lib.kemr_idmap_destroy.argtypes = [p]
+    lib.kemr_idmap_lookup.argtypes = [p, p, p, i64, i32, p]
+    lib.kemr_store_write.argtypes = [C.c_char_p, p, i64, i32]
+    lib.kemr_store_info.argtypes = [C.c_char_p, C.POINTER(i64), C.POINTER(i32)]
+    lib.kemr_store_load.argtypes = [C.c_char_p, i64, i64, p, p]
     lib.kemr_rank_count.argtypes = [p, i32, p, p, i64, i32, f64, f64, f64, p, p, p, p, p, f64, i64,
                                     p, p, p, sz, i32, p]
     lib.kemr_score_matrix.argtypes = [p, i32, p, p, i64, i32, f32, f32, p, i64, p, sz, i32, p]
@@ -66,7 +77,7 @@ def _declare(lib):
     lib.kemr_index_search_host.argtypes = [p, p, i32, i32, f64, f64, f64, p, p, p, i32, p, p, p]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("kemr_last_error", "kemr_workspace_bytes", "kemr_abi_version"):
+        if name not in ("kemr_last_error", "kemr_workspace_bytes", "kemr_abi_version", "kemr_hits_workspace_bytes"):
             fn.restype = i32
 
 

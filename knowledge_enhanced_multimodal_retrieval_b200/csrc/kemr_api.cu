@@ -17,6 +17,13 @@
 #include "select.cuh"
 #include "matrix_ops.cuh"
 #include "scan_mma.cuh"
+#include "store.cuh"
+
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
+#include <string_view>
+#include <unordered_map>
 
 using namespace kemr;
 
@@ -714,5 +721,167 @@ extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int
   memcpy(out_idx_host, ix->h_idx, (size_t)Q * k * 8);
   memcpy(out_score64_host, ix->h_score, (size_t)Q * k * 8);
   if (out_flags_host) memcpy(out_flags_host, ix->h_flags, (size_t)Q * 4);
+  return KEMR_OK;
+}
+
+// ----------------------------------------------------------------------------- KG-hit CSR builder (device)
+extern "C" size_t kemr_hits_workspace_bytes(int Q) { return align_up((size_t)std::max(Q, 1) * 8) + 256; }
+
+extern "C" int kemr_hits_build_csr(const int64_t* list_rowptr, const int64_t* list_rows, const double* bonus_per_query,
+                                   int Q, int64_t row_lo, int64_t row_hi, int sum_repeats, int64_t* out_rowptr,
+                                   int32_t* out_col, double* out_bonus, int64_t* out_max_per_query, void* workspace,
+                                   size_t workspace_bytes, kemr_stream_t stream) {
+  if (!list_rowptr || !bonus_per_query || !out_rowptr || !out_max_per_query || Q <= 0 || row_hi < row_lo)
+    return fail(KEMR_ERR_ARG, "hits_build_csr: bad argument");
+  if (row_hi - row_lo >= (1ll << 31)) return fail(KEMR_ERR_ARG, "hits_build_csr: a shard holds at most 2^31-1 rows");
+  if (!workspace || workspace_bytes < kemr_hits_workspace_bytes(Q)) return fail(KEMR_ERR_WORKSPACE, "hits_build_csr: workspace too small");
+  int64_t* count = reinterpret_cast<int64_t*>(workspace);
+  cudaStream_t st = S(stream);
+  const int blocks = (Q + kHitsWarpsPerBlock - 1) / kHitsWarpsPerBlock;
+  hits_count_kernel<<<blocks, kHitsWarpsPerBlock * 32, 0, st>>>(list_rowptr, list_rows, Q, row_lo, row_hi, count);
+  LAUNCH_CHECK("hits_count_kernel");
+  hits_scan_kernel<<<1, 1024, 0, st>>>(count, Q, out_rowptr, out_max_per_query);
+  LAUNCH_CHECK("hits_scan_kernel");
+  hits_fill_kernel<<<blocks, kHitsWarpsPerBlock * 32, 0, st>>>(list_rowptr, list_rows, bonus_per_query, Q, row_lo, row_hi,
+                                                                 sum_repeats, out_rowptr, out_col, out_bonus);
+  LAUNCH_CHECK("hits_fill_kernel");
+  return KEMR_OK;
+}
+
+// ----------------------------------------------------------------------------- uuid -> row map (host)
+struct kemr_idmap {
+  std::string blob;                                        // owns the key bytes
+  std::unordered_map<std::string_view, int64_t> map;
+};
+
+// last '/' segment of an artefact URI (fusion.py:76, text2sparql_retrieval.py:57)
+static inline std::string_view uri_tail(std::string_view s) {
+  const size_t p = s.rfind('/');
+  return p == std::string_view::npos ? s : s.substr(p + 1);
+}
+
+extern "C" int kemr_idmap_create(const char* blob, const int64_t* offsets, int64_t n, kemr_idmap_t** out) {
+  if (!offsets || !out || n < 0 || (n && !blob)) return fail(KEMR_ERR_ARG, "idmap_create: bad argument");
+  kemr_idmap* m = new kemr_idmap();
+  m->blob.assign(blob ? blob : "", (size_t)offsets[n]);
+  m->map.reserve((size_t)n * 2);
+  for (int64_t i = 0; i < n; ++i) {
+    if (offsets[i + 1] < offsets[i]) { delete m; return fail(KEMR_ERR_ARG, "idmap_create: offsets must not decrease"); }
+    // a repeated uuid keeps its LAST row, like the reference's {uuid: idx for idx, uuid in enumerate(...)} (fusion.py:62)
+    m->map[std::string_view(m->blob.data() + offsets[i], (size_t)(offsets[i + 1] - offsets[i]))] = i;
+  }
+  *out = m;
+  return KEMR_OK;
+}
+
+extern "C" int kemr_idmap_destroy(kemr_idmap_t* m) { delete m; return KEMR_OK; }
+
+extern "C" int kemr_idmap_lookup(const kemr_idmap_t* m, const char* blob, const int64_t* offsets, int64_t n,
+                                 int normalize_uri, int64_t* out_rows) {
+  if (!m || !offsets || !out_rows || n < 0 || (n && !blob)) return fail(KEMR_ERR_ARG, "idmap_lookup: bad argument");
+  for (int64_t i = 0; i < n; ++i) {
+    std::string_view key(blob + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
+    if (normalize_uri) key = uri_tail(key);
+    auto it = m->map.find(key);
+    out_rows[i] = it == m->map.end() ? -1 : it->second;
+  }
+  return KEMR_OK;
+}
+
+// ----------------------------------------------------------------------------- persisted bf16 embedding store
+// File = 64-byte header + M*D bf16 values, row-major.  Replaces the reference's `data/embeddings` directory
+// (clip_retrieval.py:28,35; contents defined by remote code) with a layout a shard can be cut from by byte range.
+struct StoreHeader {
+  char magic[8];          // "KEMRSTOR"
+  uint32_t version;       // 1
+  uint32_t dtype;         // 1 = bf16
+  int64_t rows;
+  int32_t dim;
+  int32_t reserved[9];
+};
+static_assert(sizeof(StoreHeader) == 64, "store header is 64 bytes");
+
+static int store_read_header(int fd, const char* path, StoreHeader* h) {
+  if (pread(fd, h, sizeof *h, 0) != (ssize_t)sizeof *h) return fail(KEMR_ERR_ARG, "store: %s is shorter than a header", path);
+  if (memcmp(h->magic, "KEMRSTOR", 8) != 0 || h->version != 1 || h->dtype != 1 || h->rows < 0 || h->dim <= 0)
+    return fail(KEMR_ERR_ARG, "store: %s is not a version-1 bf16 embedding store", path);
+  return KEMR_OK;
+}
+
+extern "C" int kemr_store_write(const char* path, const uint16_t* rows_host, int64_t M, int D) {
+  if (!path || (M && !rows_host) || M < 0 || D <= 0 || D % 8) return fail(KEMR_ERR_ARG, "store_write: bad argument");
+  const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd < 0) return fail(KEMR_ERR_ARG, "store_write: cannot create %s", path);
+  StoreHeader h{};
+  memcpy(h.magic, "KEMRSTOR", 8); h.version = 1; h.dtype = 1; h.rows = M; h.dim = D;
+  bool ok = write(fd, &h, sizeof h) == (ssize_t)sizeof h;
+  const char* p = reinterpret_cast<const char*>(rows_host);
+  size_t left = (size_t)M * D * 2;
+  while (ok && left) {
+    const ssize_t w = write(fd, p, std::min<size_t>(left, (size_t)1 << 30));
+    if (w <= 0) ok = false; else { p += w; left -= (size_t)w; }
+  }
+  close(fd);
+  return ok ? KEMR_OK : fail(KEMR_ERR_ARG, "store_write: short write to %s", path);
+}
+
+extern "C" int kemr_store_info(const char* path, int64_t* rows, int* dim) {
+  if (!path) return fail(KEMR_ERR_ARG, "store_info: null path");
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(KEMR_ERR_ARG, "store_info: cannot open %s", path);
+  StoreHeader h;
+  int rc = store_read_header(fd, path, &h);
+  struct stat stt;
+  if (!rc && (fstat(fd, &stt) != 0 || (int64_t)stt.st_size < (int64_t)sizeof h + h.rows * h.dim * 2))
+    rc = fail(KEMR_ERR_ARG, "store_info: %s is truncated", path);
+  close(fd);
+  if (rc) return rc;
+  if (rows) *rows = h.rows;
+  if (dim) *dim = h.dim;
+  return KEMR_OK;
+}
+
+// rows [row_lo, row_hi) -> device memory: pread into two page-locked buffers, each copy in flight while the next
+// chunk is read.  Synchronises `stream` before returning (the staging buffers are freed).
+extern "C" int kemr_store_load(const char* path, int64_t row_lo, int64_t row_hi, uint16_t* dst_device, kemr_stream_t stream) {
+  if (!path || !dst_device || row_lo < 0 || row_hi < row_lo) return fail(KEMR_ERR_ARG, "store_load: bad argument");
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(KEMR_ERR_ARG, "store_load: cannot open %s", path);
+  StoreHeader h;
+  int rc = store_read_header(fd, path, &h);
+  if (!rc && row_hi > h.rows) rc = fail(KEMR_ERR_ARG, "store_load: rows [%lld, %lld) beyond the %lld rows of %s", (long long)row_lo, (long long)row_hi, (long long)h.rows, path);
+  if (rc) { close(fd); return rc; }
+  const size_t row_bytes = (size_t)h.dim * 2, total = (size_t)(row_hi - row_lo) * row_bytes;
+  const size_t chunk = std::min<size_t>(std::max<size_t>(total, 1), (size_t)32 << 20);
+  char* stage[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  cudaStream_t st = S(stream);
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaMallocHost(&stage[i], chunk);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+  }
+  size_t off = 0;
+  int b = 0;
+  bool io_ok = true;
+  while (e == cudaSuccess && io_ok && off < total) {
+    const size_t n = std::min(chunk, total - off);
+    e = cudaEventSynchronize(done[b]);                      // the copy that last used this buffer has finished
+    size_t got = 0;
+    while (e == cudaSuccess && got < n) {
+      const ssize_t r = pread(fd, stage[b] + got, n - got, (off_t)(sizeof h + (size_t)row_lo * row_bytes + off + got));
+      if (r <= 0) { io_ok = false; break; }
+      got += (size_t)r;
+    }
+    if (e == cudaSuccess && io_ok) e = cudaMemcpyAsync(reinterpret_cast<char*>(dst_device) + off, stage[b], n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && io_ok) e = cudaEventRecord(done[b], st);
+    off += n;
+    b ^= 1;
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  for (int i = 0; i < 2; ++i) { if (done[i]) cudaEventDestroy(done[i]); if (stage[i]) cudaFreeHost(stage[i]); }
+  close(fd);
+  if (!io_ok) return fail(KEMR_ERR_ARG, "store_load: short read from %s", path);
+  if (e != cudaSuccess) return fail(KEMR_ERR_CUDA, "store_load: %s", cudaGetErrorString(e));
   return KEMR_OK;
 }
