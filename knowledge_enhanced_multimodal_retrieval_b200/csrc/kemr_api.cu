@@ -101,6 +101,15 @@ extern "C" int kemr_quantize_rows(const float* src, uint16_t* dst, int64_t rows,
   if (rows == 0) return KEMR_OK;
   const int threads = 256;
   const int64_t blocks = std::min<int64_t>((rows + 7) / 8, 148 * 16);
+  if (!normalize && D % 128 == 0 && D <= 1024 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    switch (D / 128) {
+#define KEMR_QV(n) case n: quantize_rows_vec_kernel<n><<<(unsigned)blocks, threads, 0, S(stream)>>>(src, dst, rows); break;
+      KEMR_QV(1) KEMR_QV(2) KEMR_QV(3) KEMR_QV(4) KEMR_QV(5) KEMR_QV(6) KEMR_QV(7) KEMR_QV(8)
+#undef KEMR_QV
+    }
+    LAUNCH_CHECK("quantize_rows_vec_kernel");
+    return KEMR_OK;
+  }
   quantize_rows_kernel<<<(unsigned)blocks, threads, 0, S(stream)>>>(src, dst, rows, D, normalize);
   LAUNCH_CHECK("quantize_rows_kernel");
   return KEMR_OK;
@@ -674,16 +683,28 @@ extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int
   if (Q <= 0 || Q > ix->max_q || k <= 0 || k > ix->max_k) return fail(KEMR_ERR_ARG, "index_search_host: Q or k beyond the handle's limits");
   cudaStream_t st = ix->stream;
   const size_t qbytes = (size_t)Q * ix->D * 4;
-  // page-locked caller buffers are used in place; pageable ones are staged through pinned memory
-  auto is_pinned = [](const void* p) {
+  // Page-locked caller buffers are used IN PLACE by the kernels (the quantise kernel reads the fp32 queries over
+  // PCIe, the select kernel stores the results straight into the caller's arrays): no copy engine hop in either
+  // direction.  Pageable buffers are staged through the handle's page-locked memory.
+  auto mapped = [](const void* p) -> void* {
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost) return nullptr;
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return d;
   };
-  const bool q_pinned = is_pinned(q_host);
-  const bool out_pinned = is_pinned(out_idx_host) && is_pinned(out_score64_host) && (!out_flags_host || is_pinned(out_flags_host));
-  if (!q_pinned) memcpy(ix->h_q, q_host, qbytes);
-  CUDA_TRY(cudaMemcpyAsync(ix->d_qf32, q_pinned ? q_host : ix->h_q, qbytes, cudaMemcpyHostToDevice, st));
+  static const bool no_zero_copy = getenv("KEMR_NO_ZERO_COPY") != nullptr;
+  const float* q_dev_view = no_zero_copy ? nullptr : static_cast<const float*>(mapped(q_host));
+  int64_t* oi_view = no_zero_copy ? nullptr : static_cast<int64_t*>(mapped(out_idx_host));
+  double* os_view = no_zero_copy ? nullptr : static_cast<double*>(mapped(out_score64_host));
+  int32_t* of_view = (no_zero_copy || !out_flags_host) ? nullptr : static_cast<int32_t*>(mapped(out_flags_host));
+  const bool q_pinned = q_dev_view != nullptr;
+  const bool out_pinned = oi_view && os_view && (!out_flags_host || of_view);
+  if (!q_pinned) {
+    memcpy(ix->h_q, q_host, qbytes);
+    CUDA_TRY(cudaMemcpyAsync(ix->d_qf32, ix->h_q, qbytes, cudaMemcpyHostToDevice, st));
+  }
   int64_t max_hits = 0;
   const int64_t* d_rowptr = nullptr;
   if (hit_rowptr_host) {
@@ -700,17 +721,15 @@ extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int
     }
     d_rowptr = ix->d_rowptr;
   }
-  int rc = kemr_quantize_rows(ix->d_qf32, ix->d_q, Q, ix->D, normalize, st);
+  int rc = kemr_quantize_rows(q_pinned ? q_dev_view : ix->d_qf32, ix->d_q, Q, ix->D, normalize, st);
   if (rc) return rc;
   const int ksel = std::min(kMaxKSel, (k + 6 + 7) / 8 * 8);
   rc = kemr_scan_topk(ix->d_q, Q, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, alpha, d_rowptr, ix->d_col,
-                      ix->d_bonus, max_hits, k, ksel, 2e-5, 0, ix->d_score, nullptr, ix->d_idx, ix->d_flags,
+                      ix->d_bonus, max_hits, k, ksel, 2e-5, 0, out_pinned ? os_view : ix->d_score, nullptr,
+                      out_pinned ? oi_view : ix->d_idx, out_pinned ? (of_view ? of_view : ix->d_flags) : ix->d_flags,
                       ix->ws, ix->ws_bytes, KEMR_PATH_AUTO, st);
   if (rc) return rc;
   if (out_pinned) {
-    CUDA_TRY(cudaMemcpyAsync(out_idx_host, ix->d_idx, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(out_score64_host, ix->d_score, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
-    if (out_flags_host) CUDA_TRY(cudaMemcpyAsync(out_flags_host, ix->d_flags, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return KEMR_OK;
   }

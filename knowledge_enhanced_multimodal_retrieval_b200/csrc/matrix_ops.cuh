@@ -29,6 +29,30 @@ __global__ void quantize_rows_kernel(const float* __restrict__ src, uint16_t* __
   }
 }
 
+// Round-only variant for D % 128 == 0: every lane fetches all of its 16-byte pieces of the row up front (one round
+// trip even when `src` is page-locked HOST memory read over PCIe -- the host-buffer search reads the caller's query
+// array in place) and packs 4 bf16 per 8-byte store.  Element-wise identical to quantize_rows_kernel(normalize = 0).
+template <int NV>   // float4 pieces per lane = D / 128
+__global__ void quantize_rows_vec_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int D = NV * 128;
+  for (int64_t r = wid; r < rows; r += nw) {
+    const float4* s = reinterpret_cast<const float4*>(src + (size_t)r * D);
+    float4 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = s[lane + 32 * j];
+    uint2* o = reinterpret_cast<uint2*>(dst + (size_t)r * D);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const uint32_t lo = (uint32_t)f32_to_bf16_rne(v[j].x) | ((uint32_t)f32_to_bf16_rne(v[j].y) << 16);
+      const uint32_t hi = (uint32_t)f32_to_bf16_rne(v[j].z) | ((uint32_t)f32_to_bf16_rne(v[j].w) << 16);
+      o[lane + 32 * j] = make_uint2(lo, hi);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ synthetic gallery rows
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {          // splitmix64 finaliser
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
