@@ -51,6 +51,17 @@ def peaks():
     return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel per launch, from the committed ncu --set full
+    capture of this workload (profiles/ncu_traffic.json), or None when no capture exists for it."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(workload, {}).get("scan_kernel_dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -467,7 +478,8 @@ def run_ours(args, cfg):
         else:
             roof = {"bound": "hbm", "achieved": bytes_ / scan_t / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["traffic"] = None
+        roof["traffic"] = ncu_traffic(args.workload)
+        roof["algorithmic_bytes"] = bytes_ + Q * D * 2.0
         roof["peak_source"] = pk["source"]
         roof["kernel"] = "scan (first kernel of kemr_scan_topk)"
         roof["kernel_ms"] = scan_t * 1e3
