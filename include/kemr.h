@@ -190,7 +190,8 @@ int kemr_metrics_reduce_host(const int64_t* ranks_host, int Q, const int32_t* k_
                              int64_t* out_hits_host, double* out_stats_host);
 
 /* ---- merge of R per-shard top-k lists after the all-gather:
- *   in_score64/in_idx: [R][Q][k]; output top-k by (score desc, idx asc); idx < 0 = empty slot. */
+ *   in_score64/in_idx: [R][Q][k], every list ordered as kemr_scan_topk writes it ((score desc, idx asc), empty
+ *   slots idx < 0 at the end); output top-k by (score desc, idx asc); R <= 64. */
 int kemr_merge_topk(const double* in_score64, const int64_t* in_idx, int R, int Q, int k,
                     double* out_score64, int64_t* out_idx, kemr_stream_t stream);
 

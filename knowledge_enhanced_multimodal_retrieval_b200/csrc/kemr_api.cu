@@ -602,7 +602,7 @@ extern "C" int kemr_merge_topk(const double* in_score64, const int64_t* in_idx, 
   if (!in_score64 || !in_idx || !out_score64 || !out_idx || R <= 0 || Q <= 0 || k <= 0)
     return fail(KEMR_ERR_ARG, "merge_topk: bad argument");
   const size_t smem = (size_t)R * k * 16;
-  if (smem > 200 * 1024) return fail(KEMR_ERR_ARG, "merge_topk: R*k too large (%d*%d)", R, k);
+  if (smem > 200 * 1024 || R > 64) return fail(KEMR_ERR_ARG, "merge_topk: R*k too large (%d*%d)", R, k);
   if (smem > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_topk_kernel<<<Q, 256, smem, S(stream)>>>(in_score64, in_idx, R, Q, k, out_score64, out_idx);

@@ -395,34 +395,47 @@ __global__ void rank_hits_kernel(RankFixArgs a, int Q, int64_t M, const int64_t*
 }
 
 // ------------------------------------------------------------------ post-all-gather merge
+// R per-shard lists of k entries, each already ordered by (score desc, idx asc) with empty slots (idx < 0) at the
+// end.  The global position of an entry is its position in its own list plus, for every other list, the number of
+// entries ahead of it -- a binary search, since the lists are sorted: R*log2(k) steps per entry instead of R*k.
 __global__ void merge_topk_kernel(const double* __restrict__ in_s, const int64_t* __restrict__ in_i,
                                   int R, int Q, int k, double* __restrict__ out_s,
                                   int64_t* __restrict__ out_i) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s = reinterpret_cast<double*>(smem_raw);
   int64_t* ix = reinterpret_cast<int64_t*>(s + (size_t)R * k);
+  __shared__ int s_len[64];                 // valid entries per list (R <= 64)
+  __shared__ int s_valid;
   const int qi = blockIdx.x;
   const int n = R * k;
+  if (threadIdx.x < R) s_len[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
   for (int c = threadIdx.x; c < n; c += blockDim.x) {
     const int r = c / k, j = c % k;
     const size_t o = ((size_t)r * Q + qi) * k + j;
     s[c] = in_s[o];
     ix[c] = in_i[o];
+    if (ix[c] >= 0) { atomicAdd(&s_len[r], 1); atomicAdd(&s_valid, 1); }
   }
   __syncthreads();
-  __shared__ int s_valid;
-  if (threadIdx.x == 0) s_valid = 0;
-  __syncthreads();
-  int myvalid = 0;
   for (int c = threadIdx.x; c < n; c += blockDim.x) {
     if (ix[c] < 0) continue;
-    ++myvalid;
-    int r = 0;
-    for (int j = 0; j < n; ++j) r += (ix[j] >= 0 && ahead64(s[j], ix[j], s[c], ix[c])) ? 1 : 0;
-    if (r < k) { out_s[(size_t)qi * k + r] = s[c]; out_i[(size_t)qi * k + r] = ix[c]; }
+    const int r = c / k;
+    int pos = c - r * k;                     // entries of its own list ahead of it
+    for (int r2 = 0; r2 < R; ++r2) {
+      if (r2 == r) continue;
+      const double* ls = s + (size_t)r2 * k;
+      const int64_t* li = ix + (size_t)r2 * k;
+      int lo = 0, hi = s_len[r2];
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ahead64(ls[mid], li[mid], s[c], ix[c])) lo = mid + 1; else hi = mid;
+      }
+      pos += lo;
+    }
+    if (pos < k) { out_s[(size_t)qi * k + pos] = s[c]; out_i[(size_t)qi * k + pos] = ix[c]; }
   }
-  atomicAdd(&s_valid, myvalid);
-  __syncthreads();
   for (int r = s_valid + threadIdx.x; r < k; r += blockDim.x) {
     out_s[(size_t)qi * k + r] = -INFINITY;
     out_i[(size_t)qi * k + r] = -1;

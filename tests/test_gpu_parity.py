@@ -305,18 +305,29 @@ def test_metrics_reduce_device_equals_host_and_numpy():
         assert rr == np.sum(1.0 / r)
 
 
-def test_merge_topk():
-    rng = np.random.default_rng(4)
-    R, Q, k = 4, 19, 10
+@pytest.mark.parametrize("R,Q,k", [(4, 19, 10), (8, 33, 100), (2, 5, 1), (3, 7, 37)])
+def test_merge_topk(R, Q, k):
+    """Per-shard lists as kemr_scan_topk writes them: ordered by (score desc, idx asc), empty slots (-1) at the end."""
+    rng = np.random.default_rng(4 + R)
     sc = np.round(rng.standard_normal((R, Q, k)), 1)               # plenty of exact ties
     ix = rng.permutation(R * Q * k).reshape(R, Q, k).astype(np.int64)
-    ix[1, :, 7:] = -1
+    for r in range(R):
+        for qi in range(Q):
+            order = sorted(range(k), key=lambda j: (-sc[r, qi, j], ix[r, qi, j]))
+            sc[r, qi], ix[r, qi] = sc[r, qi, order], ix[r, qi, order]
+    ix[1, :, (7 * k) // 10:] = -1                                  # a short shard
+    sc[1, :, (7 * k) // 10:] = -np.inf
+    if R > 2:
+        ix[2, 0, :] = -1                                           # an empty list
+        sc[2, 0, :] = -np.inf
     oi, os_ = engine.merge_topk(torch.from_numpy(sc).cuda(), torch.from_numpy(ix).cuda(), k)
     for qi in range(Q):
         cand = [(-(sc[r, qi, j]), ix[r, qi, j]) for r in range(R) for j in range(k) if ix[r, qi, j] >= 0]
         cand.sort()
-        assert oi[qi].cpu().tolist() == [c[1] for c in cand[:k]]
-        assert os_[qi].cpu().tolist() == [-c[0] for c in cand[:k]]
+        want_i = [c[1] for c in cand[:k]] + [-1] * max(0, k - len(cand))
+        want_s = [-c[0] for c in cand[:k]] + [-np.inf] * max(0, k - len(cand))
+        assert oi[qi].cpu().tolist() == want_i
+        assert os_[qi].cpu().tolist() == want_s
 
 
 def test_host_index_equals_device_index(small_set):
