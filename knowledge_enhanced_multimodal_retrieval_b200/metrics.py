@@ -114,6 +114,49 @@ def compute_training_metrics(query_embeddings, target_embeddings, image_embeddin
                                          tasks=tasks, compute_recall=False, compute_mrr=True)
 
 
+def grouped_ranks(q: torch.Tensor, cand: torch.Tensor, candidate_to_artifact, query_artifact=None) -> torch.Tensor:
+    """1-based position of the first candidate belonging to the query's artefact (many candidates per artefact:
+    the N x 4 pools of `baselines/evaluate_text_models.py:176-186,237-249`).  The best positive of each query is
+    found on canonical scores of its (few) positives, then one fused scan counts the candidates ranked ahead of it."""
+    c2a = np.asarray(candidate_to_artifact, dtype=np.int64)
+    n = q.shape[0]
+    qa = np.arange(n, dtype=np.int64) if query_artifact is None else np.asarray(query_artifact, dtype=np.int64)
+    order = np.argsort(c2a, kind="stable")
+    first = np.searchsorted(c2a[order], qa, side="left")
+    last = np.searchsorted(c2a[order], qa, side="right")
+    sizes = last - first
+    if (sizes <= 0).any():
+        raise AssertionError("every query needs at least one candidate of its artefact")
+    g = int(sizes.max())
+    pos = np.full((n, g), -1, dtype=np.int64)                       # candidate rows of each query's artefact
+    for j in range(g):
+        m = sizes > j
+        pos[m, j] = order[first[m] + j]
+    pos_d = torch.from_numpy(pos).to(q.device)
+    valid = pos_d >= 0
+    pq = torch.arange(n, device=q.device, dtype=torch.int32).repeat_interleave(g)
+    sc = engine.score_pairs(q, cand, None, pq, pos_d.clamp(min=0).flatten()).view(n, g)
+    sc = torch.where(valid, sc, torch.full_like(sc, float("-inf")))
+    best = sc.max(dim=1, keepdim=True).values
+    big = torch.iinfo(torch.int64).max
+    tidx = torch.where(valid & (sc == best), pos_d, torch.full_like(pos_d, big)).min(dim=1).values   # ties: lowest row
+    t = sc.gather(1, (pos_d == tidx[:, None]).to(torch.int64).argmax(dim=1, keepdim=True)).flatten().contiguous()
+    return engine.rank_count(q, cand, None, t, tidx.contiguous()) + 1
+
+
+def compute_grouped_retrieval_metrics(query_embeddings, candidate_embeddings, candidate_to_artifact,
+                                      query_artifact=None, prefix: str = "T2T",
+                                      k_values: List[int] = [1, 5, 10, 20]) -> Dict[str, float]:
+    """Recall@K / MRR / Mean_Rank with several correct candidates per query -- the `single` mode of
+    `baselines/evaluate_text_models.py:171-224` (`{prefix}_R@k`, `{prefix}_MRR`, `{prefix}_Mean_Rank`).  For its
+    `multi` mode (:226-281) pass the five query variants stacked and `query_artifact = tile(arange(N), 5)` against
+    each pool in turn, or call `grouped_ranks` per variant and reduce the concatenated ranks once."""
+    q = engine.quantize(query_embeddings)
+    c = engine.quantize(candidate_embeddings)
+    ranks = grouped_ranks(q, c, candidate_to_artifact, query_artifact)
+    return _metrics_from_ranks(ranks, k_values, True, True, prefix)
+
+
 def _deprecated(name):
     logger.warning("%s is DEPRECATED. Use compute_all_retrieval_metrics / compute_training_metrics "
                    "with separate query and target embeddings.", name)

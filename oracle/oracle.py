@@ -353,3 +353,28 @@ def ref_gated_scores(query, image, target, gate: np.ndarray) -> np.ndarray:
     q = np.asarray(query, dtype=np.float32)
     g = np.asarray(gate, dtype=np.float32).reshape(-1, 1)
     return g * (q @ np.asarray(image, dtype=np.float32).T) + (np.float32(1.0) - g) * (q @ np.asarray(target, dtype=np.float32).T)
+
+
+def ref_grouped_metrics(query, cand, text_to_artifact, k_values: Sequence[int] = DEFAULT_K) -> Dict[str, float]:
+    """`baselines/evaluate_text_models.py:171-224` (single mode): fp32 similarity, full argsort per row, position of
+    the first candidate whose artefact is the query's own index."""
+    sim = np.asarray(query, dtype=np.float32) @ np.asarray(cand, dtype=np.float32).T
+    t2a = np.asarray(text_to_artifact)
+    n = sim.shape[0]
+    pos = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        ranked = t2a[np.argsort(-sim[i])]
+        pos[i] = np.where(ranked == i)[0][0] + 1
+    out = {f"T2T_R@{k}": float(np.sum(pos <= k)) / n * 100 for k in k_values}
+    out["T2T_MRR"] = np.mean(1.0 / pos) * 100
+    out["T2T_Mean_Rank"] = np.mean(pos)
+    return out
+
+
+def canon_grouped_rank(scores: np.ndarray, text_to_artifact, query_artifact=None) -> np.ndarray:
+    """Canonical form: 1 + #candidates ahead of the query's best positive under (score desc, index asc)."""
+    t2a = np.asarray(text_to_artifact)
+    n = scores.shape[0]
+    qa = np.arange(n) if query_artifact is None else np.asarray(query_artifact)
+    order = np.argsort(-scores, axis=1, kind="stable")
+    return np.array([int(np.where(t2a[order[i]] == qa[i])[0][0]) + 1 for i in range(n)], dtype=np.int64)

@@ -422,3 +422,32 @@ def test_gated_heads_follow_the_reference_formula():
     bil = FH.BilinearFusionHead(np.eye(256, dtype=np.float32), np.eye(256, dtype=np.float32), alpha=0.0)
     bil.project(s.image, s.target)
     same_dict(bil.evaluate(s.query), metrics.compute_retrieval_metrics_final(s.query, s.target, s.image))
+
+
+# --------------------------------------------------------------------------- grouped ground truth (§8f)
+def test_grouped_ground_truth_metrics():
+    """N queries against an N x 4 candidate pool, candidate c belongs to artefact c // 4
+    (baselines/evaluate_text_models.py:176-224)."""
+    N, D = 300, 256
+    base = synth.make_gallery(N, D, 31)
+    rng = np.random.default_rng(32)
+    cands = synth.round_to_bf16(synth.l2_normalize(np.repeat(base, 4, axis=0) * 0.6
+                                                   + rng.normal(0, 1.0 / np.sqrt(D), (4 * N, D)).astype(np.float32)))
+    query = synth.round_to_bf16(synth.l2_normalize(base * 0.5 + rng.normal(0, 1.0 / np.sqrt(D), (N, D)).astype(np.float32)))
+    t2a = np.repeat(np.arange(N), 4)
+    perm = rng.permutation(4 * N)                                  # positives need not be contiguous
+    cands, t2a = cands[perm], t2a[perm]
+    q, c = dev(query), dev(cands)
+    ranks = metrics.grouped_ranks(q, c, t2a)
+    can = O.canon_dot64(query, cands)
+    assert np.array_equal(ranks.cpu().numpy(), O.canon_grouped_rank(can, t2a))
+    got = metrics.compute_grouped_retrieval_metrics(query, cands, t2a)
+    same_dict(got, O.metrics_from_ranks(O.canon_grouped_rank(can, t2a), prefix="T2T"))
+    want = O.ref_grouped_metrics(query, cands, t2a)                # the reference's loops (fp32, unstable sort)
+    for key in want:
+        assert abs(float(got[key]) - float(want[key])) <= 0.34, (key, got[key], want[key])
+    # multi mode: two "variants" of queries against the same pool, reduced over the concatenated ranks
+    q2 = np.concatenate([query, query[::-1]])
+    qa = np.concatenate([np.arange(N), np.arange(N)[::-1]])
+    r2 = metrics.grouped_ranks(dev(q2), c, t2a, qa)
+    assert np.array_equal(r2.cpu().numpy()[:N], ranks.cpu().numpy()) and np.array_equal(r2.cpu().numpy()[N:], ranks.cpu().numpy()[::-1])
