@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KEMR_ABI_VERSION 1
+#define KEMR_ABI_VERSION 2
 
 enum {
   KEMR_OK = 0,

@@ -35,6 +35,19 @@
 // issues every MMA; tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both
 // CTAs, the peer's TMA loads complete on the leader's full barrier, and both CTAs' epilogue warps
 // arrive on the leader's accumulator-empty barrier.
+//
+// Quads (CL = 4, long scans of >= 1024 queries): two pairs of one cluster take adjacent 256-query blocks and the
+// SAME gallery tiles; each CTA fetches a quarter of the gallery chunk with a cta_group::2 multicast TMA load whose
+// destinations are the two CTAs holding that half, so the tile crosses L2 once per quad; a stage is free when the
+// MMAs of BOTH pairs have retired (empty barriers take two arrivals, commit mask 0xF).
+//
+// Merged double stage (two galleries, equal weights, pairs / quads): a stage holds the query chunk once plus the
+// matching chunk of both galleries; 8 MMAs accumulate q.(a) and q.(b) into the same accumulator.
+//
+// Issue discipline: the producer and the MMA warp run their loops with all 32 lanes (uniform control flow, so
+// addresses and descriptors live in uniform registers) and elect.sync picks the issuing lane around the
+// TMA / MMA / commit instructions only.  Issuing from `if (lane == 0)` put a vector->uniform register waterfall
+// (ELECT, R2UR.BROADCAST x5, BRA.U.ANY) in front of every UTCHMMA and cost a third of the tensor pipe.
 #pragma once
 #include <cuda.h>
 #include <stdlib.h>
