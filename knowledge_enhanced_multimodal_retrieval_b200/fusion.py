@@ -155,3 +155,36 @@ def evaluate_fused(query_embeddings, target_embeddings, image_embeddings, text2s
     else:
         ranks = engine.rank_targets(q, img, tgt, tidx, t2i_weight, t2t_weight, alpha, hits)
     return _metrics_from_ranks(ranks, k_values, True, True)
+
+
+def evaluate_weight_and_alpha_sweep(query_embeddings, target_embeddings, image_embeddings, text2sparql_results,
+                                    uuid_list, weight_settings=((0.5, 0.5), (0.1, 0.9)),
+                                    alphas=(0.9, 0.8, 0.7, 0.6, 0.5, 0.4, 0.3, 0.2, 0.1),
+                                    k_values: List[int] = [1, 5, 10, 20]) -> Dict[str, Dict[str, float]]:
+    """The evaluation block of the reference driver (`evaluator.py:164-218`) in one call: for every
+    (t2i_weight, t2t_weight) setting the metrics of T2I alone, T2T alone, the fused similarity, and of
+    `fuse_clip_and_text2sparql(fused, results, uuid_list, uuid_list, "weighted", {alpha, 1 - alpha})` for every alpha
+    -- 2 x (3 + 9) = 24 evaluations there, each building (N, N) matrices and sorting them twice.  Here the embeddings
+    are quantised and uploaded once, the KG result lists are mapped to gallery rows once and stay on the device, and
+    every evaluation is one target-score pass + one fused counting scan; no (N, N) matrix exists.
+    Keys: "w{t2i}_{t2t}/T2I", ".../T2T", ".../Fused", ".../alpha{a}"."""
+    from . import store
+    q = engine.quantize(query_embeddings)
+    img = engine.quantize(image_embeddings)
+    tgt = engine.quantize(target_embeddings)
+    n = q.shape[0]
+    assert n == len(uuid_list) and img.shape[0] == len(uuid_list)
+    tidx = torch.arange(n, device=q.device, dtype=torch.int64)
+    lists = store.HitLists(store.IdMap(uuid_list), text2sparql_results, uuid_list)
+    out: Dict[str, Dict[str, float]] = {}
+    single = {"T2I": _metrics_from_ranks(engine.rank_targets(q, img, None, tidx), k_values, True, True),
+              "T2T": _metrics_from_ranks(engine.rank_targets(q, tgt, None, tidx), k_values, True, True)}
+    for wi, wt in weight_settings:
+        tag = f"w{wi}_{wt}"
+        out[f"{tag}/T2I"], out[f"{tag}/T2T"] = single["T2I"], single["T2T"]     # do not depend on the weights
+        out[f"{tag}/Fused"] = _metrics_from_ranks(engine.rank_targets(q, img, tgt, tidx, wi, wt), k_values, True, True)
+        for a in alphas:
+            alpha, hits = lists.for_strategy("weighted", {"alpha": a, "sparql_weight": 1 - a})
+            ranks = engine.rank_targets(q, img, tgt, tidx, wi, wt, alpha, hits)
+            out[f"{tag}/alpha{a}"] = _metrics_from_ranks(ranks, k_values, True, True)
+    return out

@@ -66,3 +66,24 @@ def test_store_roundtrip_and_sharded_search(kg_set, tmp_path):
     want = fusion.evaluate_fused(s.query, s.target, s.image, s.kg_results, s.query_uuids, s.uuids, 0.5, 0.5, "weighted",
                                  {"alpha": 0.8, "sparql_weight": 0.2})
     assert {k: float(v) for k, v in got.items()} == {k: float(v) for k, v in want.items()}
+
+
+def test_driver_sweep_equals_per_call_evaluations(kg_set):
+    """evaluator.py:164-218 in one call == the same evaluations through the per-call mirror functions."""
+    s = kg_set
+    sub = slice(0, s.Q)
+    img, tgt = s.image[: s.Q], s.target[: s.Q]                      # the driver's arrays are (N, D) with uuid_list for both
+    uu = s.uuids[: s.Q]
+    res = {uu[i]: list(s.kg_results[qu]) for i, qu in enumerate(s.query_uuids) if qu in s.kg_results}   # query uuid == artefact uuid
+    got = fusion.evaluate_weight_and_alpha_sweep(s.query[sub], tgt, img, res, uu, weight_settings=((0.5, 0.5), (0.1, 0.9)),
+                                                 alphas=(0.9, 0.5, 0.1))
+    from knowledge_enhanced_multimodal_retrieval_b200 import metrics
+    same = lambda a, b: {k: float(v) for k, v in a.items()} == {k: float(v) for k, v in b.items()}
+    assert same(got["w0.5_0.5/T2I"], metrics.compute_retrieval_metrics(s.query[sub], img))
+    assert same(got["w0.1_0.9/T2T"], metrics.compute_retrieval_metrics(s.query[sub], tgt))
+    assert same(got["w0.1_0.9/Fused"], metrics.compute_retrieval_metrics_final(s.query[sub], tgt, img, t2i_weight=0.1, t2t_weight=0.9))
+    for wi, wt in ((0.5, 0.5), (0.1, 0.9)):
+        for a in (0.9, 0.5, 0.1):
+            want = fusion.evaluate_fused(s.query[sub], tgt, img, res, uu, uu, wi, wt, "weighted",
+                                         {"alpha": a, "sparql_weight": 1 - a})
+            assert same(got[f"w{wi}_{wt}/alpha{a}"], want)
