@@ -294,7 +294,7 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
   if (smem > 200 * 1024) return fail(KEMR_ERR_UNSUPPORTED, "select kernel needs %zu bytes of shared memory", smem);
   // one CTA per query: 4 warps for the common small case, 8 when there are many candidates to re-score
   const int np = (D + 255) / 256;
-  const bool small = s.max_cand <= kSelSmallCand;
+  const bool small = s.max_cand <= kSelSmallCand && Q > 64;   // tiny batches leave the GPU empty: 8 warps per query
 #define KEMR_SEL(NPV, WV)                                                                                         \
   do {                                                                                                            \
     if (smem > 48 * 1024)                                                                                         \

@@ -175,25 +175,32 @@ __global__ void __launch_bounds__(kWarpScanThreads, 2) scan_warp_kernel(ScanArgs
   }
 
   if (a.mode == kModeTopk) {
-    // CTA merge: warp qq folds the other warps' lists into its own (lists are sorted, so a
-    // foreign list is abandoned at its first entry below the threshold).
+    // CTA merge: the 8 warps' lists of a query are 8*K distinct keys; every thread ranks some of them by counting
+    // and the K best go out in order (a serial merge of sorted lists by one warp cost ~5 us of a 37 us batch-1 scan).
     __syncthreads();
-    if (warp < nq) {
-      const int qq = warp;
-      uint64_t* mine = lists + ((size_t)warp * QB + qq) * K;
-      uint64_t t = mine[K - 1];
-      for (int w2 = 0; w2 < kWarpScanWarps; ++w2) {
-        if (w2 == warp) continue;
-        const uint64_t* other = lists + ((size_t)w2 * QB + qq) * K;
-        for (int i = 0; i < K; ++i) {
-          const uint64_t x = other[i];
-          if (x <= t) break;
-          warp_list_insert(mine, K, x, lane);
-          t = mine[K - 1];
-        }
-      }
+    const int nk = kWarpScanWarps * K;
+    for (int qq = 0; qq < nq; ++qq) {
       uint64_t* dst = a.part_keys + ((size_t)blockIdx.x * a.Q + (q0 + qq)) * K;
-      for (int i = lane; i < K; i += 32) dst[i] = mine[i];
+      for (int i = threadIdx.x; i < nk; i += kWarpScanThreads) {
+        const uint64_t x = lists[((size_t)(i / K) * QB + qq) * K + (i % K)];
+        if (!x) continue;
+        int r = 0;
+        for (int w2 = 0; w2 < kWarpScanWarps; ++w2) {
+          const uint64_t* L = lists + ((size_t)w2 * QB + qq) * K;
+          for (int j = 0; j < K; ++j) r += L[j] > x ? 1 : 0;
+        }
+        if (r < K) dst[r] = x;
+      }
+      // fewer than K rows seen by this CTA: the tail stays empty
+      __shared__ int s_cnt;
+      if (threadIdx.x == 0) s_cnt = 0;
+      __syncthreads();
+      int mine = 0;
+      for (int i = threadIdx.x; i < nk; i += kWarpScanThreads) mine += lists[((size_t)(i / K) * QB + qq) * K + (i % K)] != 0;
+      if (mine) atomicAdd(&s_cnt, mine);
+      __syncthreads();
+      for (int r = s_cnt + threadIdx.x; r < K; r += kWarpScanThreads) dst[r] = 0;
+      __syncthreads();
     }
   } else if (a.mode == kModeCount) {
     __shared__ int32_t csum[QB];
