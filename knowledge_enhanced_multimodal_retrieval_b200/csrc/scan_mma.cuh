@@ -346,7 +346,7 @@ struct MmaArgs {
   int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, upq, vq;
   long long W;
   long long* dbg;   // optional [ctas][16] cycle counters + stage trace (KEMR_MMA_DEBUG=1)
-  int epi_variant;  // 1 = per-lane predicated appends without warp votes (short lists); KEMR_MMA_EPI overrides
+  int epi_variant;  // 1 = per-lane predicated appends without warp votes (short lists), 2 = the same on RAW accumulators; KEMR_MMA_EPI overrides
   int dbg_skip;     // timing experiments only (results invalid): after a unit's first tile skip the TMA loads of bit0 = queries, bit1 = gallery
 };
 
@@ -603,6 +603,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     RegList<K> list;
     list.reset();
     float thr = INFINITY;
+    float thr_raw = INFINITY;                            // thr / w0 rounded down: raw accumulator <= thr_raw  =>  w0*acc <= thr
     int bcnt = 0;                                        // entries in this thread's append buffer
     int32_t cnt = 0;
     float blo = 0.f, bhi = 0.f;
@@ -629,6 +630,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
         }
       }
+      thr_raw = __fdiv_rd(thr, w0);
       bcnt = 0;
       if (dbg) t_fold += clock64() - tf0;
     };
@@ -638,6 +640,17 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       for (int j = 0; j < 8; ++j) {
         if (v[j] > thr) {
           st_shared_v2(my_buf + (uint32_t)bcnt * (kEpiThreads * 8u), v[j], row + (uint32_t)j);
+          ++bcnt;
+        }
+      }
+    };
+    // single accumulator, positive weight: compare the RAW accumulator with thr / w0 and weight the survivors only
+    auto append8_raw = [&](const uint32_t* v, uint32_t row, int nvalid) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = __uint_as_float(v[j]);
+        if (x > thr_raw && j < nvalid) {
+          st_shared_v2(my_buf + (uint32_t)bcnt * (kEpiThreads * 8u), w0 * x, row + (uint32_t)j);
           ++bcnt;
         }
       }
@@ -673,6 +686,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         qvalid = qg < a.s.Q;
         list.reset();
         thr = qvalid ? -INFINITY : INFINITY;             // padded query rows never collect candidates
+        thr_raw = thr;
         if (a.s.wq[0] && qvalid) { w0 = a.s.wq[0][qg]; w1 = a.s.wq[1][qg]; }   // per-query gate (two accumulators)
         cnt = 0;
         if (mode == kModeCount) { blo = a.s.band_lo[qg]; bhi = a.s.band_hi[qg]; }   // padded rows hold +huge: never count
@@ -693,6 +707,15 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (TWO) tmem_ld16(acc0 + 128u + (uint32_t)c0, rb);
       };
       auto process = [&](int c0, const uint32_t (&ra)[16], const uint32_t (&rb)[16]) {
+        if (!TWO && mode == kModeTopk && a.epi_variant == 2 && w0 > 0.f) {
+          const uint32_t r = (uint32_t)(row0 + c0);
+          const int nv = full_tile ? 16 : ncols - c0;            // columns of this chunk inside the gallery
+          append8_raw(ra, r, nv);
+          if (__any_sync(0xffffffffu, bcnt >= kBufTrigger)) fold();
+          append8_raw(ra + 8, r + 8u, nv - 8);
+          if (__any_sync(0xffffffffu, bcnt >= kBufTrigger)) fold();
+          return;
+        }
         float sv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -880,7 +903,7 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
   static const char* epi_env = getenv("KEMR_MMA_EPI");
   const long long units_run = pl.ctas / std::max(1, pl.cl);
   const double per_list = (double)ma.W / (double)std::max(1ll, units_run) * (pl.n_tile / 2) / std::max(1, pl.vq);
-  ma.epi_variant = epi_env ? atoi(epi_env) : (per_list < 8192.0 ? 1 : 0);
+  ma.epi_variant = epi_env ? atoi(epi_env) : (per_list < 8192.0 ? 2 : 0);
   static const bool debug = getenv("KEMR_MMA_DEBUG") != nullptr;
   if (debug) {
     static long long* dbuf = nullptr;
