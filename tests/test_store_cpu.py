@@ -49,3 +49,33 @@ def test_store_file_format_roundtrip(tmp_path):
         _lib.check(lib.kemr_store_info(path, C.byref(rows), C.byref(dim)))
     with pytest.raises(_lib.KemrError):
         _lib.check(lib.kemr_store_info(str(tmp_path / "missing.kemr").encode(), C.byref(rows), C.byref(dim)))
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    import ctypes as C
+    lib = _lib.load()
+    null = None
+    one = (C.c_int64 * 2)(0, 0)
+    # hits_build_csr: null pointers, negative sizes, inverted row range
+    assert lib.kemr_hits_build_csr(null, null, null, 4, 0, 10, 0, null, null, null, null, null, 0, null) == 1
+    assert lib.kemr_hits_build_csr(one, one, one, 0, 0, 10, 0, one, null, null, one, one, 4096, null) == 1
+    assert lib.kemr_hits_build_csr(one, one, one, 1, 10, 5, 0, one, null, null, one, one, 4096, null) == 1
+    assert b"hits_build_csr" in lib.kemr_last_error()
+    assert lib.kemr_hits_workspace_bytes(1000) >= 8000
+    # idmap: bad offsets are refused, empty maps work
+    h = C.c_void_p()
+    bad = (C.c_int64 * 3)(0, 5, 2)
+    assert lib.kemr_idmap_create(b"abcde", bad, 2, C.byref(h)) == 1
+    zero = (C.c_int64 * 1)(0)
+    assert lib.kemr_idmap_create(b"", zero, 0, C.byref(h)) == 0
+    out = (C.c_int64 * 1)(7)
+    off = (C.c_int64 * 2)(0, 3)
+    assert lib.kemr_idmap_lookup(h, b"abc", off, 1, 1, out) == 0 and out[0] == -1
+    lib.kemr_idmap_destroy(h)
+    # gated calls without weight arrays, store calls with bad shapes
+    assert lib.kemr_scan_topk_gated(null, 1, null, null, 1, 8, null, null, 1.0, null, null, null, 0, 1, 1, 1e-5, 0,
+                                    null, null, null, null, null, 0, 0, null) == 1
+    assert lib.kemr_gate_linear(null, 1, 8, null, 0.0, null, null, null) == 1
+    assert lib.kemr_store_write(b"/tmp/x.kemr", null, 3, 8) == 1
+    assert lib.kemr_store_write(b"/nonexistent-dir/x.kemr", (C.c_uint16 * 8)(), 1, 8) == 1
+    assert lib.kemr_store_load(b"/tmp/definitely-missing.kemr", 0, 1, (C.c_uint16 * 8)(), null) == 1
