@@ -18,8 +18,8 @@ CASES = [
     (1100, 3000, 512, 1, (1.0, 0.0), 10),     # single gallery, odd number of 256-query blocks (phantom block in a quad)
     (520, 7000, 256, 1, (1.0, 0.0), 100),     # large k: many short lists
     (300, 2500, 128, 2, (0.5, 0.5), 20),
-    (3300, 3000, 64, 1, (1.0, 0.0), 10),      # more query blocks than units can split evenly: flattened (block, tile) ranges
-    (3300, 2000, 64, 2, (0.3, 0.7), 10),
+    (3300, 3400, 64, 1, (1.0, 0.0), 10),      # more query blocks than units can split evenly: flattened (block, tile) ranges
+    (3300, 3400, 64, 2, (0.3, 0.7), 10),
 ]
 
 
