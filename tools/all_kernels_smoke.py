@@ -1,4 +1,4 @@
-"""Small invocation of every kernel family for `compute-sanitizer --tool memcheck` (diagnostics)."""
+"""Small invocation of every kernel family (diagnostics; compute-sanitizer is closed on this pool, so this is a plain run)."""
 import os
 import sys
 
@@ -27,4 +27,4 @@ engine.merge_topk(torch.stack([a[1], b[1]]), torch.stack([a[0], b[0]]), 10)
 metrics.compute_recall_at_k(np.random.default_rng(1).normal(size=(50, 70)).astype(np.float32))
 metrics.compute_grouped_retrieval_metrics(s.query[:100], s.image[:400], np.repeat(np.arange(100), 4))
 torch.cuda.synchronize()
-print("sanitize_small: all launches completed")
+print("all_kernels_smoke: all launches completed")
