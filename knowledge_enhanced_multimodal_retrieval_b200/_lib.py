@@ -21,7 +21,7 @@ EXPORTS = (
     "kemr_index_search_host", "kemr_set_scan_done_event", "kemr_scan_plan",
     "kemr_scan_topk_gated", "kemr_rank_count_gated", "kemr_score_pairs_gated", "kemr_gate_linear",
     "kemr_hits_workspace_bytes", "kemr_hits_build_csr", "kemr_idmap_create", "kemr_idmap_destroy", "kemr_idmap_lookup",
-    "kemr_store_write", "kemr_store_info", "kemr_store_load",
+    "kemr_store_write", "kemr_store_info", "kemr_store_load", "kemr_debug_mma_plan",
 )
 
 
@@ -62,6 +62,7 @@ def _declare(lib):
     lib.kemr_store_write.argtypes = [C.c_char_p, p, i64, i32]
     lib.kemr_store_info.argtypes = [C.c_char_p, C.POINTER(i64), C.POINTER(i32)]
     lib.kemr_store_load.argtypes = [C.c_char_p, i64, i64, p, p]
+    lib.kemr_debug_mma_plan.argtypes = [i32, i64, i32, i32, i32, i32, i32, i32, p]
     lib.kemr_rank_count.argtypes = [p, i32, p, p, i64, i32, f64, f64, f64, p, p, p, p, p, f64, i64,
                                     p, p, p, sz, i32, p]
     lib.kemr_score_matrix.argtypes = [p, i32, p, p, i64, i32, f32, f32, p, i64, p, sz, i32, p]

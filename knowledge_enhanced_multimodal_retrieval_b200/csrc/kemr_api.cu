@@ -904,3 +904,21 @@ extern "C" int kemr_store_load(const char* path, int64_t row_lo, int64_t row_hi,
   if (e != cudaSuccess) return fail(KEMR_ERR_CUDA, "store_load: %s", cudaGetErrorString(e));
   return KEMR_OK;
 }
+
+// ----------------------------------------------------------------------------- plan introspection (no device needed)
+// The tcgen05 plan for a shape on a hypothetical device with `sms` SMs and room for `quads` clusters of four:
+// out[0..15] = parts, q_pad, n_tile, n_qb, n_t, ctas, stages, kc, K, cl, upq, vq, all_slots, two, merged, q_blk;
+// returns KEMR_ERR_UNSUPPORTED when the shape cannot be planned.  Lets the host-side scheduling logic (unit ranges,
+// part slots) be property-tested on a CPU (tests/test_plan_cpu.py).
+extern "C" int kemr_debug_mma_plan(int Q, int64_t M, int D, int galleries, int k_sel, int equal_weights, int sms, int quads,
+                                   int64_t* out16) {
+  if (!out16 || Q <= 0 || M <= 0 || galleries < 1 || galleries > 2) return fail(KEMR_ERR_ARG, "debug_mma_plan: bad argument");
+  if (!mma_supported(D, k_sel)) return fail(KEMR_ERR_UNSUPPORTED, "debug_mma_plan: unsupported D / k_sel");
+  MmaPlan p;
+  if (mma_make_plan(Q, M, D, galleries, k_sel, kModeTopk, sms, quads, equal_weights != 0, &p))
+    return fail(KEMR_ERR_UNSUPPORTED, "debug_mma_plan: shape cannot be planned");
+  const int64_t v[16] = {p.parts, p.q_pad, p.n_tile, p.n_qb, p.n_t, p.ctas, p.stages, p.kc, p.K, p.cl, p.upq, p.vq,
+                         p.all_slots, p.two, p.merged, p.q_blk};
+  for (int i = 0; i < 16; ++i) out16[i] = v[i];
+  return KEMR_OK;
+}
