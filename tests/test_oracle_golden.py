@@ -136,3 +136,33 @@ def test_canonical_vs_reference_confined_to_near_ties(golden):
     assert abs(float(got["Mean_Rank"]) - g["Mean_Rank"]) * s.Q <= risky_rows + 1e-6
     for k in (1, 5, 10, 20):
         assert abs(float(got[f"R@{k}"]) - g[f"R@{k}"]) * s.Q / 100.0 <= risky_rows + 1e-6
+
+
+def test_grouped_and_gated_restatements_agree_with_the_canonical_forms():
+    """The reference's grouped-ground-truth loops (baselines/evaluate_text_models.py:171-224) and gated-head formula
+    (fusion_model.py:16-22) restated in the oracle, against the canonical (binary64, stable) forms on data without
+    near ties: same ranks, hence same metrics."""
+    from knowledge_enhanced_multimodal_retrieval_b200 import synth
+    rng = np.random.default_rng(11)
+    N, D = 60, 64
+    base = synth.make_gallery(N, D, 5)
+    cands = synth.round_to_bf16(synth.l2_normalize(np.repeat(base, 4, axis=0) * 0.7
+                                                   + rng.normal(0, 1 / np.sqrt(D), (4 * N, D)).astype(np.float32)))
+    query = synth.round_to_bf16(synth.l2_normalize(base * 0.6 + rng.normal(0, 1 / np.sqrt(D), (N, D)).astype(np.float32)))
+    t2a = np.repeat(np.arange(N), 4)
+    perm = rng.permutation(4 * N)
+    cands, t2a = cands[perm], t2a[perm]
+    ref = O.ref_grouped_metrics(query, cands, t2a)
+    can = O.metrics_from_ranks(O.canon_grouped_rank(O.canon_dot64(query, cands), t2a), prefix="T2T")
+    assert set(ref) == set(can)
+    for k in ref:
+        assert float(ref[k]) == pytest.approx(float(can[k]), abs=1e-9)
+    gate = rng.uniform(0.1, 0.9, N).astype(np.float32)
+    img, tgt = cands[:N], cands[N:2 * N]
+    dense = O.ref_gated_scores(query, img, tgt, gate)
+    canon = O.canon_fused64(O.canon_dot64(query, img), O.canon_dot64(query, tgt), gate.astype(np.float64),
+                            (np.float32(1) - gate).astype(np.float64))
+    assert np.abs(dense - canon).max() < 1e-5
+    w = rng.normal(0, 0.3, D).astype(np.float32)
+    g = O.ref_gate_linear(query, w, -0.5)
+    assert g.dtype == np.float32 and np.allclose(g, 1 / (1 + np.exp(-(query.astype(np.float64) @ w.astype(np.float64) - 0.5))), atol=1e-6)
