@@ -840,7 +840,15 @@ inline int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int D,
 template <int K, int CL, bool TWO>
 inline int mma_launch_kpt(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
                           const MmaPlan& pl, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(scan_mma_kernel<K, CL, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
+  // the attribute sticks to the function on a device: set it once per (instantiation, device, size) of this thread
+  static thread_local int attr_dev = -1;
+  static thread_local size_t attr_smem = 0;
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess && (dev != attr_dev || pl.smem + 1024 > attr_smem)) {
+    e = cudaFuncSetAttribute(scan_mma_kernel<K, CL, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
+    if (e == cudaSuccess) { attr_dev = dev; attr_smem = pl.smem + 1024; }
+  }
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "smem attribute: %s", cudaGetErrorString(e)); return 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)pl.ctas);
