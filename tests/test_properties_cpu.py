@@ -1,0 +1,86 @@
+"""Property tests (hypothesis) of the mathematical claims the engine's design rests on, checked on the
+CPU oracle: rank-by-counting == rank-by-sorting, the KG boost as a sparse side path, shard-and-merge == one scan,
+row permutations permute indices."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import oracle as O
+
+
+def _scores(draw, q, m, ties):
+    vals = draw(st.lists(st.integers(-40, 40) if ties else st.floats(-1, 1, allow_nan=False, width=32),
+                         min_size=q * m, max_size=q * m))
+    return (np.array(vals, dtype=np.float64) / (8.0 if ties else 1.0)).reshape(q, m)
+
+
+@st.composite
+def case(draw):
+    q, m = draw(st.integers(1, 6)), draw(st.integers(1, 24))
+    s = _scores(draw, q, m, draw(st.booleans()))
+    tgt = np.array(draw(st.lists(st.integers(0, m - 1), min_size=q, max_size=q)), dtype=np.int64)
+    return s, tgt
+
+
+@settings(max_examples=200, deadline=None)
+@given(case())
+def test_rank_by_counting_equals_rank_by_stable_sort(c):
+    s, tgt = c
+    order = np.argsort(-s, axis=1, kind="stable")
+    by_sort = np.array([int(np.where(order[i] == tgt[i])[0][0]) + 1 for i in range(len(tgt))])
+    assert np.array_equal(O.canon_rank(s, tgt), by_sort)
+    t = s[np.arange(len(tgt)), tgt][:, None]
+    by_count = 1 + ((s > t) | ((s == t) & (np.arange(s.shape[1])[None, :] < tgt[:, None]))).sum(axis=1)
+    assert np.array_equal(by_count, by_sort)
+
+
+@settings(max_examples=200, deadline=None)
+@given(case(), st.integers(1, 8), st.floats(0.05, 1.0), st.floats(0.0, 2.0), st.data())
+def test_kg_boost_is_a_sparse_side_path(c, k, alpha, bonus, data):
+    """final = alpha*clip + bonus*[hit], alpha > 0, bonus >= 0  =>  top-k(final) is inside top-k(clip) U hits."""
+    s, _ = c
+    q, m = s.shape
+    k = min(k, m)
+    hit = np.array(data.draw(st.lists(st.booleans(), min_size=q * m, max_size=q * m))).reshape(q, m)
+    final = O.canon_fused64(s, None, 1.0, 0.0, alpha, np.where(hit, bonus, 0.0))
+    top_final, _ = O.canon_topk(final, k)
+    top_clip, _ = O.canon_topk(s, k)
+    for i in range(q):
+        allowed = set(top_clip[i].tolist()) | set(np.nonzero(hit[i])[0].tolist())
+        assert set(top_final[i].tolist()) <= allowed
+
+
+@settings(max_examples=150, deadline=None)
+@given(case(), st.integers(1, 8), st.integers(1, 4))
+def test_shard_and_merge_equals_one_scan(c, k, shards):
+    s, _ = c
+    q, m = s.shape
+    k = min(k, m)
+    want_i, want_s = O.canon_topk(s, k)
+    bounds = [m * r // shards for r in range(shards + 1)]
+    cand = [[] for _ in range(q)]
+    for r in range(shards):
+        lo, hi = bounds[r], bounds[r + 1]
+        if hi == lo:
+            continue
+        idx, sc = O.canon_topk(s[:, lo:hi], min(k, hi - lo))
+        for i in range(q):
+            cand[i] += [(-sc[i, j], idx[i, j] + lo) for j in range(idx.shape[1])]
+    for i in range(q):
+        best = sorted(cand[i])[:k]                                  # (score desc, global index asc)
+        assert [b[1] for b in best] == want_i[i].tolist() and [-b[0] for b in best] == want_s[i].tolist()
+
+
+@settings(max_examples=150, deadline=None)
+@given(case(), st.integers(1, 6), st.randoms(use_true_random=False))
+def test_row_permutation_permutes_indices_when_scores_are_distinct(c, k, rnd):
+    s, _ = c
+    q, m = s.shape
+    k = min(k, m)
+    if any(len(set(row.tolist())) < m for row in s):
+        return                                                      # ties are broken by index, which a permutation changes
+    perm = list(range(m))
+    rnd.shuffle(perm)
+    perm = np.array(perm)
+    a, _ = O.canon_topk(s, k)
+    b, _ = O.canon_topk(s[:, perm], k)
+    assert np.array_equal(perm[b], a)
