@@ -14,7 +14,7 @@ injectable so that the collective logic can be exercised with the gloo backend o
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.distributed as dist

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import KemrError, PATH_AUTO, PATH_MMA, PATH_WARP, FLAG_OVERFLOW, FLAG_UNCERTIFIED
+from ._lib import KemrError, PATH_AUTO, PATH_MMA, PATH_WARP, FLAG_OVERFLOW, FLAG_UNCERTIFIED  # noqa: F401  (PATH_* re-exported)
 
 DEFAULT_EPS = 2e-5      # assumed bound on |fp32 scan score - canonical binary64 score|
 MAX_K_SEL = 128

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import engine
-from .metrics import _metrics_from_ranks, compute_mrr_and_mean_rank, compute_recall_at_k
+from .metrics import _metrics_from_ranks, compute_mrr_and_mean_rank, compute_recall_at_k  # noqa: F401  (re-exported like the reference's fusion.py:3)
 
 _DEFAULT_OMEGA = {1: 1.0, 5: 0.8, 20: 0.5, 50: 0.3, float("inf"): 0.1}      # fusion.py:164-170
 

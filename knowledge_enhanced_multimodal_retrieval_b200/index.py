@@ -9,7 +9,7 @@ the reference delegates to remote code (`CLIPRetriever.search`, fetched from the
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -11,7 +11,7 @@ a fused device reduction that reproduces numpy's summation order, so the returne
 from __future__ import annotations
 
 import logging
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import numpy as np
 import torch

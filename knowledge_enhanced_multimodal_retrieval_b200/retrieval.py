@@ -14,7 +14,7 @@ uses (`metrics.py:145-148`): score = alpha*T2I + (1-alpha)*T2T, top-`top_k`, des
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Sequence, Union
+from typing import Callable, Dict, List, Optional
 
 import numpy as np
 
