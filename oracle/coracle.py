@@ -41,6 +41,28 @@ def _csr(hits):
             np.ascontiguousarray(bon, np.float64))
 
 
+class _QueryWeights:
+    """Per-query fusion weights (arrays [Q]) for the duration of one oracle call; scalars pass through."""
+
+    def __init__(self, w_a, w_b, Q):
+        self.arrays = None
+        if np.ndim(w_a) or np.ndim(w_b):
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(w_a, np.float64).reshape(-1), (Q,)))
+            b = np.ascontiguousarray(np.broadcast_to(np.asarray(w_b, np.float64).reshape(-1), (Q,)))
+            self.arrays = (a, b)
+        self.w_a = 0.0 if self.arrays else float(w_a)
+        self.w_b = 0.0 if self.arrays else float(w_b)
+
+    def __enter__(self):
+        if self.arrays:
+            load().oracle_set_query_weights(_p(self.arrays[0]), _p(self.arrays[1]))
+        return self
+
+    def __exit__(self, *exc):
+        if self.arrays:
+            load().oracle_set_query_weights(None, None)
+
+
 def scores(q, ga, gb=None, w_a=1.0, w_b=0.0, alpha=1.0, hits=None):
     q, ga = _bits(q), _bits(ga)
     gb = _bits(gb) if gb is not None else None
@@ -48,8 +70,9 @@ def scores(q, ga, gb=None, w_a=1.0, w_b=0.0, alpha=1.0, hits=None):
     M = ga.shape[0]
     out = np.empty((Q, M), np.float64)
     rp, col, bon = _csr(hits)
-    load().oracle_scores(_p(q), Q, _p(ga), _p(gb), C.c_int64(M), D, C.c_double(w_a), C.c_double(w_b),
-                         C.c_double(alpha), _p(rp), _p(col), _p(bon), _p(out))
+    with _QueryWeights(w_a, w_b, Q) as w:
+        load().oracle_scores(_p(q), Q, _p(ga), _p(gb), C.c_int64(M), D, C.c_double(w.w_a), C.c_double(w.w_b),
+                             C.c_double(alpha), _p(rp), _p(col), _p(bon), _p(out))
     return out
 
 
@@ -64,6 +87,7 @@ def topk_rank(q, ga, gb=None, w_a=1.0, w_b=0.0, alpha=1.0, hits=None, k=0, targe
     tgt = np.ascontiguousarray(target, np.int64) if target is not None else None
     rank = np.empty((Q,), np.int64) if target is not None else None
     rp, col, bon = _csr(hits)
-    load().oracle_topk_rank(_p(q), Q, _p(ga), _p(gb), C.c_int64(M), D, C.c_double(w_a), C.c_double(w_b),
-                            C.c_double(alpha), _p(rp), _p(col), _p(bon), k, _p(idx), _p(sc), _p(tgt), _p(rank))
+    with _QueryWeights(w_a, w_b, Q) as w:
+        load().oracle_topk_rank(_p(q), Q, _p(ga), _p(gb), C.c_int64(M), D, C.c_double(w.w_a), C.c_double(w.w_b),
+                                C.c_double(alpha), _p(rp), _p(col), _p(bon), k, _p(idx), _p(sc), _p(tgt), _p(rank))
     return idx, sc, rank

@@ -57,11 +57,18 @@ static inline int ahead(double sa, int64_t ia, double sb, int64_t ib) {
   return sa > sb || (sa == sb && ia < ib);
 }
 
+/* optional per-query fusion weights [Q] (gated fusion heads, fusion_model.py:21,178,194); NULL = the scalars.
+ * Set before a call with oracle_set_query_weights, cleared with (NULL, NULL). */
+static const double* g_wq_a = 0;
+static const double* g_wq_b = 0;
+void oracle_set_query_weights(const double* wq_a, const double* wq_b) { g_wq_a = wq_a; g_wq_b = wq_b; }
+
 /* final scores of query qi against all M rows -> out[M]; hits (CSR, unique cols) add their bonus */
 static void score_row(const uint16_t* q, const uint16_t* ga, const uint16_t* gb, int64_t M, int D, double wa,
                       double wb, double alpha, const int64_t* rowptr, const int32_t* col, const double* bonus,
                       int qi, double* out, double* qd) {
   for (int d = 0; d < D; ++d) qd[d] = bf16_to_f64(q[(size_t)qi * D + d]);
+  if (g_wq_a) { wa = g_wq_a[qi]; wb = g_wq_b[qi]; }
   for (int64_t j = 0; j < M; ++j) {
     const double sa = canon_dot(qd, ga + (size_t)j * D, D);
     const double sb = gb ? canon_dot(qd, gb + (size_t)j * D, D) : 0.0;

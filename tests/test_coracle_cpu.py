@@ -32,3 +32,22 @@ def test_c_oracle_short_gallery_padding():
     s = synth.make_retrieval_set(Q=3, M=4, D=16, seed=1, fused=False, diagonal=False)
     idx, sc, _ = CO.topk_rank(s.query, s.image, k=7)
     assert (idx[:, 4:] == -1).all() and np.isneginf(sc[:, 4:]).all()
+
+
+def test_c_oracle_per_query_weights_equal_numpy_oracle():
+    """Gated fusion heads: per-query (w_a, w_b) arrays through the C oracle == oracle.canon_fused64 with arrays."""
+    import numpy as np
+    from oracle import oracle as O
+    from knowledge_enhanced_multimodal_retrieval_b200 import synth
+    s = synth.make_retrieval_set(Q=40, M=300, D=128, seed=13, fused=True, lam=0.2, diagonal=True)
+    rng = np.random.default_rng(1)
+    gate = rng.uniform(0.05, 0.95, 40).astype(np.float32)
+    wa, wb = gate.astype(np.float64), (np.float32(1) - gate).astype(np.float64)
+    want = O.canon_fused64(O.canon_dot64(s.query, s.image), O.canon_dot64(s.query, s.target), wa, wb)
+    got = CO.scores(s.query, s.image, s.target, wa, wb)
+    assert np.array_equal(got, want)
+    idx, sc, rank = CO.topk_rank(s.query, s.image, s.target, wa, wb, k=7, target=s.target_idx)
+    widx, wsc = O.canon_topk(want, 7)
+    assert np.array_equal(idx, widx) and np.array_equal(sc, wsc) and np.array_equal(rank, O.canon_rank(want, s.target_idx))
+    again = CO.scores(s.query, s.image, s.target, 0.5, 0.5)            # the scalars are back after the call
+    assert np.array_equal(again, O.canon_fused64(O.canon_dot64(s.query, s.image), O.canon_dot64(s.query, s.target), 0.5, 0.5))
