@@ -178,6 +178,49 @@ def main():
     out_json["engine"] = {"fuse_cases": cases, "calls": engine_calls,
                           "call_inputs": {"clip": cases[-1]["clip"], "sparql": cases[-1]["sparql"]}}
 
+    # ------------------------------------------------------------------ learned fusion heads (fusion_model.py)
+    # the UNMODIFIED torch modules of the reference, CPU fp32, eval mode, parameters set from a seeded generator;
+    # scores -> the reference's own metrics.  Inputs: the square small set above (query i <-> candidate i).
+    import torch
+    from src.clip.model import fusion_model as rheads
+    hr = np.random.default_rng(29)
+    D = sq.query.shape[1]
+    tq, ti, tt = (torch.from_numpy(np.ascontiguousarray(x)) for x in (sq.query, sq.image, sq.target))
+    heads = {}
+
+    def run_head(name, module, params):
+        module.eval()
+        with torch.no_grad():
+            for key, val in params.items():
+                obj, attr = module, key
+                for part in key.split(".")[:-1]:
+                    obj = getattr(obj, part) if not part.isdigit() else obj[int(part)]
+                attr = key.split(".")[-1]
+                getattr(obj, attr).copy_(torch.from_numpy(np.asarray(val, dtype=np.float32)).reshape(getattr(obj, attr).shape))
+            scores = module(tq, ti, tt).numpy().astype(np.float32)
+        heads[name] = {"params": {k: np.asarray(v, dtype=np.float32).reshape(-1).tolist() for k, v in params.items()},
+                       "metrics": f64dict(rmetrics.compute_retrieval_metrics_fusion(scores)),
+                       "top5": np.argsort(-scores, axis=1, kind="stable")[:, :5].tolist(),
+                       "score_checksum": float(scores.astype(np.float64).sum()),
+                       "score_row0": scores[0, :8].astype(np.float64).tolist()}
+        return scores
+
+    w = hr.normal(0, 0.6, D).astype(np.float32)
+    run_head("simple_gated", rheads.SimpleGatedFusion(embed_dim=D), {"query_weight": w, "bias": [0.3]})
+    run_head("simple_gated_with_bias", rheads.SimpleGatedFusionWithBias(embed_dim=D), {"query_weight": w * 0.5, "bias": -1.0})
+    run_head("gated_mlp", rheads.GatedFusionHead(embed_dim=D),
+             {"gate_net.0.weight": hr.normal(0, 0.2, (128, D)), "gate_net.0.bias": hr.normal(0, 0.1, 128),
+              "gate_net.3.weight": hr.normal(0, 0.3, (1, 128)), "gate_net.3.bias": [0.05]})
+    run_head("bilinear", rheads.BilinearFusionHead(embed_dim=D),
+             {"W_image.weight": np.eye(D) + hr.normal(0, 0.02, (D, D)), "W_target.weight": np.eye(D) + hr.normal(0, 0.02, (D, D)),
+              "alpha": 0.4})
+    with torch.no_grad():
+        g = rheads.SimpleGatedFusion(embed_dim=D)
+        g.query_weight.copy_(torch.from_numpy(w)); g.bias.fill_(0.3)
+        gate = torch.sigmoid((tq * g.query_weight).sum(dim=1, keepdim=True) + g.bias).numpy().reshape(-1)
+    heads["simple_gated"]["gate"] = gate.astype(np.float64).tolist()
+    out_json["fusion_heads"] = heads
+
     import numpy
     out_json["provenance"] = {"numpy": numpy.__version__, "reference": REF,
                               "note": "outputs of the unmodified reference functions"}

@@ -1,4 +1,6 @@
 """CPU: the numpy oracle reproduces every golden vector produced by the unmodified reference."""
+import os
+
 import numpy as np
 import pytest
 
@@ -166,3 +168,47 @@ def test_grouped_and_gated_restatements_agree_with_the_canonical_forms():
     w = rng.normal(0, 0.3, D).astype(np.float32)
     g = O.ref_gate_linear(query, w, -0.5)
     assert g.dtype == np.float32 and np.allclose(g, 1 / (1 + np.exp(-(query.astype(np.float64) @ w.astype(np.float64) - 0.5))), atol=1e-6)
+
+
+def test_fusion_heads_restatements_match_the_reference_modules(golden):
+    """The oracle's restatements of the learned fusion heads against outputs of the UNMODIFIED torch modules of
+    `src/clip/model/fusion_model.py` (tests/golden/make_golden.py, section "learned fusion heads")."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_set.npz"))
+    from knowledge_enhanced_multimodal_retrieval_b200 import synth
+    q, img, tgt = (synth.bf16_bits_to_f32(z[k]) for k in ("sq_query_bits", "sq_image_bits", "sq_target_bits"))
+    H = golden["fusion_heads"]
+
+    def check(name, scores, exact_rows=True):
+        h = H[name]
+        assert np.allclose(scores[0, :8], h["score_row0"], atol=2e-6), name
+        assert abs(float(scores.astype(np.float64).sum()) - h["score_checksum"]) < 1e-2, name
+        got = O.ref_metrics_from_matrix(scores)
+        for k, v in h["metrics"].items():                        # at most one near-tie may flip between torch and numpy
+            assert abs(float(got[k]) - v) <= 100.0 / len(scores) + 1e-9, (name, k, got[k], v)
+        top5 = np.argsort(-scores, axis=1, kind="stable")[:, :5]
+        assert (top5 == np.array(h["top5"])).mean() > 0.99, name
+
+    p = H["simple_gated"]["params"]
+    gate = O.ref_gate_linear(q, np.array(p["query_weight"], np.float32), p["bias"][0])
+    assert np.abs(gate - np.array(H["simple_gated"]["gate"])).max() < 2e-6
+    check("simple_gated", O.ref_gated_scores(q, img, tgt, gate))
+    p = H["simple_gated_with_bias"]["params"]
+    check("simple_gated_with_bias", O.ref_gated_scores(q, img, tgt, O.ref_gate_linear(q, np.array(p["query_weight"], np.float32), p["bias"][0])))
+    p = H["gated_mlp"]["params"]
+    D = q.shape[1]
+    w1 = np.array(p["gate_net.0.weight"], np.float32).reshape(128, D)
+    hid = np.maximum(q @ w1.T + np.array(p["gate_net.0.bias"], np.float32), 0)
+    logit = hid @ np.array(p["gate_net.3.weight"], np.float32).reshape(-1) + np.float32(p["gate_net.3.bias"][0])
+    check("gated_mlp", O.ref_gated_scores(q, img, tgt, (1 / (1 + np.exp(-logit))).astype(np.float32)))
+    p = H["bilinear"]["params"]
+    wi = np.array(p["W_image.weight"], np.float32).reshape(D, D)
+    wt = np.array(p["W_target.weight"], np.float32).reshape(D, D)
+    a = np.float32(1 / (1 + np.exp(-np.float32(p["alpha"][0]))))
+    check("bilinear", a * (q @ (img @ wi.T).T) + (np.float32(1) - a) * (q @ (tgt @ wt.T).T))
+    # the canonical (binary64, stable) form of the gated score gives the reference's metrics as well
+    g64 = gate.astype(np.float64)
+    can = O.canon_fused64(O.canon_dot64(q, img), O.canon_dot64(q, tgt), g64, (np.float32(1) - gate).astype(np.float64))
+    want = H["simple_gated"]["metrics"]
+    got = O.metrics_from_ranks(O.canon_rank(can, np.arange(len(q))))
+    for k, v in want.items():
+        assert abs(float(got[k]) - v) <= 100.0 / len(q) + 1e-9, (k, got[k], v)
