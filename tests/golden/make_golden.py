@@ -48,6 +48,36 @@ def import_reference():
     return rmetrics, rfusion, rretrieval
 
 
+class FakeTextDataset:
+    """Stands in for TextOnlyDataset (evaluate_text_models.py:28-81): item i = the 5 text variants of artefact i."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return [f"t{i}v{v}" for v in range(5)]
+
+
+class FakeTextModel:
+    """Stands in for a SentenceTransformer: `.encode(texts, ...)` returns the stored (already normalised) vectors."""
+
+    def __init__(self, table):
+        self.table = table
+
+    def to(self, device):
+        return self
+
+    def eval(self):
+        return self
+
+    def encode(self, texts, convert_to_tensor=True, device="cpu", show_progress_bar=False, normalize_embeddings=True):
+        import torch
+        return torch.from_numpy(np.stack([self.table[t] for t in texts]).astype(np.float32))
+
+
 def quiet(fn, *a, **k):
     with contextlib.redirect_stdout(io.StringIO()):
         return fn(*a, **k)
@@ -220,6 +250,30 @@ def main():
         gate = torch.sigmoid((tq * g.query_weight).sum(dim=1, keepdim=True) + g.bias).numpy().reshape(-1)
     heads["simple_gated"]["gate"] = gate.astype(np.float64).tolist()
     out_json["fusion_heads"] = heads
+
+    # ------------------------------------------------------------------ grouped ground truth (baselines/evaluate_text_models.py)
+    # the UNMODIFIED evaluate_text_model(), fed by a fake SentenceTransformer that looks embeddings up by text and a
+    # fake 5-variant dataset; `sentence_transformers` itself is absent here and stubbed.
+    if "sentence_transformers" not in sys.modules:
+        st_mod = types.ModuleType("sentence_transformers")
+        st_mod.SentenceTransformer = object
+        sys.modules["sentence_transformers"] = st_mod
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_eval_text_models", os.path.join(REF, "baselines", "evaluate_text_models.py"))
+    rtext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rtext)
+    Ng, Dg = 48, 64
+    gr = np.random.default_rng(41)
+    base = synth.make_gallery(Ng, Dg, 43)
+    variants = [synth.round_to_bf16(synth.l2_normalize(base * 0.7 + gr.normal(0, 1 / np.sqrt(Dg), (Ng, Dg)).astype(np.float32)))
+                for _ in range(5)]
+    table = {f"t{i}v{v}": variants[v][i] for i in range(Ng) for v in range(5)}
+    grouped = {"variants_bits": [synth.f32_to_bf16_bits(v).tolist() for v in variants]}
+    for mode in ("single", "multi"):
+        res = quiet(rtext.evaluate_text_model, FakeTextModel(table), FakeTextDataset(Ng), batch_size=16, device="cpu",
+                    mode=mode, seed=42)
+        grouped[mode] = f64dict(res)
+    out_json["grouped_text_models"] = grouped
 
     import numpy
     out_json["provenance"] = {"numpy": numpy.__version__, "reference": REF,

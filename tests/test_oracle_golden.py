@@ -212,3 +212,38 @@ def test_fusion_heads_restatements_match_the_reference_modules(golden):
     got = O.metrics_from_ranks(O.canon_rank(can, np.arange(len(q))))
     for k, v in want.items():
         assert abs(float(got[k]) - v) <= 100.0 / len(q) + 1e-9, (k, got[k], v)
+
+
+def test_grouped_ground_truth_restatement_matches_the_reference_driver(golden):
+    """`baselines/evaluate_text_models.py::evaluate_text_model` itself (unmodified, run with a fake encoder and a
+    fake 5-variant dataset by make_golden.py), single and multi mode.  The driver re-normalises the embeddings in
+    fp32 (:160-162) before scoring; with that step the oracle's restatement reproduces its numbers, and the
+    canonical counting form on the bf16 inputs stays within one near-tie rank flip of them."""
+    G = golden["grouped_text_models"]
+    bf16 = [synth.bf16_bits_to_f32(np.array(v, dtype=np.uint16)) for v in G["variants_bits"]]
+    renorm = [v / np.linalg.norm(v, axis=1, keepdims=True) for v in bf16]          # evaluate_text_models.py:161
+    N = len(bf16[0])
+
+    def pool(variants, exclude):
+        cands = np.stack([variants[v][i] for i in range(N) for v in range(5) if v != exclude])
+        return cands, np.repeat(np.arange(N), 4)
+
+    def positions(query, cands, t2a):                                # the driver's loops (:237-279), fp32 + argsort
+        sim = query @ cands.T
+        return np.array([int(np.where(t2a[np.argsort(-sim[i])] == i)[0][0]) + 1 for i in range(N)])
+
+    cands, t2a = pool(renorm, 0)
+    ref = O.ref_grouped_metrics(renorm[0], cands, t2a)
+    for k, v in G["single"].items():
+        assert float(ref[k]) == pytest.approx(v, abs=1e-9), k
+    multi_pos = np.concatenate([positions(renorm[qv], *pool(renorm, qv)) for qv in range(5)])
+    multi = O.metrics_from_ranks(multi_pos, prefix="T2T")
+    for k, v in G["multi"].items():
+        assert float(multi[k]) == pytest.approx(v, abs=1e-9), k
+    # canonical (binary64, stable) ranks on the bf16 inputs the engine sees
+    can_pos = np.concatenate([O.canon_grouped_rank(O.canon_dot64(bf16[qv], pool(bf16, qv)[0]), pool(bf16, qv)[1])
+                              for qv in range(5)])
+    assert (can_pos != multi_pos).sum() <= 1                         # one fp32 near-tie at ranks 2/3 in this set
+    can = O.metrics_from_ranks(can_pos, prefix="T2T")
+    for k, v in G["multi"].items():
+        assert abs(float(can[k]) - v) <= 100.0 / len(can_pos) + 1e-9, k
