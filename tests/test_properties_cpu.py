@@ -84,3 +84,28 @@ def test_row_permutation_permutes_indices_when_scores_are_distinct(c, k, rnd):
     a, _ = O.canon_topk(s, k)
     b, _ = O.canon_topk(s[:, perm], k)
     assert np.array_equal(perm[b], a)
+
+
+def _rd_div32(a, b):
+    """fp32 division rounded toward -inf (what __fdiv_rd does), from a binary64 quotient: the quotient of two 24-bit
+    significands is either an fp32 value or at least ~2^-47 (relative) away from one, so the 2^-53 rounding of the
+    binary64 division cannot move it across an fp32 value."""
+    q = np.float64(a) / np.float64(b)
+    f = np.float32(q)
+    return np.nextafter(f, np.float32(-np.inf)) if np.float64(f) > q else f
+
+
+@settings(max_examples=2000, deadline=None)
+@given(st.floats(-4, 4, width=32, allow_nan=False), st.floats(2 ** -10, 4, width=32), st.floats(-8, 8, width=32, allow_nan=False),
+       st.integers(-3, 3))
+def test_raw_accumulator_compare_never_rejects_a_survivor(thr, w, raw, ulps):
+    """Epilogue of the tcgen05 scan on short lists (csrc/scan_mma.cuh, append8_raw): the raw accumulator is compared
+    with thr_raw = RD(thr / w) instead of weighting every score; `raw <= thr_raw  =>  fl(w * raw) <= thr` must hold
+    for every fp32 thr, w > 0 and raw, so nothing that would pass the weighted test is ever skipped."""
+    thr, w = np.float32(thr), np.float32(w)
+    thr_raw = _rd_div32(thr, w)
+    for r in (np.float32(raw), thr_raw):                             # a random value, and the neighbourhood of the cut
+        for _ in range(abs(ulps)):
+            r = np.nextafter(r, np.float32(np.inf if ulps > 0 else -np.inf))
+        if r <= thr_raw:
+            assert np.float32(w * r) <= thr
