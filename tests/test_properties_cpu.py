@@ -109,3 +109,39 @@ def test_raw_accumulator_compare_never_rejects_a_survivor(thr, w, raw, ulps):
             r = np.nextafter(r, np.float32(np.inf if ulps > 0 else -np.inf))
         if r <= thr_raw:
             assert np.float32(w * r) <= thr
+
+
+def _reglist_insert(sc, ix, s, r):
+    """RegList<K>::insert of csrc/scan_mma.cuh, statement for statement (precondition: s > sc[K-1])."""
+    K = len(sc)
+    up_next = True
+    for p in range(K - 1, 0, -1):
+        up = s > sc[p - 1]
+        nsc = sc[p - 1] if up else (s if up_next else sc[p])
+        nix = ix[p - 1] if up else (r if up_next else ix[p])
+        sc[p], ix[p] = nsc, nix
+        up_next = up
+    if up_next:
+        sc[0], ix[0] = s, r
+
+
+@settings(max_examples=500, deadline=None)
+@given(st.sampled_from([1, 2, 8, 16]), st.lists(st.integers(-6, 6), min_size=0, max_size=60), st.integers(1, 16))
+def test_register_list_keeps_the_exact_topk_with_lowest_row_first(K, values, trigger):
+    """The epilogue's per-thread list: scores arrive in increasing row order, survivors (score > running threshold)
+    are buffered and folded in batches (the threshold only tightens at a fold), ties keep the lower row ahead."""
+    sc, ix = [-np.inf] * K, [0xffffffff] * K
+    thr, buf = -np.inf, []
+    for row, v in enumerate(values):
+        s = v / 4.0
+        if s > thr:
+            buf.append((s, row))
+        if len(buf) >= trigger or row == len(values) - 1:
+            for bs, br in buf:                                       # fold: re-check against the tightened threshold
+                if bs > thr:
+                    _reglist_insert(sc, ix, bs, br)
+                    thr = sc[K - 1]
+            buf = []
+    want = sorted(((-v / 4.0, row) for row, v in enumerate(values)))[:K]
+    got = [(-s, r) for s, r in zip(sc, ix) if r != 0xffffffff]
+    assert got == want
