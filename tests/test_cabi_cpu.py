@@ -102,3 +102,25 @@ def test_order_key_roundtrip():
     xs = np.array([-np.inf, -1.0, -1e-30, -0.0, 0.0, 1e-30, 0.5, 1.0, np.inf], np.float32)
     keys = [int(order(x)) for x in xs]
     assert keys == sorted(keys)
+
+
+def test_integration_md_ctypes_stub_matches_the_abi():
+    """The stub INTEGRATION.md shows a maintainer (section 2) must keep working against the header: same entry points,
+    same argument order.  Without a GPU the calls fail in CUDA, not in argument marshalling."""
+    import ctypes as C
+    import re
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    used = set(re.findall(r"lib\.(kemr_\w+)", text))
+    assert used and used <= set(_lib.EXPORTS), used - set(_lib.EXPORTS)
+    header = open(os.path.join(ROOT, "include", "kemr.h")).read()
+    for name in re.findall(r"`(kemr_\w+)`", text):
+        base = name.rstrip("*")
+        assert any(e.startswith(base.replace("_*", "")) for e in _lib.EXPORTS) or base in header, name
+    lib = C.CDLL(_lib.LIB_PATH)
+    lib.kemr_last_error.restype = C.c_char_p
+    img = np.zeros((4, 8), np.uint16)
+    h = C.c_void_p()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.kemr_index_create(vp(img), vp(img), C.c_int64(4), 8, 16, 10, C.byref(h))      # the stub's call, verbatim shape
+    if rc != 0:
+        assert rc == 2 and b"cuda" in lib.kemr_last_error().lower()                         # KEMR_ERR_CUDA on a CPU-only box
