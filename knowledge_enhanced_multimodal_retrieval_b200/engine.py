@@ -54,6 +54,11 @@ def scan_plan(Q: int, M: int, D: int, galleries: int = 1, k_sel: int = 16, equal
 
 # --------------------------------------------------------------------------- workspace
 class _Workspace:
+    """One scratch buffer per device, grown on demand and reused by every call of this module.  Calls are enqueued
+    on the caller's current stream and share this buffer, so two scans must not be in flight on DIFFERENT streams at
+    the same time (the reference is single-threaded); callers that want that pass their own workspace to
+    `scan_topk_raw`."""
+
     def __init__(self):
         self.buf: Dict[int, torch.Tensor] = {}
 
