@@ -33,3 +33,14 @@ def small_set():
         d[name] = synth.bf16_bits_to_f32(d[name + "_bits"])
     d.update(kg)
     return d
+
+
+# hypothesis: the same examples on every run (the driver's CPU suite must not depend on a random seed); explore with
+# `HYPOTHESIS_PROFILE=explore pytest ...` when hunting for counterexamples
+try:
+    from hypothesis import settings as _hyp_settings
+    _hyp_settings.register_profile("repeatable", derandomize=True, deadline=None)
+    _hyp_settings.register_profile("explore", deadline=None, max_examples=5000)
+    _hyp_settings.load_profile(os.environ.get("HYPOTHESIS_PROFILE", "repeatable"))
+except ImportError:                      # pragma: no cover
+    pass
