@@ -30,7 +30,7 @@ WORKLOADS = {
     # name: Q, M, D, fused, k, kg
     "c1": dict(Q=4300, M=43000, D=512, fused=False, k=10, seed=0),
     "c2": dict(Q=1000, M=43000, D=768, fused=True, k=10, seed=1),
-    "c3": dict(Q=1, M=43000, D=768, fused=True, k=10, seed=1),
+    "c3": dict(Q=1, M=43000, D=768, fused=True, k=10, seed=1, kg=True),      # + KG-hit boost: alpha 0.8 / beta 0.2, ~Poisson(20) hits
     "b64": dict(Q=64, M=2_000_000, D=768, fused=False, k=10, seed=5, device_synth=True),
     "b4096": dict(Q=4096, M=1_250_000, D=768, fused=False, k=100, seed=4, device_synth=True),
     # row-sharded gallery (north_star multi-GPU path): M rows PER GPU, queries replicated, local top-k with
@@ -110,11 +110,17 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
-def reference_step(q, img, tgt, wi, wt, k):
+KG_ALPHA, KG_BETA = 0.8, 0.2            # RetrievalEngine defaults (retrieval.py:79)
+
+
+def reference_step(q, img, tgt, wi, wt, k, kg=None):
     """The reference's own CPU scoring path for this workload, restated in oracle/oracle.py:
-    fp32 BLAS similarity (metrics.py:102,145-148), weighted sum, full-row argsort (metrics.py:34)."""
+    fp32 BLAS similarity (metrics.py:102,145-148), weighted sum, dense KG-indicator fusion (fusion.py:22-85) when the
+    workload has KG hits, full-row argsort (metrics.py:34)."""
     from oracle import oracle as O
     sim = O.ref_fused_similarity(q, tgt, img, wi, wt) if tgt is not None else O.ref_similarity(q, img)
+    if kg is not None:
+        sim = O.ref_weighted_fusion(sim, kg[0], kg[1], kg[2], KG_ALPHA, KG_BETA)
     order = np.argsort(-sim, axis=1)          # the reference sorts the entire row (metrics.py:34)
     return order[:, :k]
 
@@ -124,8 +130,12 @@ def cpu_sample(cfg, max_q):
     Q = min(cfg["Q"], max_q)
     M = min(cfg["M"], 43000)
     s = synth.make_retrieval_set(Q=Q, M=M, D=cfg["D"], seed=cfg["seed"], fused=cfg["fused"], lam=0.1,
-                                 diagonal=False)
+                                 diagonal=False, with_kg=bool(cfg.get("kg")))
     return s, Q, M
+
+
+def kg_of(cfg, s):
+    return (s.kg_results, s.query_uuids, s.uuids) if cfg.get("kg") else None
 
 
 def run_reference(args, cfg):
@@ -136,10 +146,10 @@ def run_reference(args, cfg):
     s, Q, M = cpu_sample(cfg, 1000)
     scale = (cfg["M"] / M)                      # rows beyond the sample are extrapolated linearly
     for _ in range(max(1, args.warmup if args.warmup < 2 else 1)):
-        reference_step(s.query, s.image, s.target, 0.5, 0.5, cfg["k"])
+        reference_step(s.query, s.image, s.target, 0.5, 0.5, cfg["k"], kg_of(cfg, s))
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        reference_step(s.query, s.image, s.target, 0.5, 0.5, cfg["k"])
+        reference_step(s.query, s.image, s.target, 0.5, 0.5, cfg["k"], kg_of(cfg, s))
     dt = (time.perf_counter() - t0) * scale
     qps = Q * args.steps / dt
     cores = os.cpu_count()
@@ -160,6 +170,7 @@ def workload_config(args, cfg, world):
                         f"{'fused T2I+T2T (0.5/0.5)' if cfg['fused'] else 'single gallery'}, top-{cfg['k']}",
             "queries_per_step": cfg["Q"] * world, "gallery_rows": cfg["M"], "dim": cfg["D"],
             "galleries": 2 if cfg["fused"] else 1, "k": cfg["k"],
+            "kg_boost": f"alpha {KG_ALPHA} / beta {KG_BETA}, ~Poisson(20) KG hits per query (CSR in the step)" if cfg.get("kg") else None,
             "parallelism": "single GPU" if world == 1 else f"query-sharded x{world}, gallery replicated, "
                                                            "NCCL all-gather of top-k",
             "l2": "L2 flushed (512 MiB memset) before every timed step"}
@@ -404,7 +415,8 @@ def run_ours(args, cfg):
         q_host = torch.nn.functional.normalize(q_host, dim=1).cpu().numpy()
         host_sets = None
     else:
-        s = synth.make_retrieval_set(Q=Q, M=M, D=D, seed=cfg["seed"], fused=cfg["fused"], lam=0.1, diagonal=False)
+        s = synth.make_retrieval_set(Q=Q, M=M, D=D, seed=cfg["seed"], fused=cfg["fused"], lam=0.1, diagonal=False,
+                                     with_kg=bool(cfg.get("kg")))
         if rank:
             s.query = synth.make_queries((s.image, s.target) if cfg["fused"] else (s.image,),
                                          s.target_idx, 0.1, cfg["seed"] + 100 + rank)
@@ -413,7 +425,14 @@ def run_ours(args, cfg):
         host_sets = s
     q = engine.quantize(q_host)
     k_sel = engine.default_k_sel(k)
-    ws = engine.workspace_for(Q, M, D, k_sel)
+    alpha, hits, hits_csr = 1.0, None, None
+    if cfg.get("kg"):
+        # knowledge-graph boost in the step (BASELINE config 3): final = 0.8 * clip + 0.2 * [row in KG result]
+        from knowledge_enhanced_multimodal_retrieval_b200 import fusion
+        alpha, hits = fusion.kg_hits_for_strategy(host_sets.kg_results, host_sets.query_uuids, host_sets.uuids,
+                                                  "weighted", {"alpha": KG_ALPHA, "sparql_weight": KG_BETA})
+        hits_csr = (hits.rowptr.cpu().numpy(), hits.col.cpu().numpy(), hits.bonus.cpu().numpy())
+    ws = engine.workspace_for(Q, M, D, k_sel, hits.max_per_query if hits else 0)
     flags = torch.empty((Q,), dtype=torch.int32, device="cuda")
     packed = torch.empty((2, Q, k), dtype=torch.float64, device="cuda")      # [score | idx bit-cast]: the NCCL send buffer
     score, idx = packed[0], packed[1].view(torch.int64)                        # the select kernel writes straight into it
@@ -421,7 +440,7 @@ def run_ours(args, cfg):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
     def step():
-        engine.scan_topk_raw(q, img, tgt, wi, wt, 1.0, None, k, k_sel, engine.DEFAULT_EPS, 0, score, idx, flags, ws)
+        engine.scan_topk_raw(q, img, tgt, wi, wt, alpha, hits, k, k_sel, engine.DEFAULT_EPS, 0, score, idx, flags, ws)
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
 
@@ -449,12 +468,12 @@ def run_ours(args, cfg):
     qh = pin((Q, D), torch.float32)
     qh[:] = np.ascontiguousarray(q_host, dtype=np.float32)
     for _ in range(3):
-        hi.search(qh, k=k, t2i_weight=wi, t2t_weight=wt, out=out)
+        hi.search(qh, k=k, t2i_weight=wi, t2t_weight=wt, alpha=alpha, hits_csr=hits_csr, out=out)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        hi.search(qh, k=k, t2i_weight=wi, t2t_weight=wt, out=out)
+        hi.search(qh, k=k, t2i_weight=wi, t2t_weight=wt, alpha=alpha, hits_csr=hits_csr, out=out)
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -503,11 +522,11 @@ def run_ours(args, cfg):
         # CPU baseline beside it: bounded sample of the same workload on the host cores
         if world == 1 and not args.no_cpu_baseline:
             s2, Q2, M2 = cpu_sample(cfg, 1000)
-            reference_step(s2.query, s2.image, s2.target, 0.5, 0.5, k)
+            reference_step(s2.query, s2.image, s2.target, 0.5, 0.5, k, kg_of(cfg, s2))
             t0 = time.perf_counter()
             reps = 3
             for _ in range(reps):
-                reference_step(s2.query, s2.image, s2.target, 0.5, 0.5, k)
+                reference_step(s2.query, s2.image, s2.target, 0.5, 0.5, k, kg_of(cfg, s2))
             dt = (time.perf_counter() - t0) / reps * (M / M2)
             line["cpu_baseline"] = {"value": Q2 / dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{Q2} queries x {M2} rows x {D}-d, numpy sgemm + weighted sum + full-row "

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KEMR_ABI_VERSION 2
+#define KEMR_ABI_VERSION 3
 
 enum {
   KEMR_OK = 0,
@@ -108,8 +108,8 @@ int kemr_scan_topk(const uint16_t* q, int Q,
                    void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream);
 
 /* ---- canonical final score of arbitrary (query, local row) pairs (target scores, spot checks).
- *   pair_bonus may be NULL. */
-int kemr_score_pairs(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
+ *   pair_bonus may be NULL.  A pair whose row lies outside [0, M) scores NaN (ranks after everything). */
+int kemr_score_pairs(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int64_t M, int D,
                      double w_a, double w_b, double alpha,
                      const int32_t* pair_q, const int64_t* pair_row, const double* pair_bonus,
                      int64_t n_pairs, double* out_score64, kemr_stream_t stream);
@@ -147,7 +147,7 @@ int kemr_rank_count_gated(const uint16_t* q, int Q,
                           const double* t_score64, const int64_t* t_gidx, double eps, int64_t idx_base,
                           int64_t* out_count, int32_t* out_flags,
                           void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream);
-int kemr_score_pairs_gated(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
+int kemr_score_pairs_gated(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int64_t M, int D,
                            const double* w_a_q, const double* w_b_q, double alpha,
                            const int32_t* pair_q, const int64_t* pair_row, const double* pair_bonus,
                            int64_t n_pairs, double* out_score64, kemr_stream_t stream);

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libkemr.so")
 KEMR_OK = 0
 PATH_AUTO, PATH_WARP, PATH_MMA = 0, 1, 2
 FLAG_UNCERTIFIED, FLAG_OVERFLOW = 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = (
     "kemr_last_error", "kemr_abi_version", "kemr_device_info", "kemr_quantize_rows", "kemr_synth_rows",
@@ -46,12 +46,12 @@ def _declare(lib):
     lib.kemr_workspace_bytes.argtypes = [i32, i64, i32, i32, i64]
     lib.kemr_scan_topk.argtypes = [p, i32, p, p, i64, i32, f64, f64, f64, p, p, p, i64, i32, i32, f64, i64,
                                    p, p, p, p, p, sz, i32, p]
-    lib.kemr_score_pairs.argtypes = [p, p, p, i32, f64, f64, f64, p, p, p, i64, p, p]
+    lib.kemr_score_pairs.argtypes = [p, p, p, i64, i32, f64, f64, f64, p, p, p, i64, p, p]
     lib.kemr_scan_topk_gated.argtypes = [p, i32, p, p, i64, i32, p, p, f64, p, p, p, i64, i32, i32, f64, i64,
                                          p, p, p, p, p, sz, i32, p]
     lib.kemr_rank_count_gated.argtypes = [p, i32, p, p, i64, i32, p, p, f64, p, p, p, p, p, f64, i64,
                                           p, p, p, sz, i32, p]
-    lib.kemr_score_pairs_gated.argtypes = [p, p, p, i32, p, p, f64, p, p, p, i64, p, p]
+    lib.kemr_score_pairs_gated.argtypes = [p, p, p, i64, i32, p, p, f64, p, p, p, i64, p, p]
     lib.kemr_gate_linear.argtypes = [p, i32, i32, p, f32, p, p, p]
     lib.kemr_hits_workspace_bytes.restype = sz
     lib.kemr_hits_workspace_bytes.argtypes = [i32]

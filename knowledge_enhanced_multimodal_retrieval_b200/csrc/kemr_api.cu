@@ -333,34 +333,34 @@ extern "C" int kemr_scan_topk_gated(const uint16_t* q, int Q, const uint16_t* ga
                         workspace, workspace_bytes, path, stream);
 }
 
-static int score_pairs_impl(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
+static int score_pairs_impl(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int64_t M, int D,
                             double w_a, double w_b, const double* wq_a, const double* wq_b, double alpha,
                             const int32_t* pair_q, const int64_t* pair_row, const double* pair_bonus, int64_t n_pairs,
                             double* out_score64, kemr_stream_t stream) {
   if (!q || !gal_a || !pair_q || !pair_row || !out_score64) return fail(KEMR_ERR_ARG, "score_pairs: null pointer");
-  if (D <= 0 || D > kMaxD) return fail(KEMR_ERR_ARG, "score_pairs: bad D");
+  if (D <= 0 || D > kMaxD || M <= 0) return fail(KEMR_ERR_ARG, "score_pairs: bad D or M");
   if (n_pairs <= 0) return KEMR_OK;
   const int64_t blocks = std::min<int64_t>((n_pairs + 7) / 8, 148 * 8);
-  score_pairs_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(q, gal_a, gal_b, D, w_a, w_b, wq_a, wq_b, alpha, pair_q,
+  score_pairs_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(q, gal_a, gal_b, M, D, w_a, w_b, wq_a, wq_b, alpha, pair_q,
                                                               pair_row, pair_bonus, n_pairs, out_score64);
   LAUNCH_CHECK("score_pairs_kernel");
   return KEMR_OK;
 }
 
-extern "C" int kemr_score_pairs(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
+extern "C" int kemr_score_pairs(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int64_t M, int D,
                                 double w_a, double w_b, double alpha, const int32_t* pair_q,
                                 const int64_t* pair_row, const double* pair_bonus, int64_t n_pairs,
                                 double* out_score64, kemr_stream_t stream) {
-  return score_pairs_impl(q, gal_a, gal_b, D, w_a, w_b, nullptr, nullptr, alpha, pair_q, pair_row, pair_bonus, n_pairs,
+  return score_pairs_impl(q, gal_a, gal_b, M, D, w_a, w_b, nullptr, nullptr, alpha, pair_q, pair_row, pair_bonus, n_pairs,
                           out_score64, stream);
 }
 
-extern "C" int kemr_score_pairs_gated(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int D,
+extern "C" int kemr_score_pairs_gated(const uint16_t* q, const uint16_t* gal_a, const uint16_t* gal_b, int64_t M, int D,
                                       const double* w_a_q, const double* w_b_q, double alpha, const int32_t* pair_q,
                                       const int64_t* pair_row, const double* pair_bonus, int64_t n_pairs,
                                       double* out_score64, kemr_stream_t stream) {
   if (!w_a_q || !w_b_q || !gal_b) return fail(KEMR_ERR_ARG, "score_pairs_gated: needs both weight arrays and two galleries");
-  return score_pairs_impl(q, gal_a, gal_b, D, 0.0, 0.0, w_a_q, w_b_q, alpha, pair_q, pair_row, pair_bonus, n_pairs,
+  return score_pairs_impl(q, gal_a, gal_b, M, D, 0.0, 0.0, w_a_q, w_b_q, alpha, pair_q, pair_row, pair_bonus, n_pairs,
                           out_score64, stream);
 }
 
@@ -589,8 +589,8 @@ extern "C" int kemr_metrics_reduce_host(const int64_t* ranks, int Q, const int32
   unsigned long long sum = 0;
   for (int j = 0; j < n_k; ++j) out_hits[j] = 0;
   for (int i = 0; i < Q; ++i) {
-    sum += (unsigned long long)ranks[i];
-    for (int j = 0; j < n_k; ++j) out_hits[j] += ranks[i] <= k_values[j];
+    sum += (unsigned long long)rank_pos(ranks[i]);
+    for (int j = 0; j < n_k; ++j) out_hits[j] += ranks[i] > 0 && ranks[i] <= k_values[j];
   }
   out_stats[0] = (double)sum;
   out_stats[1] = 0.0 + pairwise_tree(Q, [&](int64_t off, int64_t n) { return pairwise_leaf(ranks, off, n); });

@@ -83,12 +83,19 @@ __global__ void synth_rows_kernel(uint16_t* __restrict__ dst, int64_t rows, int 
 
 // ------------------------------------------------------------------ rank of a column in a given matrix
 // metrics.py:34,62,68 on a caller-supplied matrix: stable descending order, NaN last.
+// A target column outside [0, M) (a matrix with more rows than columns, metrics.py:37) has no match in the
+// reference: `any(top_k == i)` is false and `argmax(all False) + 1` is 1.  It is reported as rank 0, which the
+// reductions below read as "recall miss, position 1".
 __global__ void __launch_bounds__(256) matrix_rank_kernel(const float* __restrict__ S, int Q, int64_t M,
                                                          int64_t ld, const int64_t* __restrict__ tcol,
                                                          int64_t* __restrict__ out_rank) {
   const int qi = blockIdx.x;
   const float* row = S + (size_t)qi * ld;
   const int64_t tc = tcol[qi];
+  if (tc < 0 || tc >= M) {
+    if (threadIdx.x == 0) out_rank[qi] = 0;
+    return;
+  }
   const float t = row[tc];
   const bool tnan = isnan(t);
   unsigned long long cnt = 0;
@@ -183,7 +190,9 @@ __global__ void matrix_hits_kernel(float* __restrict__ out, int Q, int64_t M, in
 // ------------------------------------------------------------------ metrics reduction
 // numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, *_pairwise_sum) over
 // a[i] = 1.0 / rank[i]; reproduced so that MRR is bit-identical to np.mean(1.0/pos)*100.
-__host__ __device__ inline double recip_rank(const int64_t* r, int64_t i) { return 1.0 / (double)r[i]; }
+// rank 0 = "target column not in the matrix": position 1 for MRR / Mean_Rank, never a recall hit (matrix_rank_kernel)
+__host__ __device__ inline int64_t rank_pos(int64_t r) { return r > 0 ? r : 1; }
+__host__ __device__ inline double recip_rank(const int64_t* r, int64_t i) { return 1.0 / (double)rank_pos(r[i]); }
 
 __host__ __device__ inline double pairwise_leaf(const int64_t* r, int64_t off, int64_t n) {
   if (n < 8) {
@@ -245,8 +254,8 @@ __global__ void __launch_bounds__(kMetricsThreads) metrics_reduce_kernel(
   unsigned long long sum = 0;
   for (int i = threadIdx.x; i < Q; i += blockDim.x) {
     const int64_t r = ranks[i];
-    sum += (unsigned long long)r;
-    for (int j = 0; j < nk; ++j) hits[j] += (r <= kv[j]) ? 1ull : 0ull;
+    sum += (unsigned long long)rank_pos(r);
+    for (int j = 0; j < nk; ++j) hits[j] += (r > 0 && r <= kv[j]) ? 1ull : 0ull;
   }
   atomicAdd(&s_sum, sum);
   for (int j = 0; j < nk; ++j) if (hits[j]) atomicAdd(&s_hits[j], hits[j]);

@@ -438,6 +438,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const int unit = (int)(blockIdx.x / CL);                      // persistent CTA, pair or quad
   const int units = (int)(gridDim.x / CL);
   const bool dbg = a.dbg != nullptr;
+  if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[blockIdx.x * 16 + 8] = (long long)t; }
   long long w_lo, w_hi;                      // this unit's range of the flattened (query block, tile) grid
   if (a.upq > 0) {
     const int j = unit % a.upq;
@@ -793,6 +794,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (dbg && warp == 2 && lane == 0) { a.dbg[blockIdx.x * 16 + 5] = w_tfull; a.dbg[blockIdx.x * 16 + 6] = t_fold; a.dbg[blockIdx.x * 16 + 7] = clock64() - t_begin; }
   }
 
+  if (dbg && threadIdx.x == 64) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[blockIdx.x * 16 + 9] = (long long)t; }
   // no CTA of a pair may leave (or free TMEM) while its peer can still signal its barriers
   ptx::tc_fence_before();
   if (PAIR) ptx::cluster_sync_all(); else __syncthreads();
@@ -944,6 +946,16 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
       fprintf(stderr, "[kemr mma dbg] cl=%d merged=%d vq=%d parts=%d n_tile=%d K=%d ctas=%d tiles/unit=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f (min %lld @cta %d, max %lld @cta %d; max cta: wait_full=%lld wait_tempty=%lld) | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f  cycles\n",
               pl.cl, pl.merged, pl.vq, pl.parts, pl.n_tile, pl.K, pl.ctas, (double)ma.W / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
               tmin, cmin, tmax, cmax, h[(size_t)cmax * 16 + 2], h[(size_t)cmax * 16 + 3], avg[5], avg[6], avg[7]);
+      {
+        long long s_min = 1ll << 62, s_max = 0, e_max = 0, e_min = 1ll << 62;
+        for (int c = 0; c < pl.ctas; ++c) {
+          const long long t0 = h[(size_t)c * 16 + 8], t1 = h[(size_t)c * 16 + 9];
+          if (t0) { s_min = std::min(s_min, t0); s_max = std::max(s_max, t0); }
+          if (t1) { e_max = std::max(e_max, t1); e_min = std::min(e_min, t1); }
+        }
+        fprintf(stderr, "[kemr mma dbg] globaltimer: first CTA start -> last CTA start %lld ns, -> first epilogue done %lld ns, -> last epilogue done %lld ns\n",
+                s_max - s_min, e_min - s_min, e_max - s_min);
+      }
       if (getenv("KEMR_MMA_DEBUG_TRACE")) {
         std::vector<long long> tr((size_t)8 * kTraceLen);
         cudaMemcpy(tr.data(), ma.dbg + kTraceBase, tr.size() * 8, cudaMemcpyDeviceToHost);

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(W * 32) select_kernel(SelectArgs a) {
 
 // ------------------------------------------------------------------ canonical pair scores
 __global__ void score_pairs_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ ga,
-                                   const uint16_t* __restrict__ gb, int D, double wa, double wb,
+                                   const uint16_t* __restrict__ gb, int64_t M, int D, double wa, double wb,
                                    const double* __restrict__ wqa, const double* __restrict__ wqb,
                                    double alpha, const int32_t* __restrict__ pq,
                                    const int64_t* __restrict__ prow, const double* __restrict__ pbonus,
@@ -299,6 +299,10 @@ __global__ void score_pairs_kernel(const uint16_t* __restrict__ q, const uint16_
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = wid; i < n; i += nw) {
     const uint16_t* qrow = q + (size_t)pq[i] * D;
+    if (prow[i] < 0 || prow[i] >= M) {                      // row outside the shard: no score (NaN ranks last)
+      if (lane == 0) out[i] = __longlong_as_double(0x7ff8000000000000ll);
+      continue;
+    }
     const size_t off = (size_t)prow[i] * D;
     const double sa = canon_dot_warp(qrow, ga + off, D, lane);
     const double sb = gb ? canon_dot_warp(qrow, gb + off, D, lane) : 0.0;

@@ -324,10 +324,10 @@ def score_pairs(q, gal_a, gal_b, pair_q: torch.Tensor, pair_row: torch.Tensor, w
     pb = None if pair_bonus is None else pair_bonus.to(device=q.device, dtype=torch.float64).contiguous()
     if _per_query(w_a) or _per_query(w_b):
         wa, wb = query_weights(w_a, w_b, q.shape[0], q.device)
-        _lib.check(_lib.load().kemr_score_pairs_gated(_ptr(q), _ptr(gal_a), _ptr(gal_b), q.shape[1], _ptr(wa), _ptr(wb),
+        _lib.check(_lib.load().kemr_score_pairs_gated(_ptr(q), _ptr(gal_a), _ptr(gal_b), gal_a.shape[0], q.shape[1], _ptr(wa), _ptr(wb),
                                                       float(alpha), _ptr(pq), _ptr(pr), _ptr(pb), n, _ptr(out), _stream()))
         return out
-    _lib.check(_lib.load().kemr_score_pairs(_ptr(q), _ptr(gal_a), _ptr(gal_b), q.shape[1], float(w_a),
+    _lib.check(_lib.load().kemr_score_pairs(_ptr(q), _ptr(gal_a), _ptr(gal_b), gal_a.shape[0], q.shape[1], float(w_a),
                                             float(w_b), float(alpha), _ptr(pq), _ptr(pr), _ptr(pb), n,
                                             _ptr(out), _stream()))
     return out

@@ -49,13 +49,16 @@ def compute_mrr_and_mean_rank(similarity_matrix) -> Dict[str, float]:
 
 
 def _rank_metrics(q, gal_a, gal_b, w_a, w_b, prefix, k_values, compute_recall, compute_mrr):
-    n = q.shape[0]
-    if n > gal_a.shape[0]:
-        raise AssertionError(f"query {n} rows > candidates {gal_a.shape[0]}: target of row i is column i")
+    n, m = q.shape[0], gal_a.shape[0]
     if not (compute_recall or compute_mrr):
         return {}
-    tidx = torch.arange(n, device=q.device, dtype=torch.int64)          # metrics.py:37
-    ranks = engine.rank_targets(q, gal_a, gal_b, tidx, w_a, w_b)
+    nv = min(n, m)
+    tidx = torch.arange(nv, device=q.device, dtype=torch.int64)         # metrics.py:37
+    ranks = engine.rank_targets(q[:nv].contiguous() if nv < n else q, gal_a, gal_b, tidx, w_a, w_b)
+    if nv < n:
+        # more queries than candidates: column i does not exist for i >= M, so the reference finds no match --
+        # never a recall hit, position argmax(all False) + 1 = 1 (metrics.py:41,68); rank 0 encodes exactly that
+        ranks = torch.cat([ranks, torch.zeros(n - nv, dtype=ranks.dtype, device=ranks.device)])
     return _metrics_from_ranks(ranks, k_values, compute_recall, compute_mrr, prefix)
 
 

@@ -33,9 +33,9 @@ class CLIPRetriever:
 
     def search(self, query, alpha: float = 0.5, top_k: Optional[int] = None) -> List[Dict]:
         k = min(top_k or self.top_k, self.index.M)
-        emb = self.encode_text(query) if isinstance(query, str) else query
         if isinstance(query, str) and self.encode_text is None:
             raise ValueError("no text encoder configured; pass a query embedding")
+        emb = self.encode_text(query) if isinstance(query, str) else query
         emb = np.asarray(emb, dtype=np.float32).reshape(1, -1)
         if self.index.target is not None:
             idx, score = self.index.search(emb, k=k, t2i_weight=alpha, t2t_weight=1.0 - alpha)
@@ -43,7 +43,9 @@ class CLIPRetriever:
             idx, score = self.index.search(emb, k=k)
         idx = idx[0].cpu().numpy()
         score = score[0].cpu().numpy()
-        return [{"uuid": self.index.uuids[int(j)], "score": float(s)} for j, s in zip(idx, score) if j >= 0]
+        # a shard of a row-partitioned gallery returns GLOBAL ids (idx_base + row) but holds its own uuid slice
+        base = self.index.idx_base
+        return [{"uuid": self.index.uuids[int(j) - base], "score": float(s)} for j, s in zip(idx, score) if j >= 0]
 
 
 class CLIPRetrieval:

@@ -340,6 +340,30 @@ def near_tie_audit(scores: np.ndarray, target_idx: Optional[np.ndarray], k: int,
     return topk_risky, rank_risky
 
 
+def ref_ranks_fp32(query, image, target=None, t2i_weight=0.5, t2t_weight=0.5, chunk: int = 512,
+                   tol: float = 4e-7) -> Tuple[np.ndarray, np.ndarray]:
+    """The reference's own per-query positions at full size, in query chunks (the (N, M) matrix of C1 is 740 MB):
+    fp32 BLAS similarity (metrics.py:102 / :145-148), full-row argsort of the negated row (metrics.py:34,62),
+    `argmax(order == i) + 1` (metrics.py:68).  Target of row i is column i (metrics.py:37).
+    Returns (pos int64 [N], near_tie bool [N]) -- near_tie[i] is the row-level form of `near_tie_audit`: another column
+    lies within `tol` of the target's fp32 score, i.e. the reference's own position for that row depends on the
+    summation order of its BLAS."""
+    q = np.asarray(query, dtype=np.float32)
+    n = q.shape[0]
+    pos = np.empty(n, dtype=np.int64)
+    near = np.zeros(n, dtype=bool)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        sim = ref_similarity(q[lo:hi], image) if target is None else \
+            ref_fused_similarity(q[lo:hi], target, image, t2i_weight, t2t_weight)
+        order = np.argsort(-sim, axis=1)                           # default kind, like the reference
+        want = np.arange(lo, hi)[:, None]
+        pos[lo:hi] = np.argmax(order == want, axis=1) + 1
+        t = sim[np.arange(hi - lo), np.arange(lo, hi)][:, None]
+        near[lo:hi] = (np.abs(sim - t) <= tol).sum(axis=1) > 1
+    return pos, near
+
+
 def ref_gate_linear(query: np.ndarray, weight: np.ndarray, bias: float) -> np.ndarray:
     """Reference `fusion_model.py:18-19` / `:190-191`: gate = sigmoid((q * w).sum(1) + b), fp32 (numpy restatement of
     the torch ops; the summation order of torch's reduction is not pinned, so compare with a tolerance)."""

@@ -275,6 +275,28 @@ def main():
         grouped[mode] = f64dict(res)
     out_json["grouped_text_models"] = grouped
 
+    # ------------------------------------------------------------------ generic fp32 embeddings (NOT bf16-representable)
+    # what a real CLIP encoder hands over: the engine rounds them to bf16 on upload, the reference scores them in fp32.
+    # Recorded: the reference's metrics, its top-5 lists and a slice of its scores, so that the deviation caused by
+    # the bf16 storage format is measured against the unmodified reference (tests/test_gpu_parity.py).
+    gr2 = np.random.default_rng(77)
+    Mg, Qg, Dg2 = 600, 200, 64
+    gi = synth.l2_normalize(gr2.standard_normal((Mg, Dg2), dtype=np.float32))
+    gt = synth.l2_normalize(gr2.standard_normal((Mg, Dg2), dtype=np.float32))
+    gq = synth.l2_normalize(0.45 * (gi[:Qg] + gt[:Qg]) / 2 + gr2.standard_normal((Qg, Dg2), dtype=np.float32) / np.sqrt(Dg2))
+    gsim = (0.5 * (gq @ gi.T)) + (0.5 * (gq @ gt.T))
+    np.savez_compressed(os.path.join(HERE, "generic_fp32.npz"), query=gq, image=gi, target=gt)
+    out_json["generic_fp32"] = {
+        "final_0.5_0.5": f64dict(quiet(rmetrics.compute_retrieval_metrics_final, gq, gt, gi)),
+        "T2I": f64dict(rmetrics.compute_retrieval_metrics(gq, gi)),
+        "top5": np.argsort(-gsim, axis=1, kind="stable")[:, :5].tolist(),
+        "top5_scores": np.take_along_axis(gsim, np.argsort(-gsim, axis=1, kind="stable")[:, :5], axis=1).astype(np.float64).tolist(),
+    }
+    # more queries than candidates (metrics.py:37 has no column i for i >= M): the reference's own answer
+    tall = (q @ img[:40].T).astype(np.float32)
+    out_json["tall_matrix"] = {"metrics": f64dict(rmetrics.compute_retrieval_metrics_fusion(tall)),
+                               "embeddings": f64dict(rmetrics.compute_retrieval_metrics(q, img[:40]))}
+
     import numpy
     out_json["provenance"] = {"numpy": numpy.__version__, "reference": REF,
                               "note": "outputs of the unmodified reference functions"}

@@ -21,7 +21,7 @@ def test_library_exports_header_symbols():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().kemr_abi_version() == 2
+    assert _lib.load().kemr_abi_version() == 3
 
 
 def test_no_cpu_fallback():
@@ -55,6 +55,23 @@ def test_metrics_reduce_host_matches_numpy():
         assert s == float(r.sum())
         assert rr / np.float64(n) * 100.0 == np.mean(1.0 / r) * 100.0       # metrics.py:70
         assert s / np.float64(n) == np.mean(r)                               # metrics.py:71
+
+
+def test_reduce_host_rank_zero_is_the_reference_no_match_case(golden, small_set):
+    """More queries than candidates: the reference has no column i for rows i >= M -- never a recall hit, position
+    argmax(all False) + 1 = 1 (metrics.py:41,68).  The reductions read rank 0 as exactly that: the host twin applied
+    to canonical ranks of the first M rows + zeros reproduces the unmodified reference's dict on the tall matrix."""
+    from oracle import oracle as O
+    q, img = small_set["query"], small_set["image"][:40]
+    can = O.canon_dot64(q[:40], img)
+    ranks = np.concatenate([O.canon_rank(can, np.arange(40)), np.zeros(len(q) - 40, np.int64)])
+    ks = [1, 5, 10, 20]
+    hits, s, rr = engine.metrics_reduce_host(ranks, ks)
+    n = np.float64(len(q))
+    got = {f"R@{k}": float(np.float64(h) / n * 100.0) for k, h in zip(ks, hits)}
+    got["MRR"] = float(np.float64(rr) / n * 100.0)
+    got["Mean_Rank"] = float(np.float64(s) / n)
+    assert got == golden["tall_matrix"]["metrics"] == golden["tall_matrix"]["embeddings"]
 
 
 def test_engine_list_fusion_matches_reference(golden):

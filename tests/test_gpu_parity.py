@@ -368,6 +368,65 @@ def test_retrieval_engine_end_to_end(small_set):
         assert fused == want
 
 
+def test_sharded_index_maps_global_ids_to_its_own_uuid_slice(small_set):
+    """A shard with idx_base > 0 returns GLOBAL row ids; CLIPRetriever.search must look them up in the shard's own
+    uuid slice."""
+    q, img, tgt = small_set["query"], small_set["image"], small_set["target"]
+    lo = 57
+    gi = index.GalleryIndex(img[lo:], tgt[lo:], uuids=small_set["uuids"][lo:], idx_base=lo)
+    r = retrieval.CLIPRetriever(gi, top_k=7)
+    can = O.canon_fused64(O.canon_dot64(q[:3], img[lo:]), O.canon_dot64(q[:3], tgt[lo:]), 0.5, 0.5)
+    widx, wscore = O.canon_topk(can, 7)
+    for i in range(3):
+        got = r.search(q[i], alpha=0.5)
+        assert [g["uuid"] for g in got] == [small_set["uuids"][lo + j] for j in widx[i]]
+        assert [g["score"] for g in got] == wscore[i].tolist()
+    with pytest.raises(ValueError):
+        r.search("a string query without an encoder")
+
+
+def test_more_queries_than_candidates_follows_the_reference(golden, small_set):
+    """Tall inputs (N > M): rows i >= M have no target column; the reference scores them as 'no recall hit,
+    position 1' (metrics.py:37,41,68).  Both the matrix-taking and the embedding-taking mirrors reproduce its dicts."""
+    q, img = small_set["query"], small_set["image"][:40]
+    tall = (q @ img.T).astype(np.float32)
+    same_dict(metrics.compute_retrieval_metrics_fusion(tall), golden["tall_matrix"]["metrics"])
+    same_dict(metrics.compute_retrieval_metrics(q, img), golden["tall_matrix"]["embeddings"])
+    rec = metrics.compute_recall_at_k(tall)
+    mrr = metrics.compute_mrr_and_mean_rank(tall)
+    same_dict({**rec, **mrr}, golden["tall_matrix"]["metrics"])
+    # rows outside the shard score NaN instead of reading out of bounds
+    s = engine.score_pairs(dev(q), dev(img), None, torch.tensor([0, 1], dtype=torch.int32).cuda(),
+                           torch.tensor([40, -1]).cuda())
+    assert bool(torch.isnan(s).all())
+
+
+def test_generic_fp32_embeddings_stay_within_the_stated_tolerance(golden):
+    """Embeddings that are NOT bf16-representable (what an encoder produces): the engine stores them as bf16
+    (round-to-nearest-even) while the reference scores the fp32 values.  Against the UNMODIFIED reference's outputs
+    (tests/golden/make_golden.py, 'generic_fp32'): scores of the reference's own top-5 rows within 1e-3 absolute
+    (north_star), Recall@K within 2 queries of 200, MRR within 1 point, Mean_Rank within 2 %."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "generic_fp32.npz"))
+    q, img, tgt = z["query"], z["image"], z["target"]
+    G = golden["generic_fp32"]
+    assert not np.array_equal(synth.round_to_bf16(q), q)                      # the inputs really are generic fp32
+    top5 = np.array(G["top5"])
+    n = len(q)
+    pq = torch.arange(n, dtype=torch.int32).repeat_interleave(5).cuda()
+    got = engine.score_pairs(dev(q), dev(img), dev(tgt), pq, torch.from_numpy(top5.ravel()).cuda(), 0.5, 0.5)
+    err = np.abs(got.cpu().numpy().reshape(n, 5) - np.array(G["top5_scores"]))
+    assert err.max() < 1e-3, err.max()
+    for name, ours in (("final_0.5_0.5", metrics.compute_retrieval_metrics_final(q, tgt, img)),
+                       ("T2I", metrics.compute_retrieval_metrics(q, img))):
+        ref = G[name]
+        for k in ("R@1", "R@5", "R@10", "R@20"):
+            assert abs(float(ours[k]) - ref[k]) <= 2 * 100.0 / n + 1e-9, (name, k, float(ours[k]), ref[k])
+        assert abs(float(ours["MRR"]) - ref["MRR"]) <= 1.0, (name, float(ours["MRR"]), ref["MRR"])
+        assert abs(float(ours["Mean_Rank"]) - ref["Mean_Rank"]) <= 0.02 * ref["Mean_Rank"] + 0.05
+    print("generic fp32: max |score - reference| =", err.max())
+
+
 # --------------------------------------------------------------------------- per-query gated fusion (§8f)
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("Q,M,D,k", [(130, 2000, 128, 10), (300, 3000, 768, 20), (7, 900, 64, 5)])
