@@ -257,6 +257,24 @@ def timed_steps(args, torch, dist, world, lib, step, flush, use_graph):
         scan_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(starts, mids))
         timed_steps.after_scan_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(mids, ends))
         timed_steps.scan_timing = "CUDA events around the scan kernel of every timed step"
+    # phases of the fused small-batch kernel (scan + selection in one launch), stamped in the kernel with %globaltimer
+    timed_steps.phases = None
+    stamps = torch.zeros(3, dtype=torch.int64, device="cuda")
+    lib.kemr_set_phase_stamps(C.c_void_p(stamps.data_ptr()))
+    ph = []
+    for _ in range(5):
+        flush.zero_()
+        stamps.zero_()
+        step()
+        torch.cuda.synchronize()
+        v = stamps.cpu().tolist()
+        if v[2] > v[1] > 0:
+            ph.append(((v[1] - v[0]) * 1e-6, (v[2] - v[1]) * 1e-6))
+    lib.kemr_set_phase_stamps(None)
+    if ph:
+        timed_steps.phases = {"scan_phase_ms": statistics.median(p[0] for p in ph),
+                              "select_phase_ms": statistics.median(p[1] for p in ph),
+                              "how": "%globaltimer stamps inside the fused kernel, 5 extra steps after the timed region"}
     else:
         timed_steps.scan_timing = "3 eager probe steps before the timed region (the timed steps are CUDA graphs)"
     return [a.elapsed_time(b) for a, b in zip(starts, ends)], scan_ms, graph is not None
@@ -505,6 +523,10 @@ def run_ours(args, cfg):
         roof["kernel_share_of_step"] = sum(scan_ms) / sum(step_ms)
         roof["after_scan_ms"] = timed_steps.after_scan_ms
         roof["kernel_timing"] = timed_steps.scan_timing
+        if timed_steps.phases:
+            roof["kernel"] = "fused streaming search (scan + selection in one launch: scan_stream_kernel)"
+            roof["phases"] = timed_steps.phases
+            roof["scan_phase_frac"] = bytes_ / (timed_steps.phases["scan_phase_ms"] * 1e-3) / 1e9 / pk["hbm"]
         qps = world * Q * args.steps / (total_ms * 1e-3)
         line = {"metric": "queries_per_sec_top%d" % k, "value": qps, "unit": "queries/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,

@@ -70,6 +70,10 @@ int kemr_device_info(int* sm_count, int* cc_major, int* cc_minor, int* has_tcgen
 /* measurement hook: record `cuda_event` (a cudaEvent_t, or NULL to disable) right after the scan
  * kernel inside the following kemr_scan_topk / kemr_rank_count calls of this thread. */
 int kemr_set_scan_done_event(void* cuda_event);
+/* measurement hook: a DEVICE int64[3] (or NULL to disable) that the fused small-batch search kernel stamps with
+ * %globaltimer nanoseconds on the following kemr_scan_topk calls of this thread: [0] first CTA start, [1] last CTA's
+ * scan arrival (= scan phase done), [2] selection done. */
+int kemr_set_phase_stamps(void* device_int64x3);
 
 /* ---- embedding boundary: fp32 rows -> optional x/||x|| -> bf16 (round-to-nearest-even).
  * Replaces: evaluator.py:120-135 (normalise) + the implicit fp32 storage of the reference. */

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkemr.so")
+# KEMR_LIB selects another build of the same library (the debug build with the per-role cycle counters, tools/)
+LIB_PATH = os.environ.get("KEMR_LIB") or os.path.join(_HERE, "libkemr.so")
 
 KEMR_OK = 0
 PATH_AUTO, PATH_WARP, PATH_MMA = 0, 1, 2
@@ -21,7 +22,7 @@ EXPORTS = (
     "kemr_index_search_host", "kemr_set_scan_done_event", "kemr_scan_plan",
     "kemr_scan_topk_gated", "kemr_rank_count_gated", "kemr_score_pairs_gated", "kemr_gate_linear",
     "kemr_hits_workspace_bytes", "kemr_hits_build_csr", "kemr_idmap_create", "kemr_idmap_destroy", "kemr_idmap_lookup",
-    "kemr_store_write", "kemr_store_info", "kemr_store_load", "kemr_debug_mma_plan",
+    "kemr_store_write", "kemr_store_info", "kemr_store_load", "kemr_debug_mma_plan", "kemr_set_phase_stamps",
 )
 
 
@@ -75,6 +76,7 @@ def _declare(lib):
     lib.kemr_index_create.argtypes = [p, p, i64, i32, i32, i32, C.POINTER(p)]
     lib.kemr_index_destroy.argtypes = [p]
     lib.kemr_set_scan_done_event.argtypes = [p]
+    lib.kemr_set_phase_stamps.argtypes = [p]
     lib.kemr_index_search_host.argtypes = [p, p, i32, i32, f64, f64, f64, p, p, p, i32, p, p, p]
     for name in EXPORTS:
         fn = getattr(lib, name)

@@ -17,6 +17,7 @@
 #include "select.cuh"
 #include "matrix_ops.cuh"
 #include "scan_mma.cuh"
+#include "scan_stream.cuh"
 #include "store.cuh"
 
 #include <fcntl.h>
@@ -24,6 +25,7 @@
 #include <sys/stat.h>
 #include <string_view>
 #include <unordered_map>
+#include <mutex>
 
 using namespace kemr;
 
@@ -61,7 +63,37 @@ extern "C" int kemr_set_scan_done_event(void* cuda_event) {
   g_scan_done_event = reinterpret_cast<cudaEvent_t>(cuda_event);
   return KEMR_OK;
 }
+// measurement hook: device int64[3] that the fused small-batch kernel stamps with %globaltimer (first CTA start,
+// last scan arrival, selection done) on the following kemr_scan_topk calls of this thread
+static thread_local long long* g_phase_stamps = nullptr;
+extern "C" int kemr_set_phase_stamps(void* device_int64x3) {
+  g_phase_stamps = reinterpret_cast<long long*>(device_int64x3);
+  return KEMR_OK;
+}
 extern "C" int kemr_abi_version(void) { return KEMR_ABI_VERSION; }
+
+// Arrival counters of the fused small-batch kernel ("last CTA runs the selection"): a per-device pool, zeroed once;
+// every launch takes the next slice and its last CTA resets what it used, so launches on different streams never
+// share a counter (until 64 Ki groups later, long after the earlier launch has drained).
+static int stream_counters(int groups, unsigned int** out) {
+  constexpr int kPool = 1 << 16;
+  struct Pool { unsigned int* p = nullptr; int dev = -1; unsigned int cursor = 0; };
+  static Pool pools[64];
+  static std::mutex mu;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || groups > kPool) return fail(KEMR_ERR_UNSUPPORTED, "stream_counters: device %d / %d groups", dev, groups);
+  std::lock_guard<std::mutex> lock(mu);
+  Pool& pl = pools[dev];
+  if (!pl.p) {
+    CUDA_TRY(cudaMalloc(&pl.p, (size_t)kPool * 4));
+    CUDA_TRY(cudaMemset(pl.p, 0, (size_t)kPool * 4));
+  }
+  if (pl.cursor + (unsigned)groups > (unsigned)kPool) pl.cursor = 0;
+  *out = pl.p + pl.cursor;
+  pl.cursor += (unsigned)groups;
+  return KEMR_OK;
+}
 
 struct DevInfo { int ok = 0, dev = -1, sms = 0, major = 0, minor = 0, quads = 0; };
 static int dev_info(DevInfo* out) {
@@ -168,8 +200,16 @@ static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, 
     pl->Kp = pl->mma.K;
     return KEMR_OK;
   }
-  pl->QB = Q == 1 ? 1 : 2;
   pl->CH = (D + 255) / 256;
+  if (mode == kModeTopk) {
+    // fused streaming search (scan_stream.cuh): one persistent CTA per SM and query group of 1, 2 or 4 queries
+    pl->QB = Q == 1 ? 1 : (Q == 2 ? 2 : 4);
+    pl->groups = (Q + pl->QB - 1) / pl->QB;
+    pl->P = (int)std::min<int64_t>(dv.sms > 0 ? dv.sms : 1, std::max<int64_t>(1, (M + 31) / 32));
+    pl->Kp = K;
+    return KEMR_OK;
+  }
+  pl->QB = Q == 1 ? 1 : 2;
   pl->groups = (Q + pl->QB - 1) / pl->QB;
   int want = 2 * dv.sms;
   int P = std::max(1, (want + pl->groups - 1) / pl->groups);
@@ -215,7 +255,7 @@ static void launch_warp(const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t 
 }
 static int launch_warp_scan(const ScanArgs& a, const ScanPlan& pl, cudaStream_t st) {
   dim3 grid(pl.P, pl.groups);
-  const size_t smem = a.mode == kModeTopk ? (size_t)kWarpScanWarps * pl.QB * a.K * 8 : 0;
+  const size_t smem = 0;
   if (pl.groups > 65535) return fail(KEMR_ERR_UNSUPPORTED, "warp path: too many query groups (%d)", pl.groups);
 #define KEMR_CASE(qb, ch) if (pl.QB == qb && pl.CH == ch) { launch_warp<qb, ch>(a, grid, smem, st); }
   KEMR_CASE(1, 1) KEMR_CASE(1, 2) KEMR_CASE(1, 3) KEMR_CASE(1, 4)
@@ -272,13 +312,6 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
   a.q = q; a.Q = Q; a.gal[0] = gal_a; a.gal[1] = gal_b; a.G = G; a.M = M; a.D = D;
   a.w[0] = (float)w_a; a.w[1] = (float)w_b; a.wq[0] = wq32[0]; a.wq[1] = wq32[1];
   a.mode = kModeTopk; a.K = pl.Kp; a.part_keys = part_keys;
-  if (pl.path == KEMR_PATH_MMA) {
-    if (!pl.mma.all_slots) CUDA_TRY(cudaMemsetAsync(part_keys, 0, need, st));   // unwritten slots must read as empty
-    if ((rc = mma_launch(a, pl.mma, st))) return fail(KEMR_ERR_CUDA, "tcgen05 scan launch failed: %s", mma_last_error());
-  } else {
-    if ((rc = launch_warp_scan(a, pl, st))) return rc;
-  }
-  if (g_scan_done_event) CUDA_TRY(cudaEventRecord(g_scan_done_event, st));
 
   SelectArgs s{};
   s.part_keys = part_keys; s.P = pl.P; s.Q = Qrows; s.K = k_sel; s.Kp = pl.Kp;
@@ -292,8 +325,44 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
   if (pl.P > kMaxParts) return fail(KEMR_ERR_UNSUPPORTED, "too many part lists per query (%d)", pl.P);
   const size_t smem = select_smem_bytes(pl.P, pl.Kp, k_sel, s.max_cand);
   if (smem > 200 * 1024) return fail(KEMR_ERR_UNSUPPORTED, "select kernel needs %zu bytes of shared memory", smem);
-  // one CTA per query: 4 warps for the common small case, 8 when there are many candidates to re-score
   const int np = (D + 255) / 256;
+
+  if (pl.path != KEMR_PATH_MMA) {
+    // small batches: scan + selection in ONE launch (scan_stream.cuh)
+    StreamArgs sa{};
+    sa.s = a; sa.sel = s;
+    sa.stage_bytes = (unsigned)((size_t)G * kStreamConsumers * D * 2);
+    const size_t tail = stream_smem_bytes(0, 0, pl.QB, 0);
+    sa.stages = (int)std::min<size_t>(kStreamMaxStages, ((size_t)kSmemBudget - 1024 - tail) / sa.stage_bytes);
+    if (sa.stages < 2) return fail(KEMR_ERR_UNSUPPORTED, "stream kernel: a stage of %u bytes does not fit twice", sa.stage_bytes);
+    const size_t dyn = stream_smem_bytes(sa.stages, sa.stage_bytes, pl.QB, smem);
+    sa.tail_off = (unsigned)stream_tail_off(sa.stages, sa.stage_bytes, smem);
+    if (dyn > (size_t)kSmemBudget) return fail(KEMR_ERR_UNSUPPORTED, "stream kernel needs %zu bytes of shared memory", dyn);
+    if (pl.groups > 65535) return fail(KEMR_ERR_UNSUPPORTED, "warp path: too many query groups (%d)", pl.groups);
+    if ((rc = stream_counters(pl.groups, &sa.done))) return rc;
+    sa.stamps = g_phase_stamps;
+    if (sa.stamps) CUDA_TRY(cudaMemsetAsync(sa.stamps, 0x7f, 8, st));       // "first start" is an atomicMin
+    dim3 grid(pl.P, pl.groups);
+#define KEMR_STREAM(QBV, CHV)                                                                                     \
+  do {                                                                                                            \
+    CUDA_TRY(cudaFuncSetAttribute(scan_stream_kernel<QBV, CHV, CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+    scan_stream_kernel<QBV, CHV, CHV><<<grid, kStreamThreads, dyn, st>>>(sa);                                     \
+  } while (0)
+#define KEMR_STREAM_CH(QBV) switch (np) { case 1: KEMR_STREAM(QBV, 1); break; case 2: KEMR_STREAM(QBV, 2); break; \
+                                          case 3: KEMR_STREAM(QBV, 3); break; default: KEMR_STREAM(QBV, 4); break; }
+    if (pl.QB == 1) { KEMR_STREAM_CH(1) } else if (pl.QB == 2) { KEMR_STREAM_CH(2) } else { KEMR_STREAM_CH(4) }
+#undef KEMR_STREAM_CH
+#undef KEMR_STREAM
+    LAUNCH_CHECK("scan_stream_kernel");
+    if (g_scan_done_event) CUDA_TRY(cudaEventRecord(g_scan_done_event, st));
+    return KEMR_OK;
+  }
+
+  if (!pl.mma.all_slots) CUDA_TRY(cudaMemsetAsync(part_keys, 0, need, st));   // unwritten slots must read as empty
+  if ((rc = mma_launch(a, pl.mma, st))) return fail(KEMR_ERR_CUDA, "tcgen05 scan launch failed: %s", mma_last_error());
+  if (g_scan_done_event) CUDA_TRY(cudaEventRecord(g_scan_done_event, st));
+
+  // one CTA per query: 4 warps for the common small case, 8 when there are many candidates to re-score
   const bool small = s.max_cand <= kSelSmallCand && Q > 64;   // tiny batches leave the GPU empty: 8 warps per query
 #define KEMR_SEL(NPV, WV)                                                                                         \
   do {                                                                                                            \
@@ -907,7 +976,7 @@ extern "C" int kemr_store_load(const char* path, int64_t row_lo, int64_t row_hi,
 
 // ----------------------------------------------------------------------------- plan introspection (no device needed)
 // The tcgen05 plan for a shape on a hypothetical device with `sms` SMs and room for `quads` clusters of four:
-// out[0..15] = parts, q_pad, n_tile, n_qb, n_t, ctas, stages, kc, K, cl, upq, vq, all_slots, two, merged, q_blk;
+// out[0..15] = parts, q_pad, n_tile, n_qb, n_t, ctas, stages, kc, K, cl, gran, vq, all_slots, two, merged, q_blk;
 // returns KEMR_ERR_UNSUPPORTED when the shape cannot be planned.  Lets the host-side scheduling logic (unit ranges,
 // part slots) be property-tested on a CPU (tests/test_plan_cpu.py).
 extern "C" int kemr_debug_mma_plan(int Q, int64_t M, int D, int galleries, int k_sel, int equal_weights, int sms, int quads,
@@ -917,7 +986,7 @@ extern "C" int kemr_debug_mma_plan(int Q, int64_t M, int D, int galleries, int k
   MmaPlan p;
   if (mma_make_plan(Q, M, D, galleries, k_sel, kModeTopk, sms, quads, equal_weights != 0, &p))
     return fail(KEMR_ERR_UNSUPPORTED, "debug_mma_plan: shape cannot be planned");
-  const int64_t v[16] = {p.parts, p.q_pad, p.n_tile, p.n_qb, p.n_t, p.ctas, p.stages, p.kc, p.K, p.cl, p.upq, p.vq,
+  const int64_t v[16] = {p.parts, p.q_pad, p.n_tile, p.n_qb, p.n_t, p.ctas, p.stages, p.kc, p.K, p.cl, p.gran, p.vq,
                          p.all_slots, p.two, p.merged, p.q_blk};
   for (int i = 0; i < 16; ++i) out16[i] = v[i];
   return KEMR_OK;

@@ -15,9 +15,13 @@
 // so every scheduler hosts two epilogue warps and a query's candidates come as two lists per CTA.
 // One pipeline stage holds the query chunk ONCE plus the matching chunk of every gallery (the
 // A operand is shared by the T2I and T2T MMAs).
-// Work: the (query block, gallery tile) grid is flattened and cut into equal contiguous ranges, one
-// per persistent CTA (<= #SMs); a CTA emits one K-entry candidate list per query for every query
-// block its range touches ("part slot"), merged later by select.cuh.
+// Work: the rows of all query blocks are laid end to end (position = block * M + row) and cut into equal contiguous
+// ROW ranges, one per persistent CTA / pair / quad (<= #SMs), snapped to 32 rows inside a block.  A unit walks its
+// range in tiles of n_tile rows; the tile at the end of a range is PARTIAL: its MMA is issued with N = the rows left
+// (rounded up to 32) and its rows arrive as 16-row TMA boxes, so every unit does the same tensor work to within 32
+// rows whatever M / n_tile leaves over (C2: 9.08 tile-equivalents per pair instead of 9 or 10).  A unit emits one
+// K-entry candidate list per query and column half for every query block its range touches ("part slot"), merged
+// later by select.cuh.
 //
 // Epilogue per element: 1-2 FFMA for the fusion weights and one compare against the thread's running
 // threshold.  Survivors are appended to a small per-thread buffer in shared memory; when any lane's
@@ -79,7 +83,7 @@ struct MmaPlan {
   int K = 0;              // list length (8, 16, 24, 32)
   int pair = 0;           // 1: CTA pairs (cta_group::2), 256 queries per block
   int cl = 1;             // CTAs per cluster: 1, 2 (one pair) or 4 (two pairs on adjacent query blocks sharing the gallery tile by TMA multicast)
-  int upq = 0;            // units (CTAs or pairs) per query block; 0 = flattened (block, tile) ranges
+  int gran = 32;          // unit boundaries are multiples of this many rows inside a query block (n_tile: no partial tiles)
   int vq = 1;             // virtual parts per query block: lists are flushed and restarted at these boundaries
   int all_slots = 0;      // 1: every part slot of every query row is written (no memset needed)
   int two = 0;            // 1: two accumulators (T2I, T2T) with their own weights
@@ -94,6 +98,23 @@ inline bool mma_supported(int D, int K) { return D % 8 == 0 && D >= 8 && D <= kM
 
 static thread_local char g_mma_error[256] = "";
 inline const char* mma_last_error() { return g_mma_error; }
+
+// First position (block * M + row) of unit u when `rtot` = n_qb * M rows of work are cut into `units` ranges: the
+// even split, snapped down to a multiple of `gran` rows inside its query block.  unit_begin(units) == rtot.
+__host__ __device__ inline long long unit_begin(long long rtot, int units, long long M, int gran, int u) {
+  const long long x = rtot * u / units;
+  const long long qb = x / M, r = x - qb * M;
+  return qb * M + r - r % gran;
+}
+// the unit whose range holds position `pos` (largest u with unit_begin(u) <= pos; ranges may be empty)
+__host__ __device__ inline int unit_of(long long rtot, int units, long long M, int gran, long long pos) {
+  int lo = 0, hi = units - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (unit_begin(rtot, units, M, gran, mid) <= pos) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
 
 constexpr int kPlanMaxParts = 304;     // candidate lists per query any plan may use (workspace bound: 2*148 + 8)
 
@@ -130,27 +151,23 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
   const int64_t nt = (M + p->n_tile - 1) / p->n_tile;
   if (nt > (1ll << 30)) return 1;
   p->n_t = (int)nt;
-  const int64_t W = (int64_t)p->n_qb * p->n_t;
   const int units = quad ? quads : (p->pair ? sms / 2 : sms);       // persistent CTAs, pairs or quads
-  int nu, parts = 1;
-  const int upq_try = (int)std::min<int64_t>(units / std::max(1, p->n_qb), nt);
-  if (upq_try >= 1 && ((int64_t)upq_try * p->n_qb * 10 >= (int64_t)std::min<int64_t>(units, W) * 9)) {
-    // Every unit stays inside ONE query block (its lists and thresholds are never restarted): the
-    // units are dealt evenly to the blocks and a block's tiles evenly to its units.  A few units may
-    // idle (74 pairs over 4 blocks leave 2); taken only when at least 90 % of the units get work.
-    p->upq = upq_try;
-    nu = p->upq * p->n_qb;
-    parts = p->upq;
-  } else {
-    // more query blocks than units: flattened (block, tile) grid cut into equal contiguous ranges
-    p->upq = 0;
-    nu = (int)std::min<int64_t>(units, W);
-    for (int qb = 0; qb < p->n_qb; ++qb) {
-      const int64_t w0 = (int64_t)qb * p->n_t, w1 = w0 + p->n_t - 1;
-      const int c0 = (int)(((w0 + 1) * nu - 1) / W), c1 = (int)(((w1 + 1) * nu - 1) / W);
-      parts = std::max(parts, c1 - c0 + 1);
-    }
+  // Row ranges: position = block * M + row; unit u owns [unit_begin(u), unit_begin(u + 1)).  Partial tiles (MMA with a
+  // smaller N, 16-row TMA boxes) exist for the single-accumulator kernels of one CTA or one pair; quads and the
+  // two-accumulator kernels keep tile-aligned boundaries.
+  static const bool no_partial = getenv("KEMR_MMA_NO_PARTIAL") != nullptr;     // experiments: tile-aligned boundaries everywhere
+  p->gran = (quad || p->two || no_partial) ? p->n_tile : 32;
+  const int64_t rtot = (int64_t)p->n_qb * M;
+  const int nu = (int)std::min<int64_t>(units, std::max<int64_t>(1, rtot / p->n_tile));   // at least a tile's worth of rows per unit
+  int parts = 1;
+  bool same = true;
+  for (int qb = 0; qb < p->n_qb; ++qb) {
+    const int c0 = unit_of(rtot, nu, M, p->gran, (int64_t)qb * M), c1 = unit_of(rtot, nu, M, p->gran, (int64_t)(qb + 1) * M - 1);
+    if (qb && c1 - c0 + 1 != parts) same = false;
+    parts = std::max(parts, c1 - c0 + 1);
   }
+  for (int u = 0; u < nu; ++u)
+    if (unit_begin(rtot, nu, M, p->gran, u) == unit_begin(rtot, nu, M, p->gran, u + 1)) same = false;   // an empty unit leaves a hole
   p->ctas = p->cl * nu;
   p->a_rows = (p->pair || Q >= kBlockM) ? kBlockM : (Q + 7) / 8 * 8;
   // Candidate lists.  A query's rows are cut into segments (unit boundaries, plus `vq` virtual
@@ -192,7 +209,7 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
   p->K = Ksel;
   p->vq = vq;
   p->parts = 2 * (vq + span - 1);
-  p->all_slots = (vq == 1 && p->upq > 0) ? 1 : 0;
+  p->all_slots = (vq == 1 && same) ? 1 : 0;     // every block is covered by the same number of non-empty units
   static const bool no_ds = getenv("KEMR_MMA_NO_DS") != nullptr;
   p->ds = (p->merged && p->pair && !no_ds) ? 1 : 0;
   const size_t stage = (size_t)kBlockM * 128 + (p->pair ? (size_t)128 * 128 * (p->ds ? 2 : 1) : (size_t)256 * 128);
@@ -343,11 +360,10 @@ struct MmaArgs {
   int n_tile;       // gallery rows per tile (128 with two accumulators, else 256)
   int merged;       // both galleries accumulate into ONE accumulator (equal weights): 2*kc K chunks
   int ds;           // merged, CTA pairs: a stage holds the query chunk ONCE plus the matching chunk of BOTH galleries (8 MMAs)
-  int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, upq, vq;
-  long long W;
-  long long* dbg;   // optional [ctas][16] cycle counters + stage trace (KEMR_MMA_DEBUG=1)
+  int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, gran, vq;
+  long long rtot;   // n_qb * M: rows of work, cut into one contiguous range per unit (unit_begin)
+  long long* dbg;   // optional [ctas][16] cycle counters + stage trace (debug build, KEMR_MMA_DEBUG=1)
   int epi_variant;  // 1 = per-lane predicated appends without warp votes (short lists), 2 = the same on RAW accumulators; KEMR_MMA_EPI overrides
-  int dbg_skip;     // timing experiments only (results invalid): after a unit's first tile skip the TMA loads of bit0 = queries, bit1 = gallery
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -411,7 +427,8 @@ __device__ __forceinline__ void ld_shared_v2(uint32_t addr, float& s, uint32_t& 
 template <int K, int CL, bool TWO>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g0,
-                const __grid_constant__ CUtensorMap map_g1, MmaArgs a) {
+                const __grid_constant__ CUtensorMap map_g1, const __grid_constant__ CUtensorMap map_s0,
+                const __grid_constant__ CUtensorMap map_s1, MmaArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_mma_raw[];
   // identical shared-memory layout in both CTAs of a pair (the MMA addresses the peer by offset)
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_mma_raw + 1023) & ~(uintptr_t)1023);
@@ -437,15 +454,30 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const uint32_t lead = crank & ~1u;                            // cluster rank of this pair's leader
   const int unit = (int)(blockIdx.x / CL);                      // persistent CTA, pair or quad
   const int units = (int)(gridDim.x / CL);
+#ifdef KEMR_DEBUG
   const bool dbg = a.dbg != nullptr;
   if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[blockIdx.x * 16 + 8] = (long long)t; }
-  long long w_lo, w_hi;                      // this unit's range of the flattened (query block, tile) grid
-  if (a.upq > 0) {
-    const int j = unit % a.upq;
-    const long long base = (long long)(unit / a.upq) * a.n_t;
-    w_lo = base + (long long)a.n_t * j / a.upq; w_hi = base + (long long)a.n_t * (j + 1) / a.upq;
-  } else {
-    w_lo = a.W * unit / units; w_hi = a.W * (unit + 1) / units;
+#else
+  constexpr bool dbg = false;          // role counters and the stage trace exist in the debug build only
+#endif
+  // this unit's range of the row work (position = query block * M + row)
+  const long long p_lo = unit_begin(a.rtot, units, a.s.M, a.gran, unit);
+  const long long p_hi = unit_begin(a.rtot, units, a.s.M, a.gran, unit + 1);
+  // partial tiles: the single-accumulator kernels of one CTA / one pair, when the plan cut the ranges finer than tiles
+  const bool partial_ok = !TWO && !QUAD && a.gran < n_tile;
+  // Walk of a range, identical in the three roles: segments (one per query block touched) of tiles; the last tile of
+  // a segment may be partial.  KEMR_FOR_TILES(body) runs `body` with qb, row0 (first row of the tile inside the
+  // block) and ncols (rows of the tile that belong to this unit) in scope.
+#define KEMR_FOR_TILES(...)                                                                   \
+  for (long long p__ = p_lo; p__ < p_hi;) {                                                   \
+    const int qb = (int)(p__ / a.s.M);                                                        \
+    const long long blk0__ = (long long)qb * a.s.M;                                           \
+    const long long rend__ = (p_hi < blk0__ + a.s.M ? p_hi : blk0__ + a.s.M) - blk0__;        \
+    for (long long row0 = p__ - blk0__; row0 < rend__; row0 += n_tile) {                      \
+      const int ncols = (int)(rend__ - row0 < (long long)n_tile ? rend__ - row0 : (long long)n_tile); \
+      __VA_ARGS__                                                                             \
+    }                                                                                         \
+    p__ = blk0__ + rend__;                                                                    \
   }
 
   if (threadIdx.x == 0) {
@@ -471,9 +503,14 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       int stage = 0; uint32_t phase = 0;
       long long w_empty = 0; const long long t_begin = dbg ? clock64() : 0;
       int tr = 0;
-      const uint32_t tx = PAIR ? 2u * stage_bytes : (uint32_t)a.a_rows * 128u + 256u * 128u;
-      for (long long w = w_lo; w < w_hi; ++w) {
-        const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
+      KEMR_FOR_TILES({
+        // rows of the gallery chunk this CTA stages: a full tile, or (single accumulator) the rows left, to 32
+        const int nmma = partial_ok ? min(256, (ncols + 31) & ~31) : 256;
+        const int nb = PAIR ? (TWO ? 128 : nmma >> 1) : (TWO ? 128 : nmma);
+        const bool whole = QUAD || nb == (int)b_box;
+        const uint32_t g_bytes = (uint32_t)nb * 128u * ((TWO && !PAIR) || ds ? 2u : 1u);     // gallery bytes per CTA and stage
+        const uint32_t tx = PAIR ? 2u * (a_bytes + g_bytes) : (uint32_t)a.a_rows * 128u + g_bytes;
+        const int brow = (int)row0 + ((PAIR && !TWO) ? (int)rank * nb : 0);
         for (int kcc = 0; kcc < a.kc_total; ++kcc) {
           const int g = kcc >= a.kc ? 1 : 0;              // merged mode: second gallery's chunks follow the first's
           const int kx = (kcc - g * a.kc) * kBlockK;
@@ -481,54 +518,45 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           if (dbg && blockIdx.x < 2 && lane == 0 && tr < kTraceLen) a.dbg[kTraceBase + (blockIdx.x * 4 + 0) * kTraceLen + tr] = clock64();
           unsigned char* sa = smem + (size_t)stage * stage_bytes;
           if (ptx::elect_one()) {
-          if (a.dbg_skip && w > w_lo) {
-            // ingress experiment: the stage keeps whatever it held; only the selected operand is fetched
-            const bool la = !(a.dbg_skip & 1), lb = !(a.dbg_skip & 2);
-            const uint32_t lbar = PAIR ? ptx::map_to_cta(ptx::smem_u32(&full_bar[stage]), lead) : 0u;
-            const uint32_t txs = (la ? a_bytes : 0u) + (lb ? (PAIR ? (ds ? 2u * b_bytes : b_bytes) : 256u * 128u) : 0u);
-            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], PAIR ? 2u * txs : txs);
             if (PAIR) {
-              if (la) ptx::tma_load_2d_pair(sa, &map_q, lbar, kx, qb * a.q_blk + (int)crank * kBlockM);
-              if (lb) ptx::tma_load_2d_pair(sa + a_bytes, (!ds && g) ? &map_g1 : &map_g0, lbar, kx, t * n_tile + (int)rank * 128);
-              if (lb && ds) ptx::tma_load_2d_pair(sa + a_bytes + b_bytes, &map_g1, lbar, kx, t * n_tile + (int)rank * 128);
+              // this CTA's 128 query rows + its half of the gallery chunk; bytes land on the leader's barrier
+              const uint32_t lbar = ptx::map_to_cta(ptx::smem_u32(&full_bar[stage]), lead);
+              if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], tx);
+              ptx::tma_load_2d_pair(sa, &map_q, lbar, kx, qb * a.q_blk + (int)crank * kBlockM);
+              for (int gi = 0; gi < (ds ? 2 : 1); ++gi) {
+                const bool second = TWO ? rank != 0 : (ds ? gi : g) != 0;
+                unsigned char* sb = sa + a_bytes + (uint32_t)gi * b_bytes;
+                if (QUAD) {
+                  // this CTA's quarter of the chunk (64 rows), multicast to the CTA of the other pair holding the same half
+                  ptx::tma_load_2d_pair_mc(sb + pc * (64u * 128u), second ? &map_g1 : &map_g0, lbar, kx, brow + (int)pc * 64,
+                                           (uint16_t)((1u << rank) | (4u << rank)));
+                } else if (whole) {
+                  ptx::tma_load_2d_pair(sb, second ? &map_g1 : &map_g0, lbar, kx, brow);
+                } else {
+                  for (int r16 = 0; r16 < nb; r16 += 16)      // partial tile: 16-row boxes, same swizzled layout
+                    ptx::tma_load_2d_pair(sb + (uint32_t)r16 * 128u, second ? &map_s1 : &map_s0, lbar, kx, brow + r16);
+                }
+              }
             } else {
-              if (la) ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kx, qb * kBlockM);
-              if (lb) ptx::tma_load_2d(sa + a_bytes, g ? &map_g1 : &map_g0, &full_bar[stage], kx, t * n_tile);
-            }
-          } else if (PAIR) {
-            // this CTA's 128 query rows + its half of the gallery chunk; bytes land on the leader's barrier
-            const uint32_t lbar = ptx::map_to_cta(ptx::smem_u32(&full_bar[stage]), lead);
-            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], tx);
-            ptx::tma_load_2d_pair(sa, &map_q, lbar, kx, qb * a.q_blk + (int)crank * kBlockM);
-            const int brow = t * n_tile + (TWO ? 0 : (int)rank * 128);
-            for (int gi = 0; gi < (ds ? 2 : 1); ++gi) {
-              const CUtensorMap* mb = TWO ? (rank ? &map_g1 : &map_g0) : ((ds ? gi : g) ? &map_g1 : &map_g0);
-              unsigned char* sb = sa + a_bytes + (uint32_t)gi * b_bytes;
-              if (QUAD) {
-                // this CTA's quarter of the chunk (64 rows), multicast to the CTA of the other pair holding the same half
-                ptx::tma_load_2d_pair_mc(sb + pc * (64u * 128u), mb, lbar, kx, brow + (int)pc * 64,
-                                         (uint16_t)((1u << rank) | (4u << rank)));
+              ptx::mbar_expect_tx(&full_bar[stage], tx);
+              ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kx, qb * kBlockM);
+              if (TWO) {
+                ptx::tma_load_2d(sa + a_bytes, &map_g0, &full_bar[stage], kx, brow);
+                ptx::tma_load_2d(sa + a_bytes + b_bytes, &map_g1, &full_bar[stage], kx, brow);
+              } else if (whole) {
+                ptx::tma_load_2d(sa + a_bytes, g ? &map_g1 : &map_g0, &full_bar[stage], kx, brow);
               } else {
-                ptx::tma_load_2d_pair(sb, mb, lbar, kx, brow);
+                for (int r16 = 0; r16 < nb; r16 += 16)
+                  ptx::tma_load_2d(sa + a_bytes + (uint32_t)r16 * 128u, g ? &map_s1 : &map_s0, &full_bar[stage], kx, brow + r16);
               }
             }
-          } else {
-            ptx::mbar_expect_tx(&full_bar[stage], tx);
-            ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kx, qb * kBlockM);
-            if (TWO) {
-              ptx::tma_load_2d(sa + a_bytes, &map_g0, &full_bar[stage], kx, t * n_tile);
-              ptx::tma_load_2d(sa + a_bytes + b_bytes, &map_g1, &full_bar[stage], kx, t * n_tile);
-            } else {
-              ptx::tma_load_2d(sa + a_bytes, g ? &map_g1 : &map_g0, &full_bar[stage], kx, t * n_tile);
-            }
-          }
           }
           __syncwarp();
           if (dbg && blockIdx.x < 2 && lane == 0 && tr < kTraceLen) a.dbg[kTraceBase + (blockIdx.x * 4 + 1) * kTraceLen + tr] = clock64();
           if (dbg && blockIdx.x < 2 && tr < kTraceLen) ++tr;
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
-      }
+      })
       if (dbg && lane == 0) { a.dbg[blockIdx.x * 16 + 0] = w_empty; a.dbg[blockIdx.x * 16 + 1] = clock64() - t_begin; }
     }
   } else if (warp == 1) {
@@ -542,16 +570,17 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       // The gallery chunk(s) of a stage form ONE K-major tile of 256 rows (T2I rows then T2T rows, or
       // 256 rows of one gallery; split across the two CTAs in pair mode): a single MMA with N = 256
       // fills the whole accumulator buffer and reads the query chunk once.
-      const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, 256);
       const uint64_t adesc0 = umma_desc_sw128(ptx::smem_u32(smem));
       const uint64_t bdesc0 = umma_desc_sw128(ptx::smem_u32(smem) + a_bytes);
       const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);          // descriptor start-address units (16 B)
       long long it = 0;
       long long w_full = 0, w_tempty = 0; const long long t_begin = dbg ? clock64() : 0;
       int tr = 0;
-      for (long long w = w_lo; w < w_hi; ++w, ++it) {
+      KEMR_FOR_TILES({
         const int buf = (int)(it & 1);
         const uint32_t bphase = (uint32_t)((it >> 1) & 1);
+        // a partial tile (end of this unit's range) fills only the accumulator columns of its rows
+        const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, partial_ok ? min(256, (ncols + 31) & ~31) : 256);
         mbar_wait_dbg(&tempty_bar[buf], bphase ^ 1, dbg, w_tempty);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
@@ -587,7 +616,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           if (PAIR) ptx::mma_commit_pair(&tfull_bar[buf], (uint16_t)(3u << lead)); else ptx::mma_commit(&tfull_bar[buf]);
         }
         __syncwarp();
-      }
+        ++it;
+      })
       if (dbg && lane == 0) { a.dbg[blockIdx.x * 16 + 2] = w_full; a.dbg[blockIdx.x * 16 + 3] = w_tempty; a.dbg[blockIdx.x * 16 + 4] = clock64() - t_begin; }
     }
   } else {
@@ -611,7 +641,6 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     int cur_qb = -1, cur_part = -1, c_first = 0, slot = 0;
     bool qvalid = false;
     int qg = 0;
-    const long long Wt = a.W;
     long long it = 0;
     long long w_tfull = 0, t_fold = 0; const long long t_begin = dbg ? clock64() : 0;
     const uint32_t tempty0 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tempty_bar[0]), lead) : 0u;
@@ -670,14 +699,13 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
     };
 
-    for (long long w = w_lo; w < w_hi; ++w, ++it) {
-      const int qb = (int)(w / a.n_t), t = (int)(w % a.n_t);
+    KEMR_FOR_TILES({
       if (qb != cur_qb) {
         cur_qb = qb;
-        c_first = a.upq > 0 ? qb * a.upq : (int)((((long long)qb * a.n_t + 1) * units - 1) / Wt);   // first unit of this block
+        c_first = unit_of(a.rtot, units, a.s.M, a.gran, (long long)qb * a.s.M);       // first unit of this block
       }
       // segment ordinal inside the query block: virtual parts + unit boundaries passed so far
-      const int ord = (a.vq > 1 ? (int)(((long long)t * a.vq) / a.n_t) : 0) + (unit - c_first);
+      const int ord = (a.vq > 1 ? (int)((row0 * a.vq) / a.s.M) : 0) + (unit - c_first);
       const int part = qb * 4096 + ord;
       if (part != cur_part) {
         flush();
@@ -696,8 +724,6 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint32_t bphase = (uint32_t)((it >> 1) & 1);
       mbar_wait_dbg(&tfull_bar[buf], bphase, dbg, w_tfull);
       ptx::tc_fence_after();
-      const long long row0 = (long long)t * n_tile;
-      const int ncols = (int)min((long long)n_tile, a.s.M - row0);
       const bool full_tile = ncols == n_tile;            // warp-uniform
       const uint32_t acc0 = lane_addr + (uint32_t)buf * 256u;
       const int cbeg = half * kHalfCols;
@@ -769,17 +795,15 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
       // double-buffered TMEM reads: chunk i+1 is in flight while chunk i is processed
       uint32_t ra0[16], rb0[16], ra1[16], rb1[16];
-      const int nch_run = (a.dbg_skip & 4) ? 0 : nch;          // timing experiment: epilogue reads nothing
-      const bool no_proc = (a.dbg_skip & 8) != 0;              // timing experiment: TMEM reads only
-      if (nch_run > 0) load(cbeg, ra0, rb0);
-      for (int i = 0; i < nch_run; i += 2) {
+      if (nch > 0) load(cbeg, ra0, rb0);
+      for (int i = 0; i < nch; i += 2) {
         ptx::tmem_ld_wait();
         if (i + 1 < nch) load(cbeg + (i + 1) * 16, ra1, rb1);
-        if (!no_proc) process(cbeg + i * 16, ra0, rb0); else cnt += (int32_t)ra0[3];
+        process(cbeg + i * 16, ra0, rb0);
         if (i + 1 < nch) {
           ptx::tmem_ld_wait();
           if (i + 2 < nch) load(cbeg + (i + 2) * 16, ra0, rb0);
-          if (!no_proc) process(cbeg + (i + 1) * 16, ra1, rb1); else cnt += (int32_t)ra1[3];
+          process(cbeg + (i + 1) * 16, ra1, rb1);
         }
       }
       // release this accumulator buffer to the (leader's) MMA warp
@@ -789,12 +813,16 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (PAIR && rank != 0) ptx::mbar_arrive_remote(buf ? tempty1 : tempty0);
         else ptx::mbar_arrive(&tempty_bar[buf]);
       }
-    }
+      ++it;
+    })
     flush();
     if (dbg && warp == 2 && lane == 0) { a.dbg[blockIdx.x * 16 + 5] = w_tfull; a.dbg[blockIdx.x * 16 + 6] = t_fold; a.dbg[blockIdx.x * 16 + 7] = clock64() - t_begin; }
   }
 
+#ifdef KEMR_DEBUG
   if (dbg && threadIdx.x == 64) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[blockIdx.x * 16 + 9] = (long long)t; }
+#endif
+#undef KEMR_FOR_TILES
   // no CTA of a pair may leave (or free TMEM) while its peer can still signal its barriers
   ptx::tc_fence_before();
   if (PAIR) ptx::cluster_sync_all(); else __syncthreads();
@@ -840,8 +868,8 @@ inline int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int D,
 }
 
 template <int K, int CL, bool TWO>
-inline int mma_launch_kpt(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
-                          const MmaPlan& pl, cudaStream_t st) {
+inline int mma_launch_kpt(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& s0,
+                          const CUtensorMap& s1, const MmaArgs& ma, const MmaPlan& pl, cudaStream_t st) {
   // the attribute sticks to the function on a device: set it once per (instantiation, device, size) of this thread
   static thread_local int attr_dev = -1;
   static thread_local size_t attr_smem = 0;
@@ -862,17 +890,17 @@ inline int mma_launch_kpt(const CUtensorMap& mq, const CUtensorMap& m0, const CU
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, scan_mma_kernel<K, CL, TWO>, mq, m0, m1, ma);
+  e = cudaLaunchKernelEx(&cfg, scan_mma_kernel<K, CL, TWO>, mq, m0, m1, s0, s1, ma);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
 }
 template <int K>
-inline int mma_launch_k(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const MmaArgs& ma,
-                        const MmaPlan& pl, cudaStream_t st) {
-  if (pl.cl == 4) return pl.two ? mma_launch_kpt<K, 4, true>(mq, m0, m1, ma, pl, st) : mma_launch_kpt<K, 4, false>(mq, m0, m1, ma, pl, st);
-  if (pl.cl == 2) return pl.two ? mma_launch_kpt<K, 2, true>(mq, m0, m1, ma, pl, st) : mma_launch_kpt<K, 2, false>(mq, m0, m1, ma, pl, st);
-  return pl.two ? mma_launch_kpt<K, 1, true>(mq, m0, m1, ma, pl, st) : mma_launch_kpt<K, 1, false>(mq, m0, m1, ma, pl, st);
+inline int mma_launch_k(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& s0,
+                        const CUtensorMap& s1, const MmaArgs& ma, const MmaPlan& pl, cudaStream_t st) {
+  if (pl.cl == 4) return pl.two ? mma_launch_kpt<K, 4, true>(mq, m0, m1, s0, s1, ma, pl, st) : mma_launch_kpt<K, 4, false>(mq, m0, m1, s0, s1, ma, pl, st);
+  if (pl.cl == 2) return pl.two ? mma_launch_kpt<K, 2, true>(mq, m0, m1, s0, s1, ma, pl, st) : mma_launch_kpt<K, 2, false>(mq, m0, m1, s0, s1, ma, pl, st);
+  return pl.two ? mma_launch_kpt<K, 1, true>(mq, m0, m1, s0, s1, ma, pl, st) : mma_launch_kpt<K, 1, false>(mq, m0, m1, s0, s1, ma, pl, st);
 }
 
 // clusters of four CTAs (one 227 KB CTA per SM) the current device can hold at once
@@ -892,29 +920,44 @@ inline int mma_max_quads() {
   return n;
 }
 
-inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
-  CUtensorMap mq, m0, m1;
-  if (make_tmap_2d(&mq, s.q, s.Q, s.D, pl.a_rows)) return 1;
+// the five tensor maps of one scan: queries, the galleries with the stage-sized box, the galleries with a 16-row box
+// (partial tiles at the end of a unit's row range)
+struct MmaMaps { CUtensorMap q, g0, g1, s0, s1; };
+
+inline int mma_make_maps(const ScanArgs& s, const MmaPlan& pl, MmaMaps* m) {
+  if (make_tmap_2d(&m->q, s.q, s.Q, s.D, pl.a_rows)) return 1;
   const int b_box = pl.cl == 4 ? 64 : (pl.pair ? 128 : pl.n_tile);     // gallery rows per TMA box
-  if (make_tmap_2d(&m0, s.gal[0], s.M, s.D, b_box)) return 1;
-  if (s.G > 1) { if (make_tmap_2d(&m1, s.gal[1], s.M, s.D, b_box)) return 1; }
-  else m1 = m0;
+  if (make_tmap_2d(&m->g0, s.gal[0], s.M, s.D, b_box)) return 1;
+  if (make_tmap_2d(&m->s0, s.gal[0], s.M, s.D, 16)) return 1;
+  if (s.G > 1) {
+    if (make_tmap_2d(&m->g1, s.gal[1], s.M, s.D, b_box)) return 1;
+    if (make_tmap_2d(&m->s1, s.gal[1], s.M, s.D, 16)) return 1;
+  } else { m->g1 = m->g0; m->s1 = m->s0; }
+  return 0;
+}
+
+inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st, const MmaMaps* cached = nullptr) {
+  MmaMaps local;
+  if (!cached) { if (mma_make_maps(s, pl, &local)) return 1; cached = &local; }
+  const CUtensorMap &mq = cached->q, &m0 = cached->g0, &m1 = cached->g1, &ms0 = cached->s0, &ms1 = cached->s1;
   MmaArgs ma;
   ma.s = s;
   ma.n_tile = pl.n_tile; ma.n_qb = pl.n_qb; ma.n_t = pl.n_t; ma.stages = pl.stages; ma.kc = pl.kc;
   ma.merged = pl.merged; ma.ds = pl.ds; ma.kc_total = (pl.merged && !pl.ds) ? 2 * pl.kc : pl.kc;
-  ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.q_blk = pl.q_blk; ma.upq = pl.upq; ma.vq = pl.vq;
-  ma.W = (long long)pl.n_qb * pl.n_t;
+  ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.q_blk = pl.q_blk; ma.gran = pl.gran; ma.vq = pl.vq;
+  ma.rtot = (long long)pl.n_qb * s.M;
   ma.dbg = nullptr;
-  static const char* skip_env = getenv("KEMR_MMA_DEBUG_SKIP");
-  ma.dbg_skip = skip_env ? atoi(skip_env) : 0;
   // Short lists (a thread sees few scores: survivor probability K/n per element stays high) append per lane without
   // warp votes; long scans keep the vote that skips chunks without survivors.  Measured: C1 233 -> 212 us, C2 101.5 -> 99 us.
   static const char* epi_env = getenv("KEMR_MMA_EPI");
   const long long units_run = pl.ctas / std::max(1, pl.cl);
-  const double per_list = (double)ma.W / (double)std::max(1ll, units_run) * (pl.n_tile / 2) / std::max(1, pl.vq);
+  const double per_list = (double)ma.rtot / (double)std::max(1ll, units_run) / 2.0 / std::max(1, pl.vq);
   ma.epi_variant = epi_env ? atoi(epi_env) : (per_list < 8192.0 ? 2 : 0);
+#ifdef KEMR_DEBUG
   static const bool debug = getenv("KEMR_MMA_DEBUG") != nullptr;
+#else
+  constexpr bool debug = false;
+#endif
   if (debug) {
     static long long* dbuf = nullptr;
     if (!dbuf) cudaMalloc(&dbuf, 1024 * 16 * sizeof(long long));
@@ -923,9 +966,9 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
   }
   int rc_launch = 0;
   switch (pl.K) {
-    case 8: rc_launch = mma_launch_k<8>(mq, m0, m1, ma, pl, st); break;
-    case 16: rc_launch = mma_launch_k<16>(mq, m0, m1, ma, pl, st); break;
-    default: rc_launch = mma_launch_k<32>(mq, m0, m1, ma, pl, st); break;
+    case 8: rc_launch = mma_launch_k<8>(mq, m0, m1, ms0, ms1, ma, pl, st); break;
+    case 16: rc_launch = mma_launch_k<16>(mq, m0, m1, ms0, ms1, ma, pl, st); break;
+    default: rc_launch = mma_launch_k<32>(mq, m0, m1, ms0, ms1, ma, pl, st); break;
   }
   if (debug && rc_launch == 0) {
     static int printed = 0;
@@ -943,8 +986,8 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st) {
         if (t < tmin) { tmin = t; cmin = c; }
         if (t > tmax) { tmax = t; cmax = c; }
       }
-      fprintf(stderr, "[kemr mma dbg] cl=%d merged=%d vq=%d parts=%d n_tile=%d K=%d ctas=%d tiles/unit=%.1f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f (min %lld @cta %d, max %lld @cta %d; max cta: wait_full=%lld wait_tempty=%lld) | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f  cycles\n",
-              pl.cl, pl.merged, pl.vq, pl.parts, pl.n_tile, pl.K, pl.ctas, (double)ma.W / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
+      fprintf(stderr, "[kemr mma dbg] cl=%d merged=%d vq=%d parts=%d n_tile=%d K=%d ctas=%d tile-equivalents/unit=%.2f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f (min %lld @cta %d, max %lld @cta %d; max cta: wait_full=%lld wait_tempty=%lld) | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f  cycles\n",
+              pl.cl, pl.merged, pl.vq, pl.parts, pl.n_tile, pl.K, pl.ctas, (double)ma.rtot / pl.n_tile / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
               tmin, cmin, tmax, cmax, h[(size_t)cmax * 16 + 2], h[(size_t)cmax * 16 + 3], avg[5], avg[6], avg[7]);
       {
         long long s_min = 1ll << 62, s_max = 0, e_max = 0, e_min = 1ll << 62;

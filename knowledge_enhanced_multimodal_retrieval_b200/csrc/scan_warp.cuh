@@ -1,17 +1,15 @@
-// HBM-streaming warp-dot scan for small, latency-bound query batches (north_star kernel 1b).
+// Warp-dot scan for small query batches in the COUNT and DENSE modes (the top-k search of small batches is the fused
+// streaming kernel of scan_stream.cuh).
 //
 // One warp owns one gallery row at a time: the row's D bf16 values are fetched with fully
 // coalesced 16-byte loads (lane l takes chunk l, l+32, ...), multiplied against query values that
 // live in registers as fp32, and reduced with warp shuffles.  The T2I/T2T weights are applied to
 // the per-lane partial sums before the (single) reduction, so two galleries cost one shuffle
 // tree.  The epilogue is one of
-//   TOPK  : per-warp sorted candidate lists in shared memory behind a register threshold,
-//           merged per CTA and written as one K-entry list per (CTA, query);
 //   COUNT : number of rows scoring above a per-query threshold, rows inside the +-eps band go
-//           to an "ambiguous" list that is re-scored in binary64 later;
+//           to an "ambiguous" list that is re-scored in binary64 later (ranks for Recall@K / MRR);
 //   DENSE : fp32 scores written out (compatibility / diagnostics).
-// The score matrix never reaches HBM in the first two modes.  Algorithmic traffic is
-// G*M*D*2 bytes per query group; the kernel is HBM-bound (roofline: MEASURED_PEAKS hbm_gbs).
+// Algorithmic traffic is G*M*D*2 bytes per query group; HBM-bound (roofline: MEASURED_PEAKS hbm_gbs).
 #pragma once
 #include "common.cuh"
 
@@ -50,9 +48,6 @@ constexpr int kWarpScanWarps = kWarpScanThreads / 32;
 
 template <int QB, int CH>
 __global__ void __launch_bounds__(kWarpScanThreads, 2) scan_warp_kernel(ScanArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw);   // [warps][QB][K] (TOPK only)
-
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int q0 = blockIdx.y * QB;
@@ -85,20 +80,13 @@ __global__ void __launch_bounds__(kWarpScanThreads, 2) scan_warp_kernel(ScanArgs
     wg[qq][0] = a.w[0]; wg[qq][1] = a.w[1];
     if (a.wq[0] && qq < nq) { wg[qq][0] = a.wq[0][q0 + qq]; wg[qq][1] = a.wq[1][q0 + qq]; }
   }
-  const int K = a.K;
-  uint64_t thr[QB];
   int32_t cnt[QB];
   float blo[QB], bhi[QB];
 #pragma unroll
   for (int qq = 0; qq < QB; ++qq) {
-    thr[qq] = 0; cnt[qq] = 0; blo[qq] = 0.f; bhi[qq] = 0.f;
+    cnt[qq] = 0; blo[qq] = 0.f; bhi[qq] = 0.f;
     if (a.mode == kModeCount && qq < nq) { blo[qq] = a.band_lo[q0 + qq]; bhi[qq] = a.band_hi[q0 + qq]; }
   }
-  if (a.mode == kModeTopk) {
-    for (int i = lane; i < QB * K; i += 32) lists[(size_t)warp * QB * K + i] = 0;
-    __syncwarp();
-  }
-
   // two rows in flight per warp
   for (int64_t row = r0 + warp; row < r1; row += 2 * kWarpScanWarps) {
     const int64_t rowB = row + kWarpScanWarps;
@@ -153,14 +141,7 @@ __global__ void __launch_bounds__(kWarpScanThreads, 2) scan_warp_kernel(ScanArgs
       for (int qq = 0; qq < QB; ++qq) {
         const float sc = warp_sum(s[qq]);
         if (qq >= nq) continue;
-        if (a.mode == kModeTopk) {
-          const uint64_t key = make_key(sc, (uint32_t)rcur);
-          if (key > thr[qq]) {                                   // warp-uniform
-            uint64_t* L = lists + ((size_t)warp * QB + qq) * K;
-            warp_list_insert(L, K, key, lane);
-            thr[qq] = L[K - 1];
-          }
-        } else if (a.mode == kModeCount) {
+        if (a.mode == kModeCount) {
           if (sc > bhi[qq]) {
             cnt[qq]++;
           } else if (sc >= blo[qq] && lane == 0) {
@@ -174,35 +155,7 @@ __global__ void __launch_bounds__(kWarpScanThreads, 2) scan_warp_kernel(ScanArgs
     }
   }
 
-  if (a.mode == kModeTopk) {
-    // CTA merge: the 8 warps' lists of a query are 8*K distinct keys; every thread ranks some of them by counting
-    // and the K best go out in order (a serial merge of sorted lists by one warp cost ~5 us of a 37 us batch-1 scan).
-    __syncthreads();
-    const int nk = kWarpScanWarps * K;
-    for (int qq = 0; qq < nq; ++qq) {
-      uint64_t* dst = a.part_keys + ((size_t)blockIdx.x * a.Q + (q0 + qq)) * K;
-      for (int i = threadIdx.x; i < nk; i += kWarpScanThreads) {
-        const uint64_t x = lists[((size_t)(i / K) * QB + qq) * K + (i % K)];
-        if (!x) continue;
-        int r = 0;
-        for (int w2 = 0; w2 < kWarpScanWarps; ++w2) {
-          const uint64_t* L = lists + ((size_t)w2 * QB + qq) * K;
-          for (int j = 0; j < K; ++j) r += L[j] > x ? 1 : 0;
-        }
-        if (r < K) dst[r] = x;
-      }
-      // fewer than K rows seen by this CTA: the tail stays empty
-      __shared__ int s_cnt;
-      if (threadIdx.x == 0) s_cnt = 0;
-      __syncthreads();
-      int mine = 0;
-      for (int i = threadIdx.x; i < nk; i += kWarpScanThreads) mine += lists[((size_t)(i / K) * QB + qq) * K + (i % K)] != 0;
-      if (mine) atomicAdd(&s_cnt, mine);
-      __syncthreads();
-      for (int r = s_cnt + threadIdx.x; r < K; r += kWarpScanThreads) dst[r] = 0;
-      __syncthreads();
-    }
-  } else if (a.mode == kModeCount) {
+  if (a.mode == kModeCount) {
     __shared__ int32_t csum[QB];
     if (threadIdx.x < QB) csum[threadIdx.x] = 0;
     __syncthreads();

@@ -62,10 +62,12 @@ inline size_t select_smem_bytes(int P, int Kp, int K, int max_cand) {
 //   B   candidate table = scan candidates U KG hits;
 //   C   warp w re-scores candidates w, w+W, ...; the rows of its next candidate are in flight meanwhile;
 //   D   order by (score desc, row asc) by counting, write the first k;   E  certificate.
+// Body of the selection for ONE query, run by a whole CTA of W warps (every thread of the CTA must call it; it uses
+// __syncthreads).  `smem_raw`: select_smem_bytes(...) bytes of shared memory, 16-byte aligned.  Called by
+// select_kernel (one CTA per query) and by the last CTA of the fused small-batch scan (scan_stream.cuh).
 template <int NP, int W>
-__global__ void __launch_bounds__(W * 32) select_kernel(SelectArgs a) {
+__device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, unsigned char* smem_raw) {
   constexpr int T = W * 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = a.K, Kp = a.Kp, P = a.P, MC = a.max_cand;
   uint64_t* s_heads = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* s_keys = s_heads + P;
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(W * 32) select_kernel(SelectArgs a) {
   __shared__ int s_nlist, s_extra, s_nsurv, s_nsel, s_first;
   __shared__ double s_kth;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int qi = blockIdx.x;
+  __syncthreads();                                          // a previous query of this CTA is done with the static state
 
   CanonQueryT<NP> cq;
   cq.load(a.q + (size_t)qi * a.D, a.D, lane);
@@ -285,6 +287,12 @@ __global__ void __launch_bounds__(W * 32) select_kernel(SelectArgs a) {
     }
     a.out_flags[qi] = flag;
   }
+}
+
+template <int NP, int W>
+__global__ void __launch_bounds__(W * 32) select_kernel(SelectArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  select_query<NP, W>(a, blockIdx.x, smem_raw);
 }
 
 // ------------------------------------------------------------------ canonical pair scores

@@ -1,6 +1,7 @@
-"""Property test of the tcgen05 scan's work plan (host logic, no GPU): the unit -> (query block, gallery tile) ranges
-and the part slots the epilogue derives from them must tile the work exactly and never collide.  The simulator below
-restates the index arithmetic of `scan_mma_kernel` (csrc/scan_mma.cuh: w_lo/w_hi, c_first, ord, slot)."""
+"""Property test of the tcgen05 scan's work plan (host logic, no GPU): the unit -> (query block, row range) cuts, the
+tiles (full and partial) a unit walks and the part slots the epilogue derives from them must cover every row exactly
+once and never collide.  The simulator below restates the index arithmetic of `scan_mma_kernel`
+(csrc/scan_mma.cuh: unit_begin, unit_of, KEMR_FOR_TILES, ord, slot)."""
 import ctypes as C
 
 import numpy as np
@@ -8,7 +9,7 @@ import pytest
 
 from knowledge_enhanced_multimodal_retrieval_b200 import _lib
 
-FIELDS = ("parts", "q_pad", "n_tile", "n_qb", "n_t", "ctas", "stages", "kc", "K", "cl", "upq", "vq", "all_slots",
+FIELDS = ("parts", "q_pad", "n_tile", "n_qb", "n_t", "ctas", "stages", "kc", "K", "cl", "gran", "vq", "all_slots",
           "two", "merged", "q_blk")
 
 
@@ -18,33 +19,59 @@ def plan(Q, M, D, G, k_sel, equal, sms=148, quads=33):
     return None if rc else dict(zip(FIELDS, list(out)))
 
 
-def simulate(p):
-    """(covered[(qb, t)] count, owner[(qb, ord)] -> unit) exactly as the kernel's producer / epilogue index them."""
-    units = p["ctas"] // p["cl"]
-    n_t, n_qb, upq, vq = p["n_t"], p["n_qb"], p["upq"], p["vq"]
-    W = n_qb * n_t
-    covered = np.zeros((n_qb, n_t), dtype=np.int32)
-    owner = {}
-    for unit in range(units):
-        if upq > 0:
-            j, base = unit % upq, (unit // upq) * n_t
-            w_lo, w_hi = base + n_t * j // upq, base + n_t * (j + 1) // upq
+def unit_begin(rtot, units, M, gran, u):
+    x = rtot * u // units
+    qb, r = divmod(x, M)
+    return qb * M + r - r % gran
+
+
+def unit_of(rtot, units, M, gran, pos):
+    lo, hi = 0, units - 1
+    while lo < hi:
+        mid = (lo + hi + 1) >> 1
+        if unit_begin(rtot, units, M, gran, mid) <= pos:
+            lo = mid
         else:
-            w_lo, w_hi = W * unit // units, W * (unit + 1) // units
-        w = w_lo
-        while w < w_hi:
-            qb = w // n_t
+            hi = mid - 1
+    return lo
+
+
+def simulate(p, M):
+    """(covered[qb, row] count, owner[(qb, ord)] -> unit, tile list per unit) exactly as the kernel's roles walk a unit's
+    row range (KEMR_FOR_TILES) and as its epilogue derives the part slots."""
+    units = p["ctas"] // p["cl"]
+    n_tile, n_qb, gran, vq = p["n_tile"], p["n_qb"], p["gran"], p["vq"]
+    rtot = n_qb * M
+    covered = np.zeros((n_qb, M), dtype=np.int32)
+    owner = {}
+    work = []
+    partial_ok = (not p["two"]) and p["cl"] != 4 and gran < n_tile
+    for unit in range(units):
+        p_lo, p_hi = unit_begin(rtot, units, M, gran, unit), unit_begin(rtot, units, M, gran, unit + 1)
+        assert p_lo <= p_hi
+        mma_rows = 0
+        pos = p_lo
+        while pos < p_hi:
+            qb = pos // M
             assert qb < n_qb, "unit reaches past the last query block"
-            c_first = qb * upq if upq > 0 else ((qb * n_t + 1) * units - 1) // W
-            t_end = min(w_hi, (qb + 1) * n_t)
-            ts = np.arange(w - qb * n_t, t_end - qb * n_t)
-            covered[qb, ts] += 1
-            ords = (ts * vq // n_t if vq > 1 else np.zeros_like(ts)) + (unit - c_first)
-            for o in np.unique(ords):
-                assert 0 <= 2 * int(o) + 1 < p["parts"], f"slot {2 * int(o) + 1} outside the {p['parts']} parts"
-                assert owner.setdefault((qb, int(o)), unit) == unit, "two units write the same part slot"
-            w = t_end
-    return covered, owner
+            blk0 = qb * M
+            rend = min(p_hi, blk0 + M) - blk0
+            c_first = unit_of(rtot, units, M, gran, blk0)
+            row0 = pos - blk0
+            while row0 < rend:
+                ncols = min(n_tile, rend - row0)
+                nmma = min(256, (ncols + 31) & ~31) if partial_ok else 256
+                assert nmma % 32 == 0 and 32 <= nmma <= 256 and (p["two"] or nmma >= ncols)
+                mma_rows += nmma if not p["two"] else n_tile
+                covered[qb, row0:row0 + ncols] += 1
+                o = (row0 * vq // M if vq > 1 else 0) + (unit - c_first)
+                assert 0 <= 2 * o + 1 < p["parts"], f"slot {2 * o + 1} outside the {p['parts']} parts"
+                assert owner.setdefault((qb, o), unit) == unit, "two units write the same part slot"
+                row0 += n_tile
+            pos = blk0 + rend
+        work.append(mma_rows)
+    assert unit_begin(rtot, units, M, gran, units) == rtot
+    return covered, owner, work
 
 
 SHAPES = [
@@ -67,10 +94,13 @@ def test_plan_tiles_the_work_without_slot_collisions(shape, sms, quads):
     assert p["ctas"] % p["cl"] == 0 and 1 <= p["ctas"] <= sms and (p["cl"] != 4 or p["ctas"] // 4 <= quads)
     assert p["stages"] >= 2 and p["K"] in (8, 16, 32) and 2 <= p["parts"] <= 304 and p["parts"] % 2 == 0
     assert p["n_t"] == -(-shape[1] // p["n_tile"]) and p["kc"] == -(-shape[2] // 64)
-    covered, owner = simulate(p)
-    assert (covered == 1).all(), "every (query block, gallery tile) must be scanned exactly once"
+    covered, owner, work = simulate(p, shape[1])
+    assert (covered == 1).all(), "every (query block, gallery row) must be scanned exactly once"
     if p["all_slots"]:
         assert len(owner) == p["n_qb"] * (p["parts"] // 2), "all_slots promises that no part slot stays unwritten"
+    if p["gran"] < p["n_tile"] and shape[1] >= 4 * p["n_tile"]:
+        # partial tiles level the tensor work: no unit does more than the mean plus two 32-row steps per block boundary
+        assert max(work) <= sum(work) / len(work) + 64 * 2 + 32, (max(work), sum(work) / len(work))
 
 
 def test_plan_random_shapes():
@@ -88,7 +118,9 @@ def test_plan_random_shapes():
         if p is None:
             continue
         n += 1
-        covered, owner = simulate(p)
+        if p["n_qb"] * M > 40_000_000:
+            continue                                   # the row-level simulation of huge shapes is covered by SHAPES
+        covered, owner, _ = simulate(p, M)
         assert (covered == 1).all(), (Q, M, D, G, k_sel, equal, sms, quads, p)
         if p["all_slots"]:
             assert len(owner) == p["n_qb"] * (p["parts"] // 2), (Q, M, D, G, k_sel, p)
