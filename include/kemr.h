@@ -198,6 +198,31 @@ int kemr_metrics_reduce_host(const int64_t* ranks_host, int Q, const int32_t* k_
  *   slots idx < 0 at the end); output top-k by (score desc, idx asc); R <= 64. */
 int kemr_merge_topk(const double* in_score64, const int64_t* in_idx, int R, int Q, int k,
                     double* out_score64, int64_t* out_idx, kemr_stream_t stream);
+/* the same with list r of a query at in_*[r * rank_stride + q * k] (entries; rank_stride >= Q*k): merges straight
+ * out of an all-gather receive buffer laid out [rank][score | idx][Q][k] */
+int kemr_merge_topk_strided(const double* in_score64, const int64_t* in_idx, int64_t rank_stride, int R, int Q, int k,
+                            double* out_score64, int64_t* out_idx, kemr_stream_t stream);
+
+/* ---- result exchange of the row-sharded search over NVLink peer memory ("each GPU's local top-k is
+ * merged with a single all-gather").  Here the gather is FUSED into the selection kernel: every rank owns an exchange
+ * buffer; the selection kernel of rank r stores the k result rows of each query straight into slot r of every rank's
+ * buffer (peer-mapped stores over NVLink) and releases a per-query flag there; the merge kernel waits for the world's
+ * flags in local memory.  No collective launch and no host synchronisation in the step.  Setup (once): every rank
+ * calls kemr_peer_create, exchanges the 64-byte IPC handles out of band (e.g. torch.distributed.all_gather) and calls
+ * kemr_peer_connect with the world's handles in rank order; ranks that live in ONE process pass the other ranks'
+ * kemr_peer_local_buffer pointers to kemr_peer_connect_pointers instead.  A step on every rank:
+ *     kemr_peer_begin(peer, stream);                         new epoch; arms the push of this thread's next scan
+ *     kemr_scan_topk[_gated](...);                           as usual (idx_base = first global row of the shard)
+ *     kemr_peer_merge(peer, Q, k, out_score64, out_idx, stream);   global top-k on every rank
+ * All ranks must run the same sequence of steps with the same Q and k (world <= 8, one NVSwitch box). */
+typedef struct kemr_peer kemr_peer_t;
+int kemr_peer_create(int rank, int world, int max_queries, int max_k, kemr_peer_t** out, void* ipc_handle_host64);
+int kemr_peer_connect(kemr_peer_t* peer, const void* ipc_handles_host /* [world][64] */);
+int kemr_peer_connect_pointers(kemr_peer_t* peer, void* const* bases_host /* [world] device pointers */);
+void* kemr_peer_local_buffer(kemr_peer_t* peer);
+int kemr_peer_destroy(kemr_peer_t* peer);
+int kemr_peer_begin(kemr_peer_t* peer, kemr_stream_t stream);
+int kemr_peer_merge(kemr_peer_t* peer, int Q, int k, double* out_score64, int64_t* out_idx, kemr_stream_t stream);
 
 /* ---- resident gallery handle with HOST-buffer search: the serving-side drop-in for
  * CLIPRetriever.search (clip_retrieval.py:39-40 -> retrieval.py:80,98).  The handle owns its

@@ -23,6 +23,8 @@ EXPORTS = (
     "kemr_scan_topk_gated", "kemr_rank_count_gated", "kemr_score_pairs_gated", "kemr_gate_linear",
     "kemr_hits_workspace_bytes", "kemr_hits_build_csr", "kemr_idmap_create", "kemr_idmap_destroy", "kemr_idmap_lookup",
     "kemr_store_write", "kemr_store_info", "kemr_store_load", "kemr_debug_mma_plan", "kemr_set_phase_stamps",
+    "kemr_peer_create", "kemr_peer_connect", "kemr_peer_connect_pointers", "kemr_peer_local_buffer", "kemr_peer_destroy",
+    "kemr_peer_begin", "kemr_peer_merge", "kemr_merge_topk_strided",
 )
 
 
@@ -73,14 +75,24 @@ def _declare(lib):
     lib.kemr_metrics_reduce.argtypes = [p, i32, p, i32, p, p, p]
     lib.kemr_metrics_reduce_host.argtypes = [p, i32, p, i32, p, p]
     lib.kemr_merge_topk.argtypes = [p, p, i32, i32, i32, p, p, p]
+    lib.kemr_merge_topk_strided.argtypes = [p, p, i64, i32, i32, i32, p, p, p]
     lib.kemr_index_create.argtypes = [p, p, i64, i32, i32, i32, C.POINTER(p)]
     lib.kemr_index_destroy.argtypes = [p]
     lib.kemr_set_scan_done_event.argtypes = [p]
     lib.kemr_set_phase_stamps.argtypes = [p]
+    lib.kemr_peer_create.argtypes = [i32, i32, i32, i32, C.POINTER(p), p]
+    lib.kemr_peer_connect.argtypes = [p, p]
+    lib.kemr_peer_connect_pointers.argtypes = [p, p]
+    lib.kemr_peer_local_buffer.argtypes = [p]
+    lib.kemr_peer_local_buffer.restype = p
+    lib.kemr_peer_destroy.argtypes = [p]
+    lib.kemr_peer_begin.argtypes = [p, p]
+    lib.kemr_peer_merge.argtypes = [p, i32, i32, p, p, p]
     lib.kemr_index_search_host.argtypes = [p, p, i32, i32, f64, f64, f64, p, p, p, i32, p, p, p]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("kemr_last_error", "kemr_workspace_bytes", "kemr_abi_version", "kemr_hits_workspace_bytes"):
+        if name not in ("kemr_last_error", "kemr_workspace_bytes", "kemr_abi_version", "kemr_hits_workspace_bytes",
+                        "kemr_peer_local_buffer"):
             fn.restype = i32
 
 

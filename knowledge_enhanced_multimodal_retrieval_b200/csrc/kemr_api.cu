@@ -273,6 +273,9 @@ __global__ void weights_to_f32_kernel(const double* __restrict__ wa, const doubl
   if (i < Q) { oa[i] = (float)wa[i]; ob[i] = (float)wb[i]; }
 }
 
+struct kemr_peer;
+static int arm_peer_push(SelectArgs* s, int Q, int k);
+
 static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const uint16_t* gal_b,
                           int64_t M, int D, double w_a, double w_b, const double* wq_a, const double* wq_b, double alpha,
                           const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
@@ -322,6 +325,7 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
   s.out_score64 = out_score64; s.out_score32 = out_score32; s.out_idx = out_idx; s.out_flags = out_flags;
   s.max_cand = k_sel + (int)max_hits_per_query;
   s.key_slots = (int)select_key_slots(pl.Kp, k_sel);
+  if ((rc = arm_peer_push(&s, Q, k))) return rc;
   if (pl.P > kMaxParts) return fail(KEMR_ERR_UNSUPPORTED, "too many part lists per query (%d)", pl.P);
   const size_t smem = select_smem_bytes(pl.P, pl.Kp, k_sel, s.max_cand);
   if (smem > 200 * 1024) return fail(KEMR_ERR_UNSUPPORTED, "select kernel needs %zu bytes of shared memory", smem);
@@ -666,16 +670,147 @@ extern "C" int kemr_metrics_reduce_host(const int64_t* ranks, int Q, const int32
   return KEMR_OK;
 }
 
+extern "C" int kemr_merge_topk_strided(const double* in_score64, const int64_t* in_idx, int64_t rank_stride, int R, int Q, int k,
+                                       double* out_score64, int64_t* out_idx, kemr_stream_t stream);
 extern "C" int kemr_merge_topk(const double* in_score64, const int64_t* in_idx, int R, int Q, int k,
                                double* out_score64, int64_t* out_idx, kemr_stream_t stream) {
-  if (!in_score64 || !in_idx || !out_score64 || !out_idx || R <= 0 || Q <= 0 || k <= 0)
+  return kemr_merge_topk_strided(in_score64, in_idx, (int64_t)Q * k, R, Q, k, out_score64, out_idx, stream);
+}
+
+extern "C" int kemr_merge_topk_strided(const double* in_score64, const int64_t* in_idx, int64_t rank_stride, int R, int Q, int k,
+                                       double* out_score64, int64_t* out_idx, kemr_stream_t stream) {
+  if (!in_score64 || !in_idx || !out_score64 || !out_idx || R <= 0 || Q <= 0 || k <= 0 || rank_stride < (int64_t)Q * k)
     return fail(KEMR_ERR_ARG, "merge_topk: bad argument");
   const size_t smem = (size_t)R * k * 16;
   if (smem > 200 * 1024 || R > 64) return fail(KEMR_ERR_ARG, "merge_topk: R*k too large (%d*%d)", R, k);
   if (smem > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_topk_kernel<<<Q, 256, smem, S(stream)>>>(in_score64, in_idx, R, Q, k, out_score64, out_idx);
+  merge_topk_kernel<<<Q, 256, smem, S(stream)>>>(in_score64, in_idx, (long long)rank_stride, R, Q, k, out_score64, out_idx, nullptr, 0, nullptr);
   LAUNCH_CHECK("merge_topk_kernel");
+  return KEMR_OK;
+}
+
+// ----------------------------------------------------------------------------- result exchange over NVLink peer memory
+// One exchange buffer per rank (cudaMalloc, exported with cudaIpcGetMemHandle or shared by pointer inside one process):
+//   scores  f64 [2 parity][world][max_q * max_k]
+//   indices i64 [2 parity][world][max_q * max_k]
+//   flags   u32 [2 parity][world][max_q]          epoch of the step whose rows are complete
+//   epoch   u32                                   bumped once per step by kemr_peer_begin
+// A step of rank r: kemr_peer_begin -> kemr_scan_topk (its selection kernel stores the k rows of every query into
+// slot r of EVERY rank's buffer and releases the query's flag there) -> kemr_peer_merge (one CTA per query waits for
+// the world's flags of this epoch in LOCAL memory and merges).  Buffers alternate by epoch parity: a rank can only
+// be one step ahead of the slowest one, because its next merge needs that rank's next rows.
+struct kemr_peer {
+  int rank = 0, world = 1, max_q = 0, max_k = 0, dev = -1;
+  unsigned char* local = nullptr;
+  unsigned char* base[kMaxPeers] = {nullptr};
+  bool opened[kMaxPeers] = {false};
+  size_t bytes = 0, idx_region = 0, flag_region = 0, epoch_off = 0;
+};
+static thread_local kemr_peer* g_push_peer = nullptr;      // armed by kemr_peer_begin, consumed by the next kemr_scan_topk
+
+__global__ void peer_bump_kernel(unsigned int* epoch) { *epoch += 1u; }
+
+// the selection kernel of the kemr_scan_topk call that follows kemr_peer_begin also stores its rows into every rank's
+// buffer (select.cuh, stage D)
+static int arm_peer_push(SelectArgs* s, int Q, int k) {
+  kemr_peer* p = g_push_peer;
+  s->n_peer = 0;
+  if (!p) return KEMR_OK;
+  g_push_peer = nullptr;
+  if (Q > p->max_q || k > p->max_k) return fail(KEMR_ERR_ARG, "peer exchange: Q=%d / k=%d beyond the handle's limits (%d / %d)", Q, k, p->max_q, p->max_k);
+  s->n_peer = p->world;
+  for (int r = 0; r < p->world; ++r) s->peer_base[r] = p->base[r];
+  s->peer_block = (long long)p->max_q * p->max_k;
+  s->peer_idx_region = (long long)p->idx_region;
+  s->peer_flag_region = (long long)p->flag_region;
+  s->peer_max_q = p->max_q; s->peer_rank = p->rank; s->peer_world = p->world;
+  s->peer_epoch = reinterpret_cast<const unsigned int*>(p->local + p->epoch_off);
+  return KEMR_OK;
+}
+
+extern "C" int kemr_peer_create(int rank, int world, int max_queries, int max_k, kemr_peer_t** out, void* ipc_handle_host64) {
+  if (!out || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || max_queries <= 0 || max_k <= 0)
+    return fail(KEMR_ERR_ARG, "peer_create: bad argument (world <= %d)", kMaxPeers);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  kemr_peer* p = new kemr_peer();
+  p->rank = rank; p->world = world; p->max_q = max_queries; p->max_k = max_k;
+  const size_t block = (size_t)max_queries * max_k;
+  p->idx_region = align_up((size_t)2 * world * block * 8);
+  p->flag_region = p->idx_region + align_up((size_t)2 * world * block * 8);
+  p->epoch_off = p->flag_region + align_up((size_t)2 * world * max_queries * 4);
+  p->bytes = p->epoch_off + 256;
+  cudaError_t e = cudaGetDevice(&p->dev);
+  if (e == cudaSuccess) e = cudaMalloc(&p->local, p->bytes);
+  if (e == cudaSuccess) e = cudaMemset(p->local, 0, p->bytes);
+  if (e == cudaSuccess && ipc_handle_host64) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handle_host64), p->local);
+  if (e != cudaSuccess) { cudaFree(p->local); delete p; return fail(KEMR_ERR_CUDA, "peer_create: %s", cudaGetErrorString(e)); }
+  p->base[rank] = p->local;
+  *out = p;
+  return KEMR_OK;
+}
+
+extern "C" int kemr_peer_connect(kemr_peer_t* p, const void* ipc_handles_host) {
+  if (!p || !ipc_handles_host) return fail(KEMR_ERR_ARG, "peer_connect: null argument");
+  const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(ipc_handles_host);
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank) continue;
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(KEMR_ERR_CUDA, "peer_connect: cannot map the buffer of rank %d: %s", r, cudaGetErrorString(e));
+    p->base[r] = reinterpret_cast<unsigned char*>(ptr);
+    p->opened[r] = true;
+  }
+  return KEMR_OK;
+}
+
+extern "C" int kemr_peer_connect_pointers(kemr_peer_t* p, void* const* bases_host) {
+  if (!p || !bases_host) return fail(KEMR_ERR_ARG, "peer_connect_pointers: null argument");
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank) continue;
+    if (!bases_host[r]) return fail(KEMR_ERR_ARG, "peer_connect_pointers: no buffer for rank %d", r);
+    p->base[r] = reinterpret_cast<unsigned char*>(bases_host[r]);
+  }
+  return KEMR_OK;
+}
+
+extern "C" void* kemr_peer_local_buffer(kemr_peer_t* p) { return p ? p->local : nullptr; }
+
+extern "C" int kemr_peer_destroy(kemr_peer_t* p) {
+  if (!p) return KEMR_OK;
+  if (g_push_peer == p) g_push_peer = nullptr;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < p->world; ++r)
+    if (p->opened[r]) cudaIpcCloseMemHandle(p->base[r]);
+  cudaFree(p->local);
+  delete p;
+  return KEMR_OK;
+}
+
+extern "C" int kemr_peer_begin(kemr_peer_t* p, kemr_stream_t stream) {
+  if (!p) return fail(KEMR_ERR_ARG, "peer_begin: null handle");
+  for (int r = 0; r < p->world; ++r)
+    if (!p->base[r]) return fail(KEMR_ERR_ARG, "peer_begin: rank %d is not connected", r);
+  peer_bump_kernel<<<1, 1, 0, S(stream)>>>(reinterpret_cast<unsigned int*>(p->local + p->epoch_off));
+  LAUNCH_CHECK("peer_bump_kernel");
+  g_push_peer = p;
+  return KEMR_OK;
+}
+
+extern "C" int kemr_peer_merge(kemr_peer_t* p, int Q, int k, double* out_score64, int64_t* out_idx, kemr_stream_t stream) {
+  if (!p || !out_score64 || !out_idx || Q <= 0 || k <= 0 || Q > p->max_q || k > p->max_k)
+    return fail(KEMR_ERR_ARG, "peer_merge: bad argument (Q <= %d, k <= %d)", p ? p->max_q : 0, p ? p->max_k : 0);
+  if (g_push_peer == p) return fail(KEMR_ERR_ARG, "peer_merge: no kemr_scan_topk call since kemr_peer_begin");
+  const size_t smem = (size_t)p->world * k * 16;
+  if (smem > 200 * 1024) return fail(KEMR_ERR_ARG, "peer_merge: world*k too large");
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // both parities are passed as one base: the kernel picks the epoch's half through the rank stride arithmetic below
+  const size_t block = (size_t)p->max_q * p->max_k;
+  merge_peer_kernel<<<Q, 256, smem, S(stream)>>>(p->local, (long long)p->idx_region, (long long)p->flag_region, (long long)block,
+                                                 p->world, p->max_q, Q, k, out_score64, out_idx,
+                                                 reinterpret_cast<const unsigned int*>(p->local + p->epoch_off));
+  LAUNCH_CHECK("merge_peer_kernel");
   return KEMR_OK;
 }
 

@@ -15,13 +15,16 @@
 // so every scheduler hosts two epilogue warps and a query's candidates come as two lists per CTA.
 // One pipeline stage holds the query chunk ONCE plus the matching chunk of every gallery (the
 // A operand is shared by the T2I and T2T MMAs).
-// Work: the rows of all query blocks are laid end to end (position = block * M + row) and cut into equal contiguous
-// ROW ranges, one per persistent CTA / pair / quad (<= #SMs), snapped to 32 rows inside a block.  A unit walks its
-// range in tiles of n_tile rows; the tile at the end of a range is PARTIAL: its MMA is issued with N = the rows left
-// (rounded up to 32) and its rows arrive as 16-row TMA boxes, so every unit does the same tensor work to within 32
-// rows whatever M / n_tile leaves over (C2: 9.08 tile-equivalents per pair instead of 9 or 10).  A unit emits one
-// K-entry candidate list per query and column half for every query block its range touches ("part slot"), merged
-// later by select.cuh.
+// Work: U persistent units (CTAs / pairs / quads, <= #SMs) share n_qb query blocks x M gallery rows in ROWS, not
+// tiles.  The gallery is cut into floor(U / n_qb) full stripes of L = ceil32(n_qb * M / U) rows; unit u = s * n_qb + qb
+// scans stripe s for query block qb, so the n_qb units of a stripe read the SAME rows at the same time (one DRAM read,
+// n_qb - 1 L2 hits -- with unsynchronised ranges every block re-read the gallery from DRAM).  The rows left over form
+// a remainder stripe that the remaining U mod n_qb units share as one flat (block, row) range.  A unit walks its rows
+// in tiles of n_tile; the tile at the end of a range is PARTIAL: its MMA is issued with N = the rows left (rounded up
+// to 32) and its rows arrive as 16-row TMA boxes, so every unit does the same tensor work to within 32 rows whatever
+// M / n_tile leaves over (C2: 9.08 tile-equivalents on each of 74 pairs instead of 9 or 10 on 72).  A unit emits one
+// K-entry candidate list per query and column half for every query block it touches ("part slot"), merged later by
+// select.cuh.
 //
 // Epilogue per element: 1-2 FFMA for the fusion weights and one compare against the thread's running
 // threshold.  Survivors are appended to a small per-thread buffer in shared memory; when any lane's
@@ -84,6 +87,8 @@ struct MmaPlan {
   int pair = 0;           // 1: CTA pairs (cta_group::2), 256 queries per block
   int cl = 1;             // CTAs per cluster: 1, 2 (one pair) or 4 (two pairs on adjacent query blocks sharing the gallery tile by TMA multicast)
   int gran = 32;          // unit boundaries are multiples of this many rows inside a query block (n_tile: no partial tiles)
+  int s_full = 0;         // full stripes (one unit per stripe and query block)
+  long long L = 0;        // rows per full stripe
   int vq = 1;             // virtual parts per query block: lists are flushed and restarted at these boundaries
   int all_slots = 0;      // 1: every part slot of every query row is written (no memset needed)
   int two = 0;            // 1: two accumulators (T2I, T2T) with their own weights
@@ -99,21 +104,85 @@ inline bool mma_supported(int D, int K) { return D % 8 == 0 && D >= 8 && D <= kM
 static thread_local char g_mma_error[256] = "";
 inline const char* mma_last_error() { return g_mma_error; }
 
-// First position (block * M + row) of unit u when `rtot` = n_qb * M rows of work are cut into `units` ranges: the
-// even split, snapped down to a multiple of `gran` rows inside its query block.  unit_begin(units) == rtot.
-__host__ __device__ inline long long unit_begin(long long rtot, int units, long long M, int gran, int u) {
+// First position (block * len + row) of unit u when `rtot` = blocks * len rows of work are cut into `units` ranges:
+// the even split, snapped down to a multiple of `gran` rows inside its block.  unit_begin(units) == rtot.
+__host__ __device__ inline long long unit_begin(long long rtot, int units, long long len, int gran, int u) {
   const long long x = rtot * u / units;
-  const long long qb = x / M, r = x - qb * M;
-  return qb * M + r - r % gran;
+  const long long qb = x / len, r = x - qb * len;
+  return qb * len + r - r % gran;
 }
 // the unit whose range holds position `pos` (largest u with unit_begin(u) <= pos; ranges may be empty)
-__host__ __device__ inline int unit_of(long long rtot, int units, long long M, int gran, long long pos) {
+__host__ __device__ inline int unit_of(long long rtot, int units, long long len, int gran, long long pos) {
   int lo = 0, hi = units - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (unit_begin(rtot, units, M, gran, mid) <= pos) lo = mid; else hi = mid - 1;
+    if (unit_begin(rtot, units, len, gran, mid) <= pos) lo = mid; else hi = mid - 1;
   }
   return lo;
+}
+
+// How the units share the work (see the header comment): `s_full` stripes of `L` rows, one unit per (stripe, block);
+// the rows from s_full * L on are the remainder stripe, shared by the units past s_full * n_qb.
+struct WorkSplit {
+  long long M;        // gallery rows
+  long long L;        // rows per full stripe (multiple of gran); 0 when there is no full stripe
+  int n_qb, units, s_full, gran;
+  __host__ __device__ int full_units() const { return s_full * n_qb; }
+  __host__ __device__ long long rem_base() const { return (long long)s_full * L < M ? (long long)s_full * L : M; }
+  __host__ __device__ long long rem_len() const { return M - rem_base(); }
+};
+// One unit's walk: positions [p_lo, p_hi) of a flat space of blocks of `mod` rows; position p is row base + p % mod of
+// query block qb0 + p / mod.
+struct UnitWalk { long long base, mod, p_lo, p_hi; int qb0; };
+
+__host__ __device__ inline UnitWalk unit_walk(const WorkSplit& w, int u) {
+  UnitWalk k;
+  if (u < w.full_units()) {
+    const int s = u / w.n_qb;
+    k.base = (long long)s * w.L;
+    const long long len = (w.M - k.base < w.L ? w.M - k.base : w.L);
+    k.mod = len > 0 ? len : 1; k.p_lo = 0; k.p_hi = len > 0 ? len : 0; k.qb0 = u % w.n_qb;
+  } else {
+    const int nr = w.units - w.full_units(), j = u - w.full_units();
+    const long long len = w.rem_len();
+    k.base = w.rem_base(); k.mod = len > 0 ? len : 1; k.qb0 = 0;
+    const long long rtot = (long long)w.n_qb * len;
+    k.p_lo = len > 0 ? unit_begin(rtot, nr, len, w.gran, j) : 0;
+    k.p_hi = len > 0 ? unit_begin(rtot, nr, len, w.gran, j + 1) : 0;
+  }
+  return k;
+}
+// ordinal of unit u among the units that touch query block qb, in row order (full stripes first, then the remainder units)
+__host__ __device__ inline int unit_ordinal(const WorkSplit& w, int u, int qb) {
+  if (u < w.full_units()) return u / w.n_qb;
+  const int nr = w.units - w.full_units();
+  const long long len = w.rem_len();
+  const int first = unit_of((long long)w.n_qb * len, nr, len, w.gran, (long long)qb * len);
+  return w.s_full + (u - w.full_units() - first);
+}
+// number of units that touch query block qb
+__host__ __device__ inline int units_of_block(const WorkSplit& w, int qb) {
+  int n = w.s_full;
+  const int nr = w.units - w.full_units();
+  const long long len = w.rem_len();
+  if (nr > 0 && len > 0) {
+    const long long rtot = (long long)w.n_qb * len;
+    n += unit_of(rtot, nr, len, w.gran, (long long)(qb + 1) * len - 1) - unit_of(rtot, nr, len, w.gran, (long long)qb * len) + 1;
+  }
+  return n;
+}
+inline WorkSplit make_split(long long M, int n_qb, int units, int gran) {
+  WorkSplit w;
+  w.M = M; w.n_qb = n_qb; w.units = units; w.gran = gran;
+  w.s_full = units / n_qb;
+  w.L = 0;
+  if (w.s_full > 0) {
+    const int rem_units = units - w.s_full * n_qb;
+    // equal work for full and remainder units: L = n_qb * M / units; without remainder units the stripes must cover M
+    const long long want = rem_units > 0 ? ((long long)n_qb * M + units - 1) / units : (M + w.s_full - 1) / w.s_full;
+    w.L = (want + gran - 1) / gran * gran;
+  }
+  return w;
 }
 
 constexpr int kPlanMaxParts = 304;     // candidate lists per query any plan may use (workspace bound: 2*148 + 8)
@@ -152,22 +221,25 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
   if (nt > (1ll << 30)) return 1;
   p->n_t = (int)nt;
   const int units = quad ? quads : (p->pair ? sms / 2 : sms);       // persistent CTAs, pairs or quads
-  // Row ranges: position = block * M + row; unit u owns [unit_begin(u), unit_begin(u + 1)).  Partial tiles (MMA with a
-  // smaller N, 16-row TMA boxes) exist for the single-accumulator kernels of one CTA or one pair; quads and the
-  // two-accumulator kernels keep tile-aligned boundaries.
+  // Partial tiles (MMA with a smaller N, 16-row TMA boxes) exist for the single-accumulator kernels of one CTA or one
+  // pair; quads and the two-accumulator kernels keep tile-aligned boundaries.
   static const bool no_partial = getenv("KEMR_MMA_NO_PARTIAL") != nullptr;     // experiments: tile-aligned boundaries everywhere
   p->gran = (quad || p->two || no_partial) ? p->n_tile : 32;
   const int64_t rtot = (int64_t)p->n_qb * M;
   const int nu = (int)std::min<int64_t>(units, std::max<int64_t>(1, rtot / p->n_tile));   // at least a tile's worth of rows per unit
+  const WorkSplit ws = make_split(M, p->n_qb, nu, p->gran);
+  p->s_full = ws.s_full; p->L = ws.L;
   int parts = 1;
   bool same = true;
   for (int qb = 0; qb < p->n_qb; ++qb) {
-    const int c0 = unit_of(rtot, nu, M, p->gran, (int64_t)qb * M), c1 = unit_of(rtot, nu, M, p->gran, (int64_t)(qb + 1) * M - 1);
-    if (qb && c1 - c0 + 1 != parts) same = false;
-    parts = std::max(parts, c1 - c0 + 1);
+    const int n = units_of_block(ws, qb);
+    if (qb && n != parts) same = false;
+    parts = std::max(parts, n);
   }
-  for (int u = 0; u < nu; ++u)
-    if (unit_begin(rtot, nu, M, p->gran, u) == unit_begin(rtot, nu, M, p->gran, u + 1)) same = false;   // an empty unit leaves a hole
+  for (int u = 0; u < nu; ++u) {
+    const UnitWalk k = unit_walk(ws, u);
+    if (k.p_lo >= k.p_hi) same = false;                     // an empty unit leaves a hole in the part slots
+  }
   p->ctas = p->cl * nu;
   p->a_rows = (p->pair || Q >= kBlockM) ? kBlockM : (Q + 7) / 8 * 8;
   // Candidate lists.  A query's rows are cut into segments (unit boundaries, plus `vq` virtual
@@ -361,7 +433,7 @@ struct MmaArgs {
   int merged;       // both galleries accumulate into ONE accumulator (equal weights): 2*kc K chunks
   int ds;           // merged, CTA pairs: a stage holds the query chunk ONCE plus the matching chunk of BOTH galleries (8 MMAs)
   int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, gran, vq;
-  long long rtot;   // n_qb * M: rows of work, cut into one contiguous range per unit (unit_begin)
+  WorkSplit split;  // how the units share the (query block, gallery row) work
   long long* dbg;   // optional [ctas][16] cycle counters + stage trace (debug build, KEMR_MMA_DEBUG=1)
   int epi_variant;  // 1 = per-lane predicated appends without warp votes (short lists), 2 = the same on RAW accumulators; KEMR_MMA_EPI overrides
 };
@@ -453,16 +525,15 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const uint32_t pc = crank >> 1;                               // which pair of a quad (its 256-query block)
   const uint32_t lead = crank & ~1u;                            // cluster rank of this pair's leader
   const int unit = (int)(blockIdx.x / CL);                      // persistent CTA, pair or quad
-  const int units = (int)(gridDim.x / CL);
 #ifdef KEMR_DEBUG
   const bool dbg = a.dbg != nullptr;
   if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[blockIdx.x * 16 + 8] = (long long)t; }
 #else
   constexpr bool dbg = false;          // role counters and the stage trace exist in the debug build only
 #endif
-  // this unit's range of the row work (position = query block * M + row)
-  const long long p_lo = unit_begin(a.rtot, units, a.s.M, a.gran, unit);
-  const long long p_hi = unit_begin(a.rtot, units, a.s.M, a.gran, unit + 1);
+  // this unit's share of the work: a stripe of one query block, or a flat range of the remainder stripe
+  const UnitWalk uw = unit_walk(a.split, unit);
+  const long long p_lo = uw.p_lo, p_hi = uw.p_hi;
   // partial tiles: the single-accumulator kernels of one CTA / one pair, when the plan cut the ranges finer than tiles
   const bool partial_ok = !TWO && !QUAD && a.gran < n_tile;
   // Walk of a range, identical in the three roles: segments (one per query block touched) of tiles; the last tile of
@@ -470,11 +541,13 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   // block) and ncols (rows of the tile that belong to this unit) in scope.
 #define KEMR_FOR_TILES(...)                                                                   \
   for (long long p__ = p_lo; p__ < p_hi;) {                                                   \
-    const int qb = (int)(p__ / a.s.M);                                                        \
-    const long long blk0__ = (long long)qb * a.s.M;                                           \
-    const long long rend__ = (p_hi < blk0__ + a.s.M ? p_hi : blk0__ + a.s.M) - blk0__;        \
-    for (long long row0 = p__ - blk0__; row0 < rend__; row0 += n_tile) {                      \
-      const int ncols = (int)(rend__ - row0 < (long long)n_tile ? rend__ - row0 : (long long)n_tile); \
+    const long long b__ = p__ / uw.mod;                                                       \
+    const int qb = uw.qb0 + (int)b__;                                                         \
+    const long long blk0__ = b__ * uw.mod;                                                    \
+    const long long rend__ = (p_hi < blk0__ + uw.mod ? p_hi : blk0__ + uw.mod) - blk0__;      \
+    for (long long r__ = p__ - blk0__; r__ < rend__; r__ += n_tile) {                         \
+      const long long row0 = uw.base + r__;                                                   \
+      const int ncols = (int)(rend__ - r__ < (long long)n_tile ? rend__ - r__ : (long long)n_tile); \
       __VA_ARGS__                                                                             \
     }                                                                                         \
     p__ = blk0__ + rend__;                                                                    \
@@ -702,10 +775,10 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     KEMR_FOR_TILES({
       if (qb != cur_qb) {
         cur_qb = qb;
-        c_first = unit_of(a.rtot, units, a.s.M, a.gran, (long long)qb * a.s.M);       // first unit of this block
+        c_first = unit_ordinal(a.split, unit, qb);     // this unit's ordinal among the units of the block, in row order
       }
       // segment ordinal inside the query block: virtual parts + unit boundaries passed so far
-      const int ord = (a.vq > 1 ? (int)((row0 * a.vq) / a.s.M) : 0) + (unit - c_first);
+      const int ord = (a.vq > 1 ? (int)((row0 * a.vq) / a.s.M) : 0) + c_first;
       const int part = qb * 4096 + ord;
       if (part != cur_part) {
         flush();
@@ -945,13 +1018,14 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st, con
   ma.n_tile = pl.n_tile; ma.n_qb = pl.n_qb; ma.n_t = pl.n_t; ma.stages = pl.stages; ma.kc = pl.kc;
   ma.merged = pl.merged; ma.ds = pl.ds; ma.kc_total = (pl.merged && !pl.ds) ? 2 * pl.kc : pl.kc;
   ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.q_blk = pl.q_blk; ma.gran = pl.gran; ma.vq = pl.vq;
-  ma.rtot = (long long)pl.n_qb * s.M;
+  ma.split = make_split(s.M, pl.n_qb, pl.ctas / std::max(1, pl.cl), pl.gran);
   ma.dbg = nullptr;
   // Short lists (a thread sees few scores: survivor probability K/n per element stays high) append per lane without
   // warp votes; long scans keep the vote that skips chunks without survivors.  Measured: C1 233 -> 212 us, C2 101.5 -> 99 us.
   static const char* epi_env = getenv("KEMR_MMA_EPI");
   const long long units_run = pl.ctas / std::max(1, pl.cl);
-  const double per_list = (double)ma.rtot / (double)std::max(1ll, units_run) / 2.0 / std::max(1, pl.vq);
+  const double rtot = (double)pl.n_qb * (double)s.M;
+  const double per_list = rtot / (double)std::max(1ll, units_run) / 2.0 / std::max(1, pl.vq);
   ma.epi_variant = epi_env ? atoi(epi_env) : (per_list < 8192.0 ? 2 : 0);
 #ifdef KEMR_DEBUG
   static const bool debug = getenv("KEMR_MMA_DEBUG") != nullptr;
@@ -987,7 +1061,7 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st, con
         if (t > tmax) { tmax = t; cmax = c; }
       }
       fprintf(stderr, "[kemr mma dbg] cl=%d merged=%d vq=%d parts=%d n_tile=%d K=%d ctas=%d tile-equivalents/unit=%.2f stages=%d | producer: wait_empty=%.0f total=%.0f | mma: wait_full=%.0f wait_tempty=%.0f total=%.0f (min %lld @cta %d, max %lld @cta %d; max cta: wait_full=%lld wait_tempty=%lld) | epi(w2): wait_tfull=%.0f fold=%.0f total=%.0f  cycles\n",
-              pl.cl, pl.merged, pl.vq, pl.parts, pl.n_tile, pl.K, pl.ctas, (double)ma.rtot / pl.n_tile / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
+              pl.cl, pl.merged, pl.vq, pl.parts, pl.n_tile, pl.K, pl.ctas, rtot / pl.n_tile / nu, pl.stages, avg[0], avg[1], avg[2], avg[3], avg[4],
               tmin, cmin, tmax, cmax, h[(size_t)cmax * 16 + 2], h[(size_t)cmax * 16 + 3], avg[5], avg[6], avg[7]);
       {
         long long s_min = 1ll << 62, s_max = 0, e_max = 0, e_min = 1ll << 62;

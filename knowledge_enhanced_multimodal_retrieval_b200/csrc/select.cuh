@@ -9,6 +9,8 @@
 
 namespace kemr {
 
+constexpr int kMaxPeers = 8;             // ranks of one NVSwitch box
+
 struct SelectArgs {
   const uint64_t* part_keys;   // [P][Q][Kp]
   int P, Q, K;                 // K = candidates re-scored per query
@@ -32,6 +34,16 @@ struct SelectArgs {
   int32_t* out_flags;          // [Q]
   int max_cand;                // K + max hits per query
   int key_slots;               // select_key_slots(Kp, K)
+  // result exchange over NVLink peer memory (kemr_peer_*): when n_peer > 0 the k result rows of a query are ALSO stored
+  // into every rank's gather buffer (slot of this rank) and a per-query flag is released there -- the all-gather of
+  // the row-sharded search is fused into this kernel (no collective launch in the step)
+  int n_peer;
+  unsigned char* peer_base[kMaxPeers];   // mapped base address of every rank's exchange buffer (own rank: local memory)
+  long long peer_block;        // entries per (parity, rank) block = max_q * max_k
+  long long peer_idx_region;   // byte offset of the idx region inside a buffer
+  long long peer_flag_region;  // byte offset of the flag region
+  int peer_max_q, peer_rank, peer_world;
+  const unsigned int* peer_epoch;        // local device word: the step's epoch (bumped by kemr_peer_begin)
 };
 
 constexpr int kMaxParts = 4096;          // part lists per query the head pass can hold
@@ -255,27 +267,41 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
   }
   __syncthreads();
 
-  // D
+  // D (+ the fused all-gather: the same rows go to this rank's slot of every rank's exchange buffer)
+  unsigned int epoch = 0;
+  size_t peer_o = 0;
+  if (a.n_peer > 0) {
+    epoch = *a.peer_epoch;
+    peer_o = (size_t)(((long long)(epoch & 1u) * a.peer_world + a.peer_rank) * a.peer_block) + (size_t)qi * a.k;
+  }
+  auto emit = [&](int r, double sc, int64_t gi) {
+    const size_t o = (size_t)qi * a.k + r;
+    a.out_score64[o] = sc;
+    if (a.out_score32) a.out_score32[o] = (float)sc;
+    a.out_idx[o] = gi;
+    for (int d = 0; d < a.n_peer; ++d) {
+      reinterpret_cast<double*>(a.peer_base[d])[peer_o + r] = sc;
+      reinterpret_cast<int64_t*>(a.peer_base[d] + a.peer_idx_region)[peer_o + r] = gi;
+    }
+  };
   for (int c = tid; c < n; c += T) {
     const double sc = s_score[c];
     const int32_t rc = s_row[c];
     int r = 0;
     for (int j = 0; j < n; ++j) r += ahead64(s_score[j], s_row[j], sc, rc) ? 1 : 0;
     if (r < a.k) {
-      const size_t o = (size_t)qi * a.k + r;
-      a.out_score64[o] = sc;
-      if (a.out_score32) a.out_score32[o] = (float)sc;
-      a.out_idx[o] = a.idx_base + rc;
+      emit(r, sc, a.idx_base + rc);
       if (r == a.k - 1) s_kth = sc;
     }
   }
-  for (int r = n + tid; r < a.k; r += T) {
-    const size_t o = (size_t)qi * a.k + r;
-    a.out_score64[o] = -INFINITY;
-    if (a.out_score32) a.out_score32[o] = -INFINITY;
-    a.out_idx[o] = -1;
-  }
+  for (int r = n + tid; r < a.k; r += T) emit(r, -INFINITY, -1);
+  if (a.n_peer > 0) __threadfence_system();                  // rows before the flag, at system scope (peer GPUs)
   __syncthreads();
+  if (a.n_peer > 0 && tid < a.n_peer) {
+    unsigned int* flag = reinterpret_cast<unsigned int*>(a.peer_base[tid] + a.peer_flag_region) +
+                         ((size_t)(epoch & 1u) * a.peer_world + a.peer_rank) * a.peer_max_q + qi;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+  }
 
   // E: nothing the scan or the stages above rejected can reach the k-th canonical score
   if (tid == 0) {
@@ -410,9 +436,13 @@ __global__ void rank_hits_kernel(RankFixArgs a, int Q, int64_t M, const int64_t*
 // R per-shard lists of k entries, each already ordered by (score desc, idx asc) with empty slots (idx < 0) at the
 // end.  The global position of an entry is its position in its own list plus, for every other list, the number of
 // entries ahead of it -- a binary search, since the lists are sorted: R*log2(k) steps per entry instead of R*k.
-__global__ void merge_topk_kernel(const double* __restrict__ in_s, const int64_t* __restrict__ in_i,
-                                  int R, int Q, int k, double* __restrict__ out_s,
-                                  int64_t* __restrict__ out_i) {
+// With `flags` (exchange over peer memory) list r of query qi is complete once flags[r * flag_stride + qi] holds the
+// step's epoch: one thread per list waits for it (bounded: a rank that never arrives traps after ~20 s instead of
+// hanging the GPU) before the lists are read.
+__device__ __forceinline__ void merge_lists(const double* in_s, const int64_t* in_i, long long rank_stride,
+                                            int R, int k, double* __restrict__ out_s,
+                                            int64_t* __restrict__ out_i, const unsigned int* flags, long long flag_stride,
+                                            unsigned int epoch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s = reinterpret_cast<double*>(smem_raw);
   int64_t* ix = reinterpret_cast<int64_t*>(s + (size_t)R * k);
@@ -422,12 +452,27 @@ __global__ void merge_topk_kernel(const double* __restrict__ in_s, const int64_t
   const int n = R * k;
   if (threadIdx.x < R) s_len[threadIdx.x] = 0;
   if (threadIdx.x == 0) s_valid = 0;
+  if (flags && threadIdx.x < R) {
+    const unsigned int* f = flags + (size_t)threadIdx.x * flag_stride + qi;
+    unsigned long long t0 = 0;
+    for (unsigned int spins = 0;; ++spins) {
+      unsigned int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v == epoch) break;
+      if ((spins & 0xfffu) == 0xfffu) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (!t0) t0 = t;
+        else if (t - t0 > 20000000000ull) __trap();
+      }
+    }
+  }
   __syncthreads();
   for (int c = threadIdx.x; c < n; c += blockDim.x) {
     const int r = c / k, j = c % k;
-    const size_t o = ((size_t)r * Q + qi) * k + j;
-    s[c] = in_s[o];
-    ix[c] = in_i[o];
+    const size_t o = (size_t)r * rank_stride + (size_t)qi * k + j;
+    s[c] = __ldcg(in_s + o);                 // L2 is the point of coherence for rows a peer GPU stored
+    ix[c] = (int64_t)__ldcg(reinterpret_cast<const long long*>(in_i) + o);
     if (ix[c] >= 0) { atomicAdd(&s_len[r], 1); atomicAdd(&s_valid, 1); }
   }
   __syncthreads();
@@ -452,6 +497,25 @@ __global__ void merge_topk_kernel(const double* __restrict__ in_s, const int64_t
     out_s[(size_t)qi * k + r] = -INFINITY;
     out_i[(size_t)qi * k + r] = -1;
   }
+}
+
+__global__ void merge_topk_kernel(const double* in_s, const int64_t* in_i, long long rank_stride, int R, int Q, int k,
+                                  double* __restrict__ out_s, int64_t* __restrict__ out_i, const unsigned int* flags,
+                                  long long flag_stride, const unsigned int* epoch_ptr) {
+  (void)Q;
+  merge_lists(in_s, in_i, rank_stride, R, k, out_s, out_i, flags, flag_stride, flags ? *epoch_ptr : 0u);
+}
+
+// merge of the lists the ranks pushed into this rank's exchange buffer (kemr_peer_*): the epoch picks the buffer half
+__global__ void merge_peer_kernel(const unsigned char* base, long long idx_region, long long flag_region, long long block,
+                                  int world, int max_q, int Q, int k, double* __restrict__ out_s,
+                                  int64_t* __restrict__ out_i, const unsigned int* epoch_ptr) {
+  (void)Q;
+  const unsigned int epoch = *epoch_ptr;
+  const size_t half = (size_t)(epoch & 1u) * world;
+  merge_lists(reinterpret_cast<const double*>(base) + half * block,
+              reinterpret_cast<const int64_t*>(base + idx_region) + half * block, block, world, k, out_s, out_i,
+              reinterpret_cast<const unsigned int*>(base + flag_region) + half * max_q, max_q, epoch);
 }
 
 }  // namespace kemr

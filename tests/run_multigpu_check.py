@@ -30,6 +30,21 @@ def main():
     wi, ws = engine.scan_topk(q, img, tgt, 0.5, 0.5, alpha, hits, k=10)
     wr = engine.rank_targets(q, img, tgt, torch.from_numpy(s.target_idx).cuda(), 0.5, 0.5, alpha, hits)
     ok = torch.equal(idx, wi) and torch.equal(score, ws) and torch.equal(ranks, wr)
+    # prepared search: result exchange fused into the selection kernel over NVLink peer memory, and the NCCL
+    # all-gather fallback, eager and as a CUDA graph; several steps in a row (the buffers alternate by epoch)
+    wi0, ws0 = engine.scan_topk(q, img, tgt, 0.5, 0.5, k=10)
+    for exchange in ("peer", "nccl"):
+        for graph in (False, True):
+            plan = sg.plan(Q=q.shape[0], k=10, w_a=0.5, w_b=0.5, exchange=exchange, graph=graph)
+            for step in range(4):
+                qs = q if step % 2 == 0 else torch.flip(q, dims=[0])
+                pi, ps = plan.run(qs)
+                want_i, want_s = (wi0, ws0) if step % 2 == 0 else (torch.flip(wi0, dims=[0]), torch.flip(ws0, dims=[0]))
+                good = torch.equal(pi, want_i) and torch.equal(ps, want_s) and plan.uncertified() == 0
+                if not good:
+                    print(f"rank {rank}: plan exchange={exchange} graph={graph} step {step} MISMATCH", flush=True)
+                ok = ok and good
+            plan.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

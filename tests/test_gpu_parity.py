@@ -368,6 +368,63 @@ def test_retrieval_engine_end_to_end(small_set):
         assert fused == want
 
 
+def test_peer_exchange_two_ranks_in_one_process_equals_single_scan(small_set):
+    """The fused result exchange (kemr_peer_*): two ranks emulated in ONE process on one GPU -- each rank's selection
+    kernel stores its rows into BOTH exchange buffers, each merge reads its own buffer.  The steps run one after the
+    other on one stream, so no kernel ever waits for a kernel that is not already complete.  Must equal the
+    single-gallery scan bit for bit, over several epochs (the buffer halves alternate)."""
+    import ctypes as C
+    lib = _lib.load()
+    q, img, tgt = dev(small_set["query"]), dev(small_set["image"]), dev(small_set["target"])
+    Q, M, k = q.shape[0], img.shape[0], 10
+    cut = 71
+    shards = [(img[:cut].contiguous(), tgt[:cut].contiguous(), 0), (img[cut:].contiguous(), tgt[cut:].contiguous(), cut)]
+    hs = []
+    for r in range(2):
+        h = C.c_void_p()
+        _lib.check(lib.kemr_peer_create(r, 2, Q, k, C.byref(h), None))
+        hs.append(h)
+    bases = (C.c_void_p * 2)(*[C.c_void_p(lib.kemr_peer_local_buffer(h)) for h in hs])
+    for h in hs:
+        _lib.check(lib.kemr_peer_connect_pointers(h, bases))
+    st = torch.cuda.current_stream().cuda_stream
+    ws = engine.workspace_for(Q, M, q.shape[1], 16)
+    for step, (wa, wb) in enumerate(((0.5, 0.5), (0.1, 0.9), (1.0, 0.0))):
+        want_i, want_s = engine.scan_topk(q, img, tgt, wa, wb, k=k)
+        outs = []
+        for r, (a, b, base) in enumerate(shards):
+            _lib.check(lib.kemr_peer_begin(hs[r], st))
+            sc = torch.empty((Q, k), dtype=torch.float64, device="cuda")
+            ix = torch.empty((Q, k), dtype=torch.int64, device="cuda")
+            fl = torch.empty((Q,), dtype=torch.int32, device="cuda")
+            engine.scan_topk_raw(q, a, b, wa, wb, 1.0, None, k, 16, engine.DEFAULT_EPS, base, sc, ix, fl, ws)
+        for r in range(2):
+            os_ = torch.empty((Q, k), dtype=torch.float64, device="cuda")
+            oi = torch.empty((Q, k), dtype=torch.int64, device="cuda")
+            _lib.check(lib.kemr_peer_merge(hs[r], Q, k, C.c_void_p(os_.data_ptr()), C.c_void_p(oi.data_ptr()), st))
+            outs.append((oi, os_))
+        for oi, os_ in outs:
+            assert torch.equal(oi, want_i) and torch.equal(os_, want_s), f"step {step}"
+    torch.cuda.synchronize()
+    for h in hs:
+        lib.kemr_peer_destroy(h)
+
+
+def test_prepared_sharded_search_on_one_rank(small_set):
+    """distributed.SearchPlan with a world of one (peer exchange with itself / plain copy), eager and as a CUDA graph."""
+    from knowledge_enhanced_multimodal_retrieval_b200.distributed import CudaLocal, ShardedGallery
+    q = dev(small_set["query"])
+    sg = ShardedGallery(CudaLocal(small_set["image"], small_set["target"]), small_set["image"].shape[0])
+    want_i, want_s = engine.scan_topk(q, sg.local.image, sg.local.target, 0.3, 0.7, k=10)
+    for exchange in ("peer", "nccl"):
+        for graph in (False, True):
+            plan = sg.plan(Q=q.shape[0], k=10, w_a=0.3, w_b=0.7, exchange=exchange, graph=graph)
+            for _ in range(3):
+                pi, ps = plan.run(q)
+                assert torch.equal(pi, want_i) and torch.equal(ps, want_s) and plan.uncertified() == 0
+            plan.close()
+
+
 def test_sharded_index_maps_global_ids_to_its_own_uuid_slice(small_set):
     """A shard with idx_base > 0 returns GLOBAL row ids; CLIPRetriever.search must look them up in the shard's own
     uuid slice."""

