@@ -255,6 +255,19 @@ int kemr_hits_build_csr(const int64_t* list_rowptr, const int64_t* list_rows, co
                         int64_t* out_rowptr, int32_t* out_col, double* out_bonus, int64_t* out_max_per_query,
                         void* workspace, size_t workspace_bytes, kemr_stream_t stream);
 
+/* CSR -> CSR on the device: output query i is input query query_sel[i] (NULL: the same queries), entries whose column
+ * lies in [col_lo, col_hi) are kept in order and re-based to col - col_lo.  The per-shard hit lists of a row-sharded
+ * gallery and the subset of queries a certificate sends back for a wider selection.
+ * out_col / out_bonus need room for the input's nnz; workspace as for kemr_hits_build_csr (Q = Q_out). */
+int kemr_hits_filter_csr(const int64_t* rowptr, const int32_t* col, const double* bonus, const int64_t* query_sel,
+                         int Q_out, int64_t col_lo, int64_t col_hi,
+                         int64_t* out_rowptr, int32_t* out_col, double* out_bonus, int64_t* out_max_per_query,
+                         void* workspace, size_t workspace_bytes, kemr_stream_t stream);
+/* bonus of every query's own target column (0 where the target is not a hit): the KG term of the target's score in
+ * the rank path (fusion.py:83 evaluated at column i of row i). */
+int kemr_hits_target_bonus(const int64_t* rowptr, const int32_t* col, const double* bonus, int Q,
+                           const int64_t* target_col, double* out_bonus, kemr_stream_t stream);
+
 /* uuid -> gallery row map on the HOST (fusion.py:62 artefact_uuid_to_idx).  Keys are passed as one byte blob plus
  * n+1 offsets.  A repeated uuid keeps its last row, like the reference's dict.  Lookup returns -1 for unknown keys;
  * normalize_uri != 0 first cuts the key to its last '/' segment (fusion.py:76, text2sparql_retrieval.py:57). */

@@ -25,6 +25,7 @@ EXPORTS = (
     "kemr_store_write", "kemr_store_info", "kemr_store_load", "kemr_debug_mma_plan", "kemr_set_phase_stamps",
     "kemr_peer_create", "kemr_peer_connect", "kemr_peer_connect_pointers", "kemr_peer_local_buffer", "kemr_peer_destroy",
     "kemr_peer_begin", "kemr_peer_merge", "kemr_merge_topk_strided",
+    "kemr_hits_filter_csr", "kemr_hits_target_bonus",
 )
 
 
@@ -59,6 +60,8 @@ def _declare(lib):
     lib.kemr_hits_workspace_bytes.restype = sz
     lib.kemr_hits_workspace_bytes.argtypes = [i32]
     lib.kemr_hits_build_csr.argtypes = [p, p, p, i32, i64, i64, i32, p, p, p, p, p, sz, p]
+    lib.kemr_hits_filter_csr.argtypes = [p, p, p, p, i32, i64, i64, p, p, p, p, p, sz, p]
+    lib.kemr_hits_target_bonus.argtypes = [p, p, p, i32, p, p, p]
     lib.kemr_idmap_create.argtypes = [p, p, i64, C.POINTER(p)]
     lib.kemr_idmap_destroy.argtypes = [p]
     lib.kemr_idmap_lookup.argtypes = [p, p, p, i64, i32, p]

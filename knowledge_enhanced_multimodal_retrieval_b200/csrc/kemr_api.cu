@@ -335,7 +335,7 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
     // small batches: scan + selection in ONE launch (scan_stream.cuh)
     StreamArgs sa{};
     sa.s = a; sa.sel = s;
-    sa.stage_bytes = (unsigned)((size_t)G * kStreamConsumers * D * 2);
+    sa.stage_bytes = (unsigned)((size_t)G * kStreamRows * D * 2);
     const size_t tail = stream_smem_bytes(0, 0, pl.QB, 0);
     sa.stages = (int)std::min<size_t>(kStreamMaxStages, ((size_t)kSmemBudget - 1024 - tail) / sa.stage_bytes);
     if (sa.stages < 2) return fail(KEMR_ERR_UNSUPPORTED, "stream kernel: a stage of %u bytes does not fit twice", sa.stage_bytes);
@@ -349,7 +349,13 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
     dim3 grid(pl.P, pl.groups);
 #define KEMR_STREAM(QBV, CHV)                                                                                     \
   do {                                                                                                            \
-    CUDA_TRY(cudaFuncSetAttribute(scan_stream_kernel<QBV, CHV, CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+    /* the attribute sticks to the function on a device: set it once per (instantiation, device, size) */         \
+    static thread_local int attr_dev = -1;                                                                        \
+    static thread_local size_t attr_smem = 0;                                                                     \
+    if (dv.dev != attr_dev || dyn > attr_smem) {                                                                  \
+      CUDA_TRY(cudaFuncSetAttribute(scan_stream_kernel<QBV, CHV, CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+      attr_dev = dv.dev; attr_smem = dyn;                                                                         \
+    }                                                                                                             \
     scan_stream_kernel<QBV, CHV, CHV><<<grid, kStreamThreads, dyn, st>>>(sa);                                     \
   } while (0)
 #define KEMR_STREAM_CH(QBV) switch (np) { case 1: KEMR_STREAM(QBV, 1); break; case 2: KEMR_STREAM(QBV, 2); break; \
@@ -804,7 +810,7 @@ extern "C" int kemr_peer_merge(kemr_peer_t* p, int Q, int k, double* out_score64
   const size_t smem = (size_t)p->world * k * 16;
   if (smem > 200 * 1024) return fail(KEMR_ERR_ARG, "peer_merge: world*k too large");
   if (smem > 48 * 1024)
-    CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(merge_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // both parities are passed as one base: the kernel picks the epoch's half through the rank stride arithmetic below
   const size_t block = (size_t)p->max_q * p->max_k;
   merge_peer_kernel<<<Q, 256, smem, S(stream)>>>(p->local, (long long)p->idx_region, (long long)p->flag_region, (long long)block,
@@ -968,6 +974,35 @@ extern "C" int kemr_hits_build_csr(const int64_t* list_rowptr, const int64_t* li
   hits_fill_kernel<<<blocks, kHitsWarpsPerBlock * 32, 0, st>>>(list_rowptr, list_rows, bonus_per_query, Q, row_lo, row_hi,
                                                                  sum_repeats, out_rowptr, out_col, out_bonus);
   LAUNCH_CHECK("hits_fill_kernel");
+  return KEMR_OK;
+}
+
+extern "C" int kemr_hits_filter_csr(const int64_t* rowptr, const int32_t* col, const double* bonus, const int64_t* query_sel,
+                                    int Q_out, int64_t col_lo, int64_t col_hi, int64_t* out_rowptr, int32_t* out_col,
+                                    double* out_bonus, int64_t* out_max_per_query, void* workspace, size_t workspace_bytes,
+                                    kemr_stream_t stream) {
+  if (!rowptr || !out_rowptr || !out_max_per_query || Q_out <= 0 || col_hi < col_lo)
+    return fail(KEMR_ERR_ARG, "hits_filter_csr: bad argument");
+  if (!workspace || workspace_bytes < kemr_hits_workspace_bytes(Q_out)) return fail(KEMR_ERR_WORKSPACE, "hits_filter_csr: workspace too small");
+  int64_t* count = reinterpret_cast<int64_t*>(workspace);
+  cudaStream_t st = S(stream);
+  const int blocks = (Q_out + kHitsWarpsPerBlock - 1) / kHitsWarpsPerBlock;
+  hits_filter_count_kernel<<<blocks, kHitsWarpsPerBlock * 32, 0, st>>>(rowptr, col, query_sel, Q_out, col_lo, col_hi, count);
+  LAUNCH_CHECK("hits_filter_count_kernel");
+  hits_scan_kernel<<<1, 1024, 0, st>>>(count, Q_out, out_rowptr, out_max_per_query);
+  LAUNCH_CHECK("hits_scan_kernel");
+  hits_filter_fill_kernel<<<blocks, kHitsWarpsPerBlock * 32, 0, st>>>(rowptr, col, bonus, query_sel, Q_out, col_lo, col_hi,
+                                                                        out_rowptr, out_col, out_bonus);
+  LAUNCH_CHECK("hits_filter_fill_kernel");
+  return KEMR_OK;
+}
+
+extern "C" int kemr_hits_target_bonus(const int64_t* rowptr, const int32_t* col, const double* bonus, int Q,
+                                      const int64_t* target_col, double* out_bonus, kemr_stream_t stream) {
+  if (!rowptr || !target_col || !out_bonus || Q <= 0) return fail(KEMR_ERR_ARG, "hits_target_bonus: bad argument");
+  const int blocks = (Q + kHitsWarpsPerBlock - 1) / kHitsWarpsPerBlock;
+  hits_target_bonus_kernel<<<blocks, kHitsWarpsPerBlock * 32, 0, S(stream)>>>(rowptr, col, bonus, Q, target_col, out_bonus);
+  LAUNCH_CHECK("hits_target_bonus_kernel");
   return KEMR_OK;
 }
 

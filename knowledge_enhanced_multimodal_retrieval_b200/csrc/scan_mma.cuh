@@ -88,7 +88,6 @@ struct MmaPlan {
   int cl = 1;             // CTAs per cluster: 1, 2 (one pair) or 4 (two pairs on adjacent query blocks sharing the gallery tile by TMA multicast)
   int gran = 32;          // unit boundaries are multiples of this many rows inside a query block (n_tile: no partial tiles)
   int s_full = 0;         // full stripes (one unit per stripe and query block)
-  long long L = 0;        // rows per full stripe
   int vq = 1;             // virtual parts per query block: lists are flushed and restarted at these boundaries
   int all_slots = 0;      // 1: every part slot of every query row is written (no memset needed)
   int two = 0;            // 1: two accumulators (T2I, T2T) with their own weights
@@ -121,14 +120,21 @@ __host__ __device__ inline int unit_of(long long rtot, int units, long long len,
   return lo;
 }
 
-// How the units share the work (see the header comment): `s_full` stripes of `L` rows, one unit per (stripe, block);
-// the rows from s_full * L on are the remainder stripe, shared by the units past s_full * n_qb.
+// How the units share the work (see the header comment): `s_full` = floor(units / n_qb) stripes, one unit per (stripe,
+// block); stripe s starts at row floor_gran(s * n_qb * M / units) (cumulative rounding: stripe lengths differ by at
+// most `gran`); the rows from the end of the last full stripe on are the remainder stripe, shared by the units past
+// s_full * n_qb.  Without remainder units the last full stripe ends at M.
 struct WorkSplit {
   long long M;        // gallery rows
-  long long L;        // rows per full stripe (multiple of gran); 0 when there is no full stripe
   int n_qb, units, s_full, gran;
   __host__ __device__ int full_units() const { return s_full * n_qb; }
-  __host__ __device__ long long rem_base() const { return (long long)s_full * L < M ? (long long)s_full * L : M; }
+  __host__ __device__ long long stripe_begin(int s) const {
+    if (s >= s_full && units == s_full * n_qb) return M;
+    const long long x = (long long)s * n_qb * M / units;
+    const long long b = x - x % gran;
+    return b < M ? b : M;
+  }
+  __host__ __device__ long long rem_base() const { return stripe_begin(s_full); }
   __host__ __device__ long long rem_len() const { return M - rem_base(); }
 };
 // One unit's walk: positions [p_lo, p_hi) of a flat space of blocks of `mod` rows; position p is row base + p % mod of
@@ -139,8 +145,8 @@ __host__ __device__ inline UnitWalk unit_walk(const WorkSplit& w, int u) {
   UnitWalk k;
   if (u < w.full_units()) {
     const int s = u / w.n_qb;
-    k.base = (long long)s * w.L;
-    const long long len = (w.M - k.base < w.L ? w.M - k.base : w.L);
+    k.base = w.stripe_begin(s);
+    const long long len = w.stripe_begin(s + 1) - k.base;
     k.mod = len > 0 ? len : 1; k.p_lo = 0; k.p_hi = len > 0 ? len : 0; k.qb0 = u % w.n_qb;
   } else {
     const int nr = w.units - w.full_units(), j = u - w.full_units();
@@ -175,13 +181,6 @@ inline WorkSplit make_split(long long M, int n_qb, int units, int gran) {
   WorkSplit w;
   w.M = M; w.n_qb = n_qb; w.units = units; w.gran = gran;
   w.s_full = units / n_qb;
-  w.L = 0;
-  if (w.s_full > 0) {
-    const int rem_units = units - w.s_full * n_qb;
-    // equal work for full and remainder units: L = n_qb * M / units; without remainder units the stripes must cover M
-    const long long want = rem_units > 0 ? ((long long)n_qb * M + units - 1) / units : (M + w.s_full - 1) / w.s_full;
-    w.L = (want + gran - 1) / gran * gran;
-  }
   return w;
 }
 
@@ -224,11 +223,11 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
   // Partial tiles (MMA with a smaller N, 16-row TMA boxes) exist for the single-accumulator kernels of one CTA or one
   // pair; quads and the two-accumulator kernels keep tile-aligned boundaries.
   static const bool no_partial = getenv("KEMR_MMA_NO_PARTIAL") != nullptr;     // experiments: tile-aligned boundaries everywhere
-  p->gran = (quad || p->two || no_partial) ? p->n_tile : 32;
+  p->gran = (quad || p->two || no_partial) ? p->n_tile : (p->pair ? 32 : 16);      // MMA N: multiples of 16 (one CTA) / 32 (pair)
   const int64_t rtot = (int64_t)p->n_qb * M;
   const int nu = (int)std::min<int64_t>(units, std::max<int64_t>(1, rtot / p->n_tile));   // at least a tile's worth of rows per unit
   const WorkSplit ws = make_split(M, p->n_qb, nu, p->gran);
-  p->s_full = ws.s_full; p->L = ws.L;
+  p->s_full = ws.s_full;
   int parts = 1;
   bool same = true;
   for (int qb = 0; qb < p->n_qb; ++qb) {
@@ -270,8 +269,10 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
       const int segs = seg == span ? span : seg + span - 1;            // list slots when virtual parts are added
       if (2 * segs > kPlanMaxParts) break;
       if (overflow_prob(K, 2 * seg, Kc) <= 2e-6) {
-        const long long keys = 2ll * segs * Kc * Kc;
-        if (keys < best_keys) { best_keys = keys; Ksel = Kc; vq = seg == span ? 1 : seg; }
+        // cost ~ keys the selection reads (L * K) times the insert cost (~K); virtual parts restart the lists (cold
+        // thresholds again: C1 went 218 -> 254 us with 16 restarts per block), so they must win by a clear margin
+        const long long keys = 2ll * segs * Kc * Kc * (seg == span ? 4 : 5) / 4;
+        if (keys < best_keys || (keys == best_keys && seg == span)) { best_keys = keys; Ksel = Kc; vq = seg == span ? 1 : seg; }
         break;
       }
       if (seg >= p->n_t) break;                    // cannot cut finer than one tile per segment
@@ -435,7 +436,7 @@ struct MmaArgs {
   int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, gran, vq;
   WorkSplit split;  // how the units share the (query block, gallery row) work
   long long* dbg;   // optional [ctas][16] cycle counters + stage trace (debug build, KEMR_MMA_DEBUG=1)
-  int epi_variant;  // 1 = per-lane predicated appends without warp votes (short lists), 2 = the same on RAW accumulators; KEMR_MMA_EPI overrides
+  int epi_variant;  // short lists: 3 = survivor mask + select-tree extraction on RAW accumulators (default), 2 = predicated appends on raw accumulators, 1 = on weighted scores; 0 = max tree + vote (long scans); KEMR_MMA_EPI overrides
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -578,7 +579,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       int tr = 0;
       KEMR_FOR_TILES({
         // rows of the gallery chunk this CTA stages: a full tile, or (single accumulator) the rows left, to 32
-        const int nmma = partial_ok ? min(256, (ncols + 31) & ~31) : 256;
+        const int nmma = partial_ok ? min(256, (ncols + (PAIR ? 31 : 15)) & (PAIR ? ~31 : ~15)) : 256;
         const int nb = PAIR ? (TWO ? 128 : nmma >> 1) : (TWO ? 128 : nmma);
         const bool whole = QUAD || nb == (int)b_box;
         const uint32_t g_bytes = (uint32_t)nb * 128u * ((TWO && !PAIR) || ds ? 2u : 1u);     // gallery bytes per CTA and stage
@@ -653,7 +654,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int buf = (int)(it & 1);
         const uint32_t bphase = (uint32_t)((it >> 1) & 1);
         // a partial tile (end of this unit's range) fills only the accumulator columns of its rows
-        const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, partial_ok ? min(256, (ncols + 31) & ~31) : 256);
+        const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, partial_ok ? min(256, (ncols + (PAIR ? 31 : 15)) & (PAIR ? ~31 : ~15)) : 256);
         mbar_wait_dbg(&tempty_bar[buf], bphase ^ 1, dbg, w_tempty);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
@@ -807,6 +808,37 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (TWO) tmem_ld16(acc0 + 128u + (uint32_t)c0, rb);
       };
       auto process = [&](int c0, const uint32_t (&ra)[16], const uint32_t (&rb)[16]) {
+        if (!TWO && mode == kModeTopk && a.epi_variant == 3 && w0 > 0.f) {
+          // One compare + one predicated OR per score builds a survivor mask; the (few) survivors are then pulled
+          // out of the registers with a select tree, lane by lane in lock-step, and appended.  The straight-line
+          // part costs 2 instructions per score instead of the ~7 of a predicated append per score (ncu, C1: 16.6
+          // thread-instructions per score overall, epilogue 2.1x slower than the MMAs of a 512-d tile).
+          uint32_t mask = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (__uint_as_float(ra[j]) > thr_raw) mask |= 1u << j;
+          if (!full_tile) { const int nv = ncols - c0; mask &= nv >= 16 ? 0xffffu : ((1u << (nv > 0 ? nv : 0)) - 1u); }
+          if (__any_sync(0xffffffffu, mask != 0u)) {
+            const uint32_t r = (uint32_t)(row0 + c0);
+            do {
+              if (mask) {
+                const int j = __ffs((int)mask) - 1;
+                mask &= mask - 1u;
+                const uint32_t a0 = (j & 1) ? ra[1] : ra[0], a1 = (j & 1) ? ra[3] : ra[2], a2 = (j & 1) ? ra[5] : ra[4],
+                               a3 = (j & 1) ? ra[7] : ra[6], a4 = (j & 1) ? ra[9] : ra[8], a5 = (j & 1) ? ra[11] : ra[10],
+                               a6 = (j & 1) ? ra[13] : ra[12], a7 = (j & 1) ? ra[15] : ra[14];
+                const uint32_t b0 = (j & 2) ? a1 : a0, b1 = (j & 2) ? a3 : a2, b2 = (j & 2) ? a5 : a4, b3 = (j & 2) ? a7 : a6;
+                const uint32_t c0_ = (j & 4) ? b1 : b0, c1_ = (j & 4) ? b3 : b2;
+                const float x = __uint_as_float((j & 8) ? c1_ : c0_);
+                st_shared_v2(my_buf + (uint32_t)bcnt * (kEpiThreads * 8u), w0 * x, r + (uint32_t)j);
+                ++bcnt;
+              }
+              if (__any_sync(0xffffffffu, bcnt >= kBufCap)) fold();
+            } while (__any_sync(0xffffffffu, mask != 0u));
+            if (__any_sync(0xffffffffu, bcnt >= kBufTrigger)) fold();
+          }
+          return;
+        }
         if (!TWO && mode == kModeTopk && a.epi_variant == 2 && w0 > 0.f) {
           const uint32_t r = (uint32_t)(row0 + c0);
           const int nv = full_tile ? 16 : ncols - c0;            // columns of this chunk inside the gallery
@@ -1026,7 +1058,7 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st, con
   const long long units_run = pl.ctas / std::max(1, pl.cl);
   const double rtot = (double)pl.n_qb * (double)s.M;
   const double per_list = rtot / (double)std::max(1ll, units_run) / 2.0 / std::max(1, pl.vq);
-  ma.epi_variant = epi_env ? atoi(epi_env) : (per_list < 8192.0 ? 2 : 0);
+  ma.epi_variant = epi_env ? atoi(epi_env) : (per_list < 8192.0 ? 3 : 0);
 #ifdef KEMR_DEBUG
   static const bool debug = getenv("KEMR_MMA_DEBUG") != nullptr;
 #else

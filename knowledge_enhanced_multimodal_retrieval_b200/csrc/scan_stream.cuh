@@ -4,9 +4,11 @@
 // One persistent CTA per SM owns a contiguous range of gallery rows.  A producer warp streams that range -- which is
 // one contiguous byte range per gallery -- through a ring of shared-memory stages with bulk asynchronous copies
 // (cp.async.bulk -> UBLKCP, completion on an mbarrier), so hundreds of KB per SM are in flight without costing a
-// register.  Eight consumer warps take one row of a stage each: conflict-free 16-byte shared-memory reads, fp32 FMAs
-// against the queries held in registers (fusion weights applied to the per-lane partial sums, so T2I + T2T cost one
-// shuffle tree), and lane 0 appends (score, row) keys that beat the CTA's running threshold to a candidate buffer.
+// register.  Eight consumer warps take two rows of a 16-row stage each: conflict-free 16-byte shared-memory reads,
+// fp32 FMAs in independent chains against the queries held in registers (fusion weights applied to the per-lane
+// partial sums, so T2I + T2T cost one reduction), ONE transposed shuffle reduction for all (row, query) sums of the
+// warp (2..8 values: 5..9 shuffles instead of 5 per value), and the lanes that end up holding a sum append (score,
+// row) keys that beat the CTA's running threshold to a candidate buffer.
 // Nothing is sorted while rows stream: the buffer is cut back to its K best by counting only when it fills (never,
 // for a 43 k-row gallery) and once at the end, which leaves one K-entry list per CTA and query.
 // The last CTA to finish (device-wide arrival counter) then runs the selection stage of select.cuh in the same
@@ -19,11 +21,13 @@
 
 namespace kemr {
 
-constexpr int kStreamConsumers = 8;                       // consumer warps == rows per stage
+constexpr int kStreamConsumers = 8;                       // consumer warps
+constexpr int kStreamRW = 2;                              // rows per consumer warp and stage
+constexpr int kStreamRows = kStreamConsumers * kStreamRW; // rows per stage
 constexpr int kStreamThreads = (kStreamConsumers + 1) * 32;
 constexpr int kStreamWarps = kStreamConsumers + 1;
 constexpr int kStreamCand = 1024;                         // candidate keys per query a CTA can hold between cuts
-constexpr int kStreamCheck = 32;                          // stages between two looks at the buffer fill (<= 256 appends)
+constexpr int kStreamCheck = 16;                          // stages between two looks at the buffer fill (<= 256 appends)
 constexpr int kStreamMaxStages = 12;
 
 struct StreamArgs {
@@ -32,7 +36,7 @@ struct StreamArgs {
   unsigned int* done;       // [groups] arrival counters, zero on entry, reset by the last CTA
   long long* stamps;        // optional [4] globaltimer stamps of group 0: first CTA start, last scan end, select end
   int stages;               // ring depth
-  unsigned int stage_bytes; // G * 8 rows * D * 2
+  unsigned int stage_bytes; // G * kStreamRows * D * 2
   unsigned int tail_off;    // offset of the barriers / candidate buffers behind max(ring, selection scratch)
 };
 
@@ -68,6 +72,44 @@ __device__ __forceinline__ void stream_cut(uint64_t* cand, uint64_t* best, int n
   }
 }
 
+// Sum N per-lane values over the warp at once: every step halves the payload (lanes with the step's bit set keep the
+// upper half) until one value per lane is left, then plain butterfly steps.  Lane l returns the total of value
+// stream_value_of<N>(l); the lanes whose low bits differ hold copies.
+template <int N>
+__device__ __forceinline__ float stream_reduce(float (&v)[N], int lane) {
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int step = 16 >> j;
+    constexpr int kFull = 0;
+    (void)kFull;
+    const int nn = N >> (j + 1);                             // values kept after this step (0: already down to one)
+    if (nn >= 1) {
+      const bool up = (lane & step) != 0;
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i) {
+        if (i < nn) {
+          const float send = up ? v[i] : v[i + nn];
+          const float keep = up ? v[i + nn] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+      }
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], step);
+    }
+  }
+  return v[0];
+}
+template <int N>
+__device__ __forceinline__ int stream_value_of(int lane) {
+  int idx = 0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int nn = N >> (j + 1);
+    if (nn >= 1 && (lane & (16 >> j))) idx += nn;
+  }
+  return idx;
+}
+
 template <int QB, int CH, int NP>
 __global__ void __launch_bounds__(kStreamThreads, 1) scan_stream_kernel(StreamArgs a) {
   extern __shared__ __align__(128) unsigned char smem_stream[];
@@ -89,10 +131,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) scan_stream_kernel(StreamAr
   const int64_t r0 = (a.s.M * (int64_t)blockIdx.x) / P;
   const int64_t r1 = (a.s.M * (int64_t)(blockIdx.x + 1)) / P;
   const int nrows = (int)(r1 - r0);
-  const int niter = (nrows + kStreamConsumers - 1) / kStreamConsumers;
+  const int niter = (nrows + kStreamRows - 1) / kStreamRows;
   const int K = a.s.K;
   const uint32_t row_bytes = (uint32_t)a.s.D * 2u;
-  const uint32_t gal_bytes = kStreamConsumers * row_bytes;     // one gallery's share of a stage
+  const uint32_t gal_bytes = kStreamRows * row_bytes;          // one gallery's share of a stage
 
   if (a.stamps && group == 0 && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(a.stamps), ptx::globaltimer());
   if (threadIdx.x == 0) {
@@ -108,8 +150,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) scan_stream_kernel(StreamAr
     for (int it = 0; it < niter; ++it) {
       ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
       if (ptx::elect_one()) {
-        const int64_t row = r0 + (int64_t)it * kStreamConsumers;
-        const uint32_t n = (uint32_t)min((int64_t)kStreamConsumers, r1 - row);
+        const int64_t row = r0 + (int64_t)it * kStreamRows;
+        const uint32_t n = (uint32_t)min((int64_t)kStreamRows, r1 - row);
         const uint32_t bytes = n * row_bytes;
         const uint32_t dst = ptx::smem_u32(smem + (size_t)stage * a.stage_bytes);
         ptx::mbar_expect_tx(&full_bar[stage], bytes * (uint32_t)a.s.G);
@@ -143,67 +185,77 @@ __global__ void __launch_bounds__(kStreamThreads, 1) scan_stream_kernel(StreamAr
       wg[qq][0] = a.s.w[0]; wg[qq][1] = a.s.w[1];
       if (a.s.wq[0] && qq < nq) { wg[qq][0] = a.s.wq[0][q0 + qq]; wg[qq][1] = a.s.wq[1][q0 + qq]; }
     }
+    constexpr int NV = kStreamRW * QB;                          // (row, query) sums per warp and stage
+    const int my_val = stream_value_of<NV>(lane);               // the sum this lane holds after the reduction
+    const bool my_turn = (lane & (32 / NV - 1)) == 0;           // one lane per sum appends
     int stage = 0; uint32_t phase = 0;
     for (int it = 0; it < niter; ++it) {
       ptx::mbar_wait(&full_bar[stage], phase);
-      const int64_t row = r0 + (int64_t)it * kStreamConsumers + warp;
-      if (row < r1) {
-        const unsigned char* srow = smem + (size_t)stage * a.stage_bytes + (size_t)warp * row_bytes;
-        float s[QB];
+      const int64_t row_w = r0 + (int64_t)it * kStreamRows + (int64_t)warp * kStreamRW;     // first row of this warp
+      float v[NV];
 #pragma unroll
-        for (int qq = 0; qq < QB; ++qq) s[qq] = 0.f;
+      for (int i = 0; i < NV; ++i) v[i] = 0.f;
+      if (row_w < r1) {
+        const unsigned char* sw = smem + (size_t)stage * a.stage_bytes + (size_t)warp * kStreamRW * row_bytes;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (g < a.s.G) {
-            float acc[QB];
+            float acc[kStreamRW][QB][2];                            // two independent chains per (row, query)
 #pragma unroll
-            for (int qq = 0; qq < QB; ++qq) acc[qq] = 0.f;
+            for (int r = 0; r < kStreamRW; ++r)
+#pragma unroll
+              for (int qq = 0; qq < QB; ++qq) { acc[r][qq][0] = 0.f; acc[r][qq][1] = 0.f; }
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
               const int chunk = lane + 32 * c;
-              uint4 v = make_uint4(0, 0, 0, 0);
-              if (chunk < nchunk) v = *reinterpret_cast<const uint4*>(srow + (size_t)g * gal_bytes + (size_t)chunk * 16);
-              const float x0 = bf16_lo(v.x), x1 = bf16_hi(v.x), x2 = bf16_lo(v.y), x3 = bf16_hi(v.y);
-              const float x4 = bf16_lo(v.z), x5 = bf16_hi(v.z), x6 = bf16_lo(v.w), x7 = bf16_hi(v.w);
+              if (chunk < nchunk) {
 #pragma unroll
-              for (int qq = 0; qq < QB; ++qq) {
-                float t = acc[qq];
-                t = fmaf(x0, qr[qq][c][0], t); t = fmaf(x1, qr[qq][c][1], t);
-                t = fmaf(x2, qr[qq][c][2], t); t = fmaf(x3, qr[qq][c][3], t);
-                t = fmaf(x4, qr[qq][c][4], t); t = fmaf(x5, qr[qq][c][5], t);
-                t = fmaf(x6, qr[qq][c][6], t); t = fmaf(x7, qr[qq][c][7], t);
-                acc[qq] = t;
+                for (int r = 0; r < kStreamRW; ++r) {
+                  const uint4 x = *reinterpret_cast<const uint4*>(sw + (size_t)g * gal_bytes + (size_t)r * row_bytes + (size_t)chunk * 16);
+                  const float x0 = bf16_lo(x.x), x1 = bf16_hi(x.x), x2 = bf16_lo(x.y), x3 = bf16_hi(x.y);
+                  const float x4 = bf16_lo(x.z), x5 = bf16_hi(x.z), x6 = bf16_lo(x.w), x7 = bf16_hi(x.w);
+#pragma unroll
+                  for (int qq = 0; qq < QB; ++qq) {
+                    float t0 = acc[r][qq][0], t1 = acc[r][qq][1];
+                    t0 = fmaf(x0, qr[qq][c][0], t0); t1 = fmaf(x1, qr[qq][c][1], t1);
+                    t0 = fmaf(x2, qr[qq][c][2], t0); t1 = fmaf(x3, qr[qq][c][3], t1);
+                    t0 = fmaf(x4, qr[qq][c][4], t0); t1 = fmaf(x5, qr[qq][c][5], t1);
+                    t0 = fmaf(x6, qr[qq][c][6], t0); t1 = fmaf(x7, qr[qq][c][7], t1);
+                    acc[r][qq][0] = t0; acc[r][qq][1] = t1;
+                  }
+                }
               }
             }
 #pragma unroll
-            for (int qq = 0; qq < QB; ++qq) s[qq] = fmaf(wg[qq][g], acc[qq], s[qq]);
-          }
-        }
-        // this warp is done reading the stage: hand it back before the reductions
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+            for (int r = 0; r < kStreamRW; ++r)
 #pragma unroll
-        for (int qq = 0; qq < QB; ++qq) {
-          const float sc = warp_sum(s[qq]);
-          if (lane == 0 && qq < nq) {
-            const uint64_t key = make_key(sc, (uint32_t)row);
-            if (key > s_thr[qq]) {
-              const unsigned int slot = atomicAdd(&s_cnt[qq], 1u);
-              cand[(size_t)qq * kStreamCand + slot] = key;          // the fill check below keeps slot < kStreamCand
-            }
+              for (int qq = 0; qq < QB; ++qq)
+                v[r * QB + qq] = fmaf(wg[qq][g], acc[r][qq][0] + acc[r][qq][1], v[r * QB + qq]);
           }
         }
-      } else {
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+      }
+      // this warp is done reading the stage: hand it back before the reduction
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+      const float sc = stream_reduce<NV>(v, lane);
+      {
+        const int r = my_val / QB, qq = my_val % QB;
+        const int64_t row = row_w + r;
+        if (my_turn && row < r1 && qq < nq) {
+          const uint64_t key = make_key(sc, (uint32_t)row);
+          if (key > s_thr[qq]) {
+            const unsigned int slot = atomicAdd(&s_cnt[qq], 1u);
+            cand[(size_t)qq * kStreamCand + slot] = key;              // the fill check below keeps slot < kStreamCand
+          }
+        }
       }
       if (++stage == a.stages) { stage = 0; phase ^= 1; }
       if ((it + 1) % kStreamCheck == 0 && it + 1 < niter) {
-        // at most kStreamCheck * 8 keys per query arrived since the last look
+        // at most kStreamCheck * kStreamRows keys per query arrived since the last look
         ptx::consumer_bar();
         bool cut = false;
 #pragma unroll
-        for (int qq = 0; qq < QB; ++qq) cut = cut || s_cnt[qq] > (unsigned)(kStreamCand - kStreamCheck * kStreamConsumers - 8);
+        for (int qq = 0; qq < QB; ++qq) cut = cut || s_cnt[qq] > (unsigned)(kStreamCand - kStreamCheck * kStreamRows - kStreamRows);
         if (cut) {
           for (int qq = 0; qq < nq; ++qq)
             stream_cut(cand + (size_t)qq * kStreamCand, best + (size_t)qq * kMaxKSel, (int)s_cnt[qq], K, ctid);

@@ -89,4 +89,63 @@ __global__ void hits_fill_kernel(const int64_t* __restrict__ list_rowptr, const 
   }
 }
 
+// ------------------------------------------------------------------ CSR -> CSR: query subset and / or row shard
+// out query i = in query sel[i] (sel == null: identity); entries with col in [lo, hi) survive, re-based to col - lo,
+// order kept.  One warp per output query; used for the per-shard CSR of a row-sharded gallery (SURVEY section 8e:
+// "split each query's hit list by shard") and for the re-run of uncertified queries.
+__global__ void hits_filter_count_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                         const int64_t* __restrict__ sel, int Q_out, int64_t lo, int64_t hi,
+                                         int64_t* __restrict__ out_count) {
+  const int lane = threadIdx.x & 31;
+  const int qo = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (qo >= Q_out) return;
+  const int64_t qi = sel ? sel[qo] : qo;
+  const int64_t b = rowptr[qi], e = rowptr[qi + 1];
+  int c = 0;
+  for (int64_t i = b + lane; i < e; i += 32) { const int64_t x = col[i]; c += (x >= lo && x < hi) ? 1 : 0; }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) out_count[qo] = c;
+}
+__global__ void hits_filter_fill_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                        const double* __restrict__ bonus, const int64_t* __restrict__ sel, int Q_out,
+                                        int64_t lo, int64_t hi, const int64_t* __restrict__ out_rowptr,
+                                        int32_t* __restrict__ out_col, double* __restrict__ out_bonus) {
+  const int lane = threadIdx.x & 31;
+  const int qo = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (qo >= Q_out) return;
+  const int64_t qi = sel ? sel[qo] : qo;
+  const int64_t b = rowptr[qi], e = rowptr[qi + 1];
+  int64_t w = out_rowptr[qo];
+  for (int64_t i0 = b; i0 < e; i0 += 32) {
+    const int64_t i = i0 + lane;
+    const int64_t x = i < e ? (int64_t)col[i] : -1;
+    const bool keep = i < e && x >= lo && x < hi;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int64_t o = w + __popc(m & ((1u << lane) - 1u));
+      out_col[o] = (int32_t)(x - lo);
+      out_bonus[o] = bonus[i];
+    }
+    w += __popc(m);
+  }
+}
+
+// bonus of each query's own target column (0 when the target is not a KG hit of that query; columns are unique)
+__global__ void hits_target_bonus_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                         const double* __restrict__ bonus, int Q, const int64_t* __restrict__ target,
+                                         double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (qi >= Q) return;
+  const int64_t t = target[qi];
+  double v = 0.0;
+  for (int64_t i = rowptr[qi] + lane; i < rowptr[qi + 1]; i += 32)
+    if ((int64_t)col[i] == t) v = bonus[i];
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = v != 0.0 ? v : other;
+  }
+  if (lane == 0) out[qi] = v;
+}
+
 }  // namespace kemr

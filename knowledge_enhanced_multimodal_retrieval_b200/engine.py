@@ -131,27 +131,32 @@ class KGHits:
         return KGHits(torch.from_numpy(rowptr).to(device), torch.from_numpy(col).to(device),
                       torch.from_numpy(bon).to(device), mx)
 
+    def _filter(self, sel: Optional[torch.Tensor], n_out: int, lo: int, hi: int) -> "KGHits":
+        """kemr_hits_filter_csr: query subset and / or column range, on the device."""
+        lib = _lib.load()
+        dev = self.rowptr.device
+        nnz = self.col.numel()
+        rowptr = torch.empty(n_out + 1, dtype=torch.int64, device=dev)
+        col = torch.empty(max(1, nnz), dtype=torch.int32, device=dev)
+        bonus = torch.empty(max(1, nnz), dtype=torch.float64, device=dev)
+        mx = torch.zeros(1, dtype=torch.int64, device=dev)
+        ws = torch.empty(int(lib.kemr_hits_workspace_bytes(n_out)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.kemr_hits_filter_csr(_ptr(self.rowptr), _ptr(self.col), _ptr(self.bonus), _ptr(sel), n_out, int(lo), int(hi),
+                                            _ptr(rowptr), _ptr(col), _ptr(bonus), _ptr(mx), _ptr(ws), ws.numel(), _stream()))
+        tail = torch.stack([rowptr[-1], mx[0]]).cpu()          # one read-back: nnz and the longest list
+        n = int(tail[0])
+        return KGHits(rowptr, col[:n], bonus[:n], int(tail[1]))
+
     def subset(self, rows: torch.Tensor) -> "KGHits":
         """CSR restricted to the given query rows (in that order)."""
-        rp = self.rowptr.cpu().numpy()
-        col = self.col.cpu().numpy()
-        bon = self.bonus.cpu().numpy()
-        sel = rows.cpu().numpy()
-        return KGHits.from_lists([col[rp[i]:rp[i + 1]].tolist() for i in sel],
-                                 [bon[rp[i]:rp[i + 1]].tolist() for i in sel], device=self.rowptr.device)
+        sel = rows.to(device=self.rowptr.device, dtype=torch.int64).contiguous()
+        if sel.numel() == 0:
+            return KGHits(torch.zeros(1, dtype=torch.int64, device=self.rowptr.device), self.col[:0], self.bonus[:0], 0)
+        return self._filter(sel, sel.numel(), 0, 1 << 31)
 
     def shard(self, lo: int, hi: int) -> "KGHits":
         """Hits falling in gallery rows [lo, hi), re-based to local indices."""
-        rp = self.rowptr.cpu().numpy()
-        col = self.col.cpu().numpy()
-        bon = self.bonus.cpu().numpy()
-        cols, bons = [], []
-        for i in range(len(rp) - 1):
-            c = col[rp[i]:rp[i + 1]]
-            m = (c >= lo) & (c < hi)
-            cols.append((c[m] - lo).tolist())
-            bons.append(bon[rp[i]:rp[i + 1]][m].tolist())
-        return KGHits.from_lists(cols, bons, device=self.rowptr.device)
+        return self._filter(None, self.rowptr.numel() - 1, lo, hi)
 
 
 def uri_tail(uri: str) -> str:
@@ -334,20 +339,15 @@ def score_pairs(q, gal_a, gal_b, pair_q: torch.Tensor, pair_row: torch.Tensor, w
 
 
 def target_bonus(hits: Optional[KGHits], target_idx: torch.Tensor) -> Optional[torch.Tensor]:
-    """Bonus of each query's own target row (0 if it is not a KG hit of that query)."""
+    """Bonus of each query's own target row (0 if it is not a KG hit of that query), on the device."""
     if hits is None:
         return None
-    rp = hits.rowptr.cpu().numpy()
-    col = hits.col.cpu().numpy()
-    bon = hits.bonus.cpu().numpy()
-    t = target_idx.cpu().numpy()
-    out = np.zeros(len(t), dtype=np.float64)
-    for i in range(len(t)):
-        seg = col[rp[i]:rp[i + 1]]
-        m = np.nonzero(seg == t[i])[0]
-        if len(m):
-            out[i] = bon[rp[i] + m[0]]
-    return torch.from_numpy(out).to(target_idx.device)
+    t = target_idx.to(device=hits.rowptr.device, dtype=torch.int64).contiguous()
+    out = torch.empty(t.numel(), dtype=torch.float64, device=t.device)
+    if t.numel():
+        _lib.check(_lib.load().kemr_hits_target_bonus(_ptr(hits.rowptr), _ptr(hits.col), _ptr(hits.bonus), t.numel(),
+                                                      _ptr(t), _ptr(out), _stream()))
+    return out
 
 
 def rank_count(q, gal_a, gal_b, t_score: torch.Tensor, t_gidx: torch.Tensor, w_a=1.0, w_b=0.0, alpha=1.0,
