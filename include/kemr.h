@@ -183,6 +183,19 @@ int kemr_matrix_fuse(const float* S, float* out, int Q, int64_t M, int64_t ld,
                      const int64_t* hit_rowptr, const int32_t* hit_col, const float* hit_add,
                      kemr_stream_t stream);
 
+/* ---- LinearFusionHead of the reference (fusion_model.py:25-48): out[i] = w2 . relu(W1 [S_a[i], S_b[i]] + b1) + b2 for
+ * every element of two contiguous [Q, M] fp32 score matrices (T2I, T2T), in fp32 like torch; W1 is [hidden][2]
+ * (nn.Linear layout), b1 / w2 [hidden].  out may alias neither input. */
+int kemr_matrix_mlp2(const float* S_a, const float* S_b, float* out, int Q, int64_t M,
+                     const float* w1, const float* b1, const float* w2, float b2, int hidden, kemr_stream_t stream);
+
+/* ---- fused InfoNCE rows (train/losses.py:45-55): out_row_loss[i] = logsumexp_j(a_i.b_j / T) - a_i.b_i / T, the
+ * per-row cross entropy of logits = A B^T / T against the diagonal, in fp32, without materialising the (B, B)
+ * logits.  a, b: fp32 [B, D], D % 4 == 0, D <= 1024.  mean(out) = F.cross_entropy(logits, arange(B)); the
+ * symmetric loss is the mean of two calls, (a, b) and (b, a). */
+int kemr_infonce_rows(const float* a, const float* b, int B, int D, float temperature, float* out_row_loss,
+                      kemr_stream_t stream);
+
 /* ---- fused Recall@K / MRR / Mean-Rank reduction over 1-based ranks (metrics.py:41-42,70-71).
  *   out_hits[i] = #{rank <= k_values[i]};  out_stats[0] = sum(rank) (exact integer as double),
  *   out_stats[1] = sum(1/rank) in numpy's pairwise order, so that

@@ -25,7 +25,7 @@ EXPORTS = (
     "kemr_store_write", "kemr_store_info", "kemr_store_load", "kemr_debug_mma_plan", "kemr_set_phase_stamps",
     "kemr_peer_create", "kemr_peer_connect", "kemr_peer_connect_pointers", "kemr_peer_local_buffer", "kemr_peer_destroy",
     "kemr_peer_begin", "kemr_peer_merge", "kemr_merge_topk_strided",
-    "kemr_hits_filter_csr", "kemr_hits_target_bonus",
+    "kemr_hits_filter_csr", "kemr_hits_target_bonus", "kemr_matrix_mlp2", "kemr_infonce_rows",
 )
 
 
@@ -75,6 +75,8 @@ def _declare(lib):
     lib.kemr_matrix_rank.argtypes = [p, i32, i64, i64, p, p, p]
     lib.kemr_matrix_topk.argtypes = [p, i32, i64, i64, i32, p, p, p]
     lib.kemr_matrix_fuse.argtypes = [p, p, i32, i64, i64, i32, f32, p, p, p, p]
+    lib.kemr_matrix_mlp2.argtypes = [p, p, p, i32, i64, p, p, p, f32, i32, p]
+    lib.kemr_infonce_rows.argtypes = [p, p, i32, i32, f32, p, p]
     lib.kemr_metrics_reduce.argtypes = [p, i32, p, i32, p, p, p]
     lib.kemr_metrics_reduce_host.argtypes = [p, i32, p, i32, p, p]
     lib.kemr_merge_topk.argtypes = [p, p, i32, i32, i32, p, p, p]

@@ -631,6 +631,35 @@ extern "C" int kemr_matrix_fuse(const float* Smat, float* out, int Q, int64_t M,
   return KEMR_OK;
 }
 
+extern "C" int kemr_matrix_mlp2(const float* S_a, const float* S_b, float* out, int Q, int64_t M, const float* w1,
+                                const float* b1, const float* w2, float b2, int hidden, kemr_stream_t stream) {
+  if (!S_a || !S_b || !out || !w1 || !b1 || !w2 || Q <= 0 || M <= 0 || hidden <= 0 || hidden > 2048)
+    return fail(KEMR_ERR_ARG, "matrix_mlp2: bad argument");
+  const int64_t total = (int64_t)Q * M;
+  const int64_t blocks = std::min<int64_t>((total + 255) / 256, 148 * 8);
+  matrix_mlp2_kernel<<<(unsigned)blocks, 256, (size_t)hidden * 16, S(stream)>>>(S_a, S_b, out, total, w1, b1, w2, b2, hidden);
+  LAUNCH_CHECK("matrix_mlp2_kernel");
+  return KEMR_OK;
+}
+
+extern "C" int kemr_infonce_rows(const float* a, const float* b, int B, int D, float temperature, float* out_row_loss,
+                                 kemr_stream_t stream) {
+  if (!a || !b || !out_row_loss || B <= 0 || D <= 0 || D % 4 || D > 1024 || !(temperature > 0.f))
+    return fail(KEMR_ERR_ARG, "infonce_rows: bad argument (D %% 4 == 0, D <= 1024, temperature > 0)");
+  if (((uintptr_t)a | (uintptr_t)b) & 15) return fail(KEMR_ERR_ARG, "infonce_rows: feature pointers must be 16-byte aligned");
+  const int blocks = (B + 7) / 8;
+  const float inv_tau = 1.0f / temperature;
+  const int ch = (D + 127) / 128;
+  cudaStream_t st = S(stream);
+  switch (ch) {
+#define KEMR_NCE(n) case n: infonce_rows_kernel<n><<<blocks, 256, 0, st>>>(a, b, B, D, inv_tau, out_row_loss); break;
+    KEMR_NCE(1) KEMR_NCE(2) KEMR_NCE(3) KEMR_NCE(4) KEMR_NCE(5) KEMR_NCE(6) KEMR_NCE(7) KEMR_NCE(8)
+#undef KEMR_NCE
+  }
+  LAUNCH_CHECK("infonce_rows_kernel");
+  return KEMR_OK;
+}
+
 // ----------------------------------------------------------------------------- metrics reduction
 struct MetricsScratch { double* sums = nullptr; int64_t* off = nullptr; int64_t* n = nullptr; int dev = -1; };
 static int metrics_scratch(MetricsScratch** out) {

@@ -187,6 +187,107 @@ __global__ void matrix_hits_kernel(float* __restrict__ out, int Q, int64_t M, in
   }
 }
 
+// ------------------------------------------------------------------ learned 2 -> H -> 1 fusion of two score matrices
+// LinearFusionHead of the reference (fusion_model.py:25-48): out = w2 . relu(W1 [a, b] + b1) + b2 for every element,
+// a = T2I score, b = T2T score, fp32 like torch.  W1 is [H][2] (nn.Linear layout), hidden units summed in
+// increasing order.  Streams both matrices once; the H-unit MLP runs out of shared memory.
+__global__ void __launch_bounds__(256) matrix_mlp2_kernel(const float* __restrict__ Sa, const float* __restrict__ Sb,
+                                                         float* __restrict__ out, int64_t total,
+                                                         const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         const float* __restrict__ w2, float b2, int H) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* p = reinterpret_cast<float4*>(smem_raw);            // (w1[k][0], w1[k][1], b1[k], w2[k])
+  for (int k = threadIdx.x; k < H; k += blockDim.x) p[k] = make_float4(w1[2 * k], w1[2 * k + 1], b1[k], w2[k]);
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = Sa[i], b = Sb[i];
+    float acc = 0.f;
+    for (int k = 0; k < H; ++k) {
+      const float4 c = p[k];
+      const float h = fmaf(b, c.y, fmaf(a, c.x, c.z));
+      acc = fmaf(fmaxf(h, 0.f), c.w, acc);
+    }
+    out[i] = acc + b2;
+  }
+}
+
+// ------------------------------------------------------------------ fused InfoNCE rows (train/losses.py:45-55)
+// row_loss[i] = logsumexp_j(a_i . b_j / tau) - a_i . b_i / tau, i.e. F.cross_entropy(logits, arange(B), reduction='none')
+// of logits = A B^T / tau, without the (B, B) logits ever leaving the SM: one warp per row keeps a_i in registers and
+// walks the rows of B (L2-resident: B x D fp32) four at a time -- per-lane partial dots, one transposed shuffle
+// reduction for the four sums, online max / sum-of-exp per lane group.  fp32 like torch.  The symmetric loss is two
+// calls, (A, B) and (B, A).
+template <int CH>      // D <= 128 * CH: float4 pieces per lane
+__global__ void __launch_bounds__(256) infonce_rows_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int B,
+                                                          int D, float inv_tau, float* __restrict__ row_loss) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= B) return;
+  const int nv = D >> 2;                                         // float4 pieces per row (D % 4 == 0)
+  float4 a[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int p = lane + 32 * c;
+    a[c] = p < nv ? reinterpret_cast<const float4*>(A + (size_t)i * D)[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // lane group g = lane >> 3 owns columns j with j % 4 == g (after the transposed reduction below)
+  float m = -INFINITY, ssum = 0.f, diag = 0.f;
+  for (int j0 = 0; j0 < B; j0 += 4) {
+    float v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = j0 + t;
+      float acc = 0.f;
+      if (j < B) {
+        const float4* brow = reinterpret_cast<const float4*>(Bm + (size_t)j * D);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int p = lane + 32 * c;
+          if (p < nv) {
+            const float4 x = brow[p];
+            acc = fmaf(a[c].x, x.x, acc); acc = fmaf(a[c].y, x.y, acc);
+            acc = fmaf(a[c].z, x.z, acc); acc = fmaf(a[c].w, x.w, acc);
+          }
+        }
+      }
+      v[t] = acc;
+    }
+    // 4 sums over 32 lanes: halve the payload twice (steps 16, 8), then plain butterfly (4, 2, 1)
+    {
+      const bool up16 = (lane & 16) != 0;
+      const float s0 = up16 ? v[0] : v[2], k0 = up16 ? v[2] : v[0];
+      const float s1 = up16 ? v[1] : v[3], k1 = up16 ? v[3] : v[1];
+      v[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+      v[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+      const bool up8 = (lane & 8) != 0;
+      const float s2 = up8 ? v[0] : v[1], k2 = up8 ? v[1] : v[0];
+      v[0] = k2 + __shfl_xor_sync(0xffffffffu, s2, 8);
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 4);
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    }
+    const int t = ((lane & 16) ? 2 : 0) + ((lane & 8) ? 1 : 0);   // which of the four columns this lane now holds
+    const int j = j0 + t;
+    if (j < B) {
+      const float logit = v[0] * inv_tau;
+      if (j == i) diag = logit;
+      const float mn = fmaxf(m, logit);
+      ssum = ssum * __expf(m - mn) + __expf(logit - mn);          // m = -inf on the first column: exp(-inf) = 0
+      m = mn;
+    }
+  }
+  // merge the four lane groups' (max, sum) states and pick up the diagonal
+#pragma unroll
+  for (int o = 16; o >= 8; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, ssum, o);
+    const float d2 = __shfl_xor_sync(0xffffffffu, diag, o);
+    const float mn = fmaxf(m, m2);
+    const float sa = m == -INFINITY ? 0.f : ssum * __expf(m - mn), sb = m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn);
+    ssum = sa + sb; m = mn; diag += d2;
+  }
+  if (lane == 0) row_loss[i] = (m + logf(ssum)) - diag;
+}
+
 // ------------------------------------------------------------------ metrics reduction
 // numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, *_pairwise_sum) over
 // a[i] = 1.0 / rank[i]; reproduced so that MRR is bit-identical to np.mean(1.0/pos)*100.

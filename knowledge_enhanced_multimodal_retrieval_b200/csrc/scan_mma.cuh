@@ -436,7 +436,7 @@ struct MmaArgs {
   int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, gran, vq;
   WorkSplit split;  // how the units share the (query block, gallery row) work
   long long* dbg;   // optional [ctas][16] cycle counters + stage trace (debug build, KEMR_MMA_DEBUG=1)
-  int epi_variant;  // short lists: 3 = survivor mask + select-tree extraction on RAW accumulators (default), 2 = predicated appends on raw accumulators, 1 = on weighted scores; 0 = max tree + vote (long scans); KEMR_MMA_EPI overrides
+  int epi_variant;  // short lists: 2 = per-lane predicated appends on RAW accumulators (one accumulator, positive weight), 1 = on weighted scores; 0 = max tree + vote (long scans); KEMR_MMA_EPI overrides.  (Measured and rejected: a survivor bit mask per 16 columns + select-tree extraction -- C2 107 -> 121 us, C1 318 -> 393 us in the same build.)
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -497,7 +497,9 @@ __device__ __forceinline__ void ld_shared_v2(uint32_t addr, float& s, uint32_t& 
 // accumulators (T2I, T2T) of 128 columns each, fused in the epilogue with their own weights
 // (otherwise ONE accumulator of 256 gallery rows: single gallery, or both galleries with equal
 // weights accumulated over 2*kc K chunks).
-template <int K, int CL, bool TWO>
+// MODE (kModeTopk / kModeCount / kModeDense) is a template parameter: one epilogue per kernel keeps the loop body of
+// the eight epilogue warps inside the instruction cache (with every epilogue inlined C2 lost 11 %, C1 25 %).
+template <int K, int CL, bool TWO, int MODE>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g0,
                 const __grid_constant__ CUtensorMap map_g1, const __grid_constant__ CUtensorMap map_s0,
@@ -703,7 +705,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t my_buf = buf_u32 + (uint32_t)et * 8u;  // append-buffer entry i of this thread: + i * kEpiThreads * 8
     float w0 = a.s.w[0], w1 = a.s.w[1];
-    const int mode = a.s.mode;
+    constexpr int mode = MODE;
     constexpr int kHalfCols = n_tile / 2;                // score columns per warp and tile
     RegList<K> list;
     list.reset();
@@ -808,37 +810,6 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (TWO) tmem_ld16(acc0 + 128u + (uint32_t)c0, rb);
       };
       auto process = [&](int c0, const uint32_t (&ra)[16], const uint32_t (&rb)[16]) {
-        if (!TWO && mode == kModeTopk && a.epi_variant == 3 && w0 > 0.f) {
-          // One compare + one predicated OR per score builds a survivor mask; the (few) survivors are then pulled
-          // out of the registers with a select tree, lane by lane in lock-step, and appended.  The straight-line
-          // part costs 2 instructions per score instead of the ~7 of a predicated append per score (ncu, C1: 16.6
-          // thread-instructions per score overall, epilogue 2.1x slower than the MMAs of a 512-d tile).
-          uint32_t mask = 0;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (__uint_as_float(ra[j]) > thr_raw) mask |= 1u << j;
-          if (!full_tile) { const int nv = ncols - c0; mask &= nv >= 16 ? 0xffffu : ((1u << (nv > 0 ? nv : 0)) - 1u); }
-          if (__any_sync(0xffffffffu, mask != 0u)) {
-            const uint32_t r = (uint32_t)(row0 + c0);
-            do {
-              if (mask) {
-                const int j = __ffs((int)mask) - 1;
-                mask &= mask - 1u;
-                const uint32_t a0 = (j & 1) ? ra[1] : ra[0], a1 = (j & 1) ? ra[3] : ra[2], a2 = (j & 1) ? ra[5] : ra[4],
-                               a3 = (j & 1) ? ra[7] : ra[6], a4 = (j & 1) ? ra[9] : ra[8], a5 = (j & 1) ? ra[11] : ra[10],
-                               a6 = (j & 1) ? ra[13] : ra[12], a7 = (j & 1) ? ra[15] : ra[14];
-                const uint32_t b0 = (j & 2) ? a1 : a0, b1 = (j & 2) ? a3 : a2, b2 = (j & 2) ? a5 : a4, b3 = (j & 2) ? a7 : a6;
-                const uint32_t c0_ = (j & 4) ? b1 : b0, c1_ = (j & 4) ? b3 : b2;
-                const float x = __uint_as_float((j & 8) ? c1_ : c0_);
-                st_shared_v2(my_buf + (uint32_t)bcnt * (kEpiThreads * 8u), w0 * x, r + (uint32_t)j);
-                ++bcnt;
-              }
-              if (__any_sync(0xffffffffu, bcnt >= kBufCap)) fold();
-            } while (__any_sync(0xffffffffu, mask != 0u));
-            if (__any_sync(0xffffffffu, bcnt >= kBufTrigger)) fold();
-          }
-          return;
-        }
         if (!TWO && mode == kModeTopk && a.epi_variant == 2 && w0 > 0.f) {
           const uint32_t r = (uint32_t)(row0 + c0);
           const int nv = full_tile ? 16 : ncols - c0;            // columns of this chunk inside the gallery
@@ -972,7 +943,7 @@ inline int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int D,
   return 0;
 }
 
-template <int K, int CL, bool TWO>
+template <int K, int CL, bool TWO, int MODE>
 inline int mma_launch_kpt(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& s0,
                           const CUtensorMap& s1, const MmaArgs& ma, const MmaPlan& pl, cudaStream_t st) {
   // the attribute sticks to the function on a device: set it once per (instantiation, device, size) of this thread
@@ -981,7 +952,7 @@ inline int mma_launch_kpt(const CUtensorMap& mq, const CUtensorMap& m0, const CU
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess && (dev != attr_dev || pl.smem + 1024 > attr_smem)) {
-    e = cudaFuncSetAttribute(scan_mma_kernel<K, CL, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
+    e = cudaFuncSetAttribute(scan_mma_kernel<K, CL, TWO, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem + 1024);
     if (e == cudaSuccess) { attr_dev = dev; attr_smem = pl.smem + 1024; }
   }
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "smem attribute: %s", cudaGetErrorString(e)); return 1; }
@@ -995,22 +966,33 @@ inline int mma_launch_kpt(const CUtensorMap& mq, const CUtensorMap& m0, const CU
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, scan_mma_kernel<K, CL, TWO>, mq, m0, m1, s0, s1, ma);
+  e = cudaLaunchKernelEx(&cfg, scan_mma_kernel<K, CL, TWO, MODE>, mq, m0, m1, s0, s1, ma);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(g_mma_error, sizeof g_mma_error, "launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
 }
-template <int K>
-inline int mma_launch_k(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& s0,
+template <int K, int MODE>
+inline int mma_launch_km(const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& s0,
+                         const CUtensorMap& s1, const MmaArgs& ma, const MmaPlan& pl, cudaStream_t st) {
+  if (pl.cl == 4) return pl.two ? mma_launch_kpt<K, 4, true, MODE>(mq, m0, m1, s0, s1, ma, pl, st) : mma_launch_kpt<K, 4, false, MODE>(mq, m0, m1, s0, s1, ma, pl, st);
+  if (pl.cl == 2) return pl.two ? mma_launch_kpt<K, 2, true, MODE>(mq, m0, m1, s0, s1, ma, pl, st) : mma_launch_kpt<K, 2, false, MODE>(mq, m0, m1, s0, s1, ma, pl, st);
+  return pl.two ? mma_launch_kpt<K, 1, true, MODE>(mq, m0, m1, s0, s1, ma, pl, st) : mma_launch_kpt<K, 1, false, MODE>(mq, m0, m1, s0, s1, ma, pl, st);
+}
+// the register lists exist in the top-k epilogue only: the count and dense kernels are instantiated once (K = 8)
+inline int mma_launch_k(int K, const CUtensorMap& mq, const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& s0,
                         const CUtensorMap& s1, const MmaArgs& ma, const MmaPlan& pl, cudaStream_t st) {
-  if (pl.cl == 4) return pl.two ? mma_launch_kpt<K, 4, true>(mq, m0, m1, s0, s1, ma, pl, st) : mma_launch_kpt<K, 4, false>(mq, m0, m1, s0, s1, ma, pl, st);
-  if (pl.cl == 2) return pl.two ? mma_launch_kpt<K, 2, true>(mq, m0, m1, s0, s1, ma, pl, st) : mma_launch_kpt<K, 2, false>(mq, m0, m1, s0, s1, ma, pl, st);
-  return pl.two ? mma_launch_kpt<K, 1, true>(mq, m0, m1, s0, s1, ma, pl, st) : mma_launch_kpt<K, 1, false>(mq, m0, m1, s0, s1, ma, pl, st);
+  if (ma.s.mode == kModeCount) return mma_launch_km<8, kModeCount>(mq, m0, m1, s0, s1, ma, pl, st);
+  if (ma.s.mode == kModeDense) return mma_launch_km<8, kModeDense>(mq, m0, m1, s0, s1, ma, pl, st);
+  switch (K) {
+    case 8: return mma_launch_km<8, kModeTopk>(mq, m0, m1, s0, s1, ma, pl, st);
+    case 16: return mma_launch_km<16, kModeTopk>(mq, m0, m1, s0, s1, ma, pl, st);
+    default: return mma_launch_km<32, kModeTopk>(mq, m0, m1, s0, s1, ma, pl, st);
+  }
 }
 
 // clusters of four CTAs (one 227 KB CTA per SM) the current device can hold at once
 inline int mma_max_quads() {
-  cudaFuncSetAttribute(scan_mma_kernel<8, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  cudaFuncSetAttribute(scan_mma_kernel<8, 4, false, kModeTopk>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(4 * 64);
   cfg.blockDim = dim3(kMmaThreads);
@@ -1021,7 +1003,7 @@ inline int mma_max_quads() {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, scan_mma_kernel<8, 4, false>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaOccupancyMaxActiveClusters(&n, scan_mma_kernel<8, 4, false, kModeTopk>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
 
@@ -1058,7 +1040,7 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st, con
   const long long units_run = pl.ctas / std::max(1, pl.cl);
   const double rtot = (double)pl.n_qb * (double)s.M;
   const double per_list = rtot / (double)std::max(1ll, units_run) / 2.0 / std::max(1, pl.vq);
-  ma.epi_variant = epi_env ? atoi(epi_env) : (per_list < 8192.0 ? 3 : 0);
+  ma.epi_variant = epi_env ? atoi(epi_env) : (per_list < 8192.0 ? 2 : 0);
 #ifdef KEMR_DEBUG
   static const bool debug = getenv("KEMR_MMA_DEBUG") != nullptr;
 #else
@@ -1070,12 +1052,7 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st, con
     cudaMemsetAsync(dbuf, 0, 1024 * 16 * sizeof(long long), st);
     ma.dbg = dbuf;
   }
-  int rc_launch = 0;
-  switch (pl.K) {
-    case 8: rc_launch = mma_launch_k<8>(mq, m0, m1, ms0, ms1, ma, pl, st); break;
-    case 16: rc_launch = mma_launch_k<16>(mq, m0, m1, ms0, ms1, ma, pl, st); break;
-    default: rc_launch = mma_launch_k<32>(mq, m0, m1, ms0, ms1, ma, pl, st); break;
-  }
+  const int rc_launch = mma_launch_k(pl.K, mq, m0, m1, ms0, ms1, ma, pl, st);
   if (debug && rc_launch == 0) {
     static int printed = 0;
     cudaStreamSynchronize(st);

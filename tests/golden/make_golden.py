@@ -244,12 +244,44 @@ def main():
     run_head("bilinear", rheads.BilinearFusionHead(embed_dim=D),
              {"W_image.weight": np.eye(D) + hr.normal(0, 0.02, (D, D)), "W_target.weight": np.eye(D) + hr.normal(0, 0.02, (D, D)),
               "alpha": 0.4})
+    # LinearFusionHead takes the two similarity matrices (FusionModel.forward, fusion_model.py:318-322)
+    lin = rheads.LinearFusionHead(hidden_dim=128)
+    lin.eval()
+    lp = {"fusion.0.weight": hr.normal(0, 0.8, (128, 2)), "fusion.0.bias": hr.normal(0, 0.2, 128),
+          "fusion.3.weight": hr.normal(0, 0.3, (1, 128)), "fusion.3.bias": [0.02]}
+    with torch.no_grad():
+        for key, val in lp.items():
+            mod = lin.fusion[int(key.split(".")[1])]
+            getattr(mod, key.split(".")[2]).copy_(torch.from_numpy(np.asarray(val, dtype=np.float32)).reshape(getattr(mod, key.split(".")[2]).shape))
+        lscores = lin(tq @ ti.T, tq @ tt.T).numpy().astype(np.float32)
+    heads["linear"] = {"params": {k: np.asarray(v, dtype=np.float32).reshape(-1).tolist() for k, v in lp.items()},
+                       "metrics": f64dict(rmetrics.compute_retrieval_metrics_fusion(lscores)),
+                       "top5": np.argsort(-lscores, axis=1, kind="stable")[:, :5].tolist(),
+                       "score_row0": lscores[0, :8].astype(np.float64).tolist(),
+                       "score_checksum": float(lscores.astype(np.float64).sum())}
+    # CrossAttentionFusionHead on a small sub-problem (it scores every PAIR with a 3-layer MLP)
+    torch.manual_seed(31)
+    ca = rheads.CrossAttentionFusionHead(embed_dim=D, num_heads=8, hidden_dim=256)
+    ca.eval()
+    with torch.no_grad():
+        cscores = ca(tq[:48], ti[:48], tt[:48]).numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "cross_attention_head.npz"),
+                        **{k: v.detach().numpy() for k, v in ca.state_dict().items()}, scores=cscores)
+    heads["cross_attention"] = {"metrics": f64dict(rmetrics.compute_retrieval_metrics_fusion(cscores)), "n": 48}
     with torch.no_grad():
         g = rheads.SimpleGatedFusion(embed_dim=D)
         g.query_weight.copy_(torch.from_numpy(w)); g.bias.fill_(0.3)
         gate = torch.sigmoid((tq * g.query_weight).sum(dim=1, keepdim=True) + g.bias).numpy().reshape(-1)
     heads["simple_gated"]["gate"] = gate.astype(np.float64).tolist()
     out_json["fusion_heads"] = heads
+
+    # ------------------------------------------------------------------ contrastive losses (train/losses.py), forward values
+    from src.clip.train import losses as rlosses
+    with torch.no_grad():
+        l1, m1 = rlosses.InfoNCELoss(temperature=0.07)(tq, tt)
+        l2, m2 = rlosses.InfoNCELoss(temperature=0.5)(ti[:37], tt[:37])
+        l3, m3 = rlosses.JointContrastiveLoss(temperature=0.07, t2i_weight=0.3, t2t_weight=0.9)(ti, tq, tt)
+    out_json["losses"] = {"infonce_q_t_007": m1, "infonce_i_t_05_first37": m2, "joint_03_09": m3}
 
     # ------------------------------------------------------------------ grouped ground truth (baselines/evaluate_text_models.py)
     # the UNMODIFIED evaluate_text_model(), fed by a fake SentenceTransformer that looks embeddings up by text and a
