@@ -80,6 +80,11 @@ int kemr_set_phase_stamps(void* device_int64x3);
 int kemr_quantize_rows(const float* src, uint16_t* dst, int64_t rows, int D, int normalize,
                        kemr_stream_t stream);
 
+/* ---- largest Euclidean row norm of a bf16 matrix (device float, never under-reported).  The selection margin of
+ * the fp32 scan is eps * max||q|| * max||g|| * (|w_a| + |w_b|): callers that do not normalise
+ * their embeddings (the reference does, evaluator.py:120-135) scale eps with it. */
+int kemr_row_norm_max(const uint16_t* x, int64_t rows, int D, float* out_max, kemr_stream_t stream);
+
 /* ---- deterministic synthetic gallery, generated on the device (counter-based, keyed by
  * seed and GLOBAL row index row_base+r so any shard can be regenerated anywhere). */
 int kemr_synth_rows(uint16_t* dst, int64_t rows, int D, uint64_t seed, int64_t row_base,

@@ -25,7 +25,7 @@ EXPORTS = (
     "kemr_store_write", "kemr_store_info", "kemr_store_load", "kemr_debug_mma_plan", "kemr_set_phase_stamps",
     "kemr_peer_create", "kemr_peer_connect", "kemr_peer_connect_pointers", "kemr_peer_local_buffer", "kemr_peer_destroy",
     "kemr_peer_begin", "kemr_peer_merge", "kemr_merge_topk_strided",
-    "kemr_hits_filter_csr", "kemr_hits_target_bonus", "kemr_matrix_mlp2", "kemr_infonce_rows",
+    "kemr_hits_filter_csr", "kemr_hits_target_bonus", "kemr_matrix_mlp2", "kemr_infonce_rows", "kemr_row_norm_max",
 )
 
 
@@ -44,6 +44,7 @@ def _declare(lib):
     lib.kemr_abi_version.argtypes = []
     lib.kemr_device_info.argtypes = [C.POINTER(i32)] * 4
     lib.kemr_quantize_rows.argtypes = [p, p, i64, i32, i32, p]
+    lib.kemr_row_norm_max.argtypes = [p, i64, i32, p, p]
     lib.kemr_synth_rows.argtypes = [p, i64, i32, u64, i64, p]
     lib.kemr_scan_plan.argtypes = [i32, i64, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.kemr_workspace_bytes.restype = sz

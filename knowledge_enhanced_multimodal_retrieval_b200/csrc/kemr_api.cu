@@ -147,6 +147,16 @@ extern "C" int kemr_quantize_rows(const float* src, uint16_t* dst, int64_t rows,
   return KEMR_OK;
 }
 
+extern "C" int kemr_row_norm_max(const uint16_t* x, int64_t rows, int D, float* out_max, kemr_stream_t stream) {
+  if (!x || !out_max || rows < 0 || D <= 0 || D % 8) return fail(KEMR_ERR_ARG, "row_norm_max: bad argument");
+  CUDA_TRY(cudaMemsetAsync(out_max, 0, 4, S(stream)));
+  if (rows == 0) return KEMR_OK;
+  const int64_t blocks = std::min<int64_t>((rows + 7) / 8, 148 * 16);
+  row_norm_max_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(x, rows, D, out_max);
+  LAUNCH_CHECK("row_norm_max_kernel");
+  return KEMR_OK;
+}
+
 extern "C" int kemr_synth_rows(uint16_t* dst, int64_t rows, int D, uint64_t seed, int64_t row_base,
                                kemr_stream_t stream) {
   if (!dst || rows < 0 || D <= 0) return fail(KEMR_ERR_ARG, "synth_rows: bad argument");
@@ -202,10 +212,10 @@ static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, 
   }
   pl->CH = (D + 255) / 256;
   if (mode == kModeTopk) {
-    // fused streaming search (scan_stream.cuh): one persistent CTA per SM and query group of 1, 2 or 4 queries
-    pl->QB = Q == 1 ? 1 : (Q == 2 ? 2 : 4);
+    // fused streaming search (scan_stream.cuh): two CTAs per SM and query group of 1, 2 or 4 queries
+    pl->QB = Q == 1 ? 1 : ((Q == 2 || pl->CH >= 3) ? 2 : 4);      // four queries x 768-d do not fit the registers of 2 CTAs / SM
     pl->groups = (Q + pl->QB - 1) / pl->QB;
-    pl->P = (int)std::min<int64_t>(dv.sms > 0 ? dv.sms : 1, std::max<int64_t>(1, (M + 31) / 32));
+    pl->P = (int)std::min<int64_t>(2 * (dv.sms > 0 ? dv.sms : 1), std::max<int64_t>(1, (M + 31) / 32));
     pl->Kp = K;
     return KEMR_OK;
   }
@@ -335,12 +345,8 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
     // small batches: scan + selection in ONE launch (scan_stream.cuh)
     StreamArgs sa{};
     sa.s = a; sa.sel = s;
-    sa.stage_bytes = (unsigned)((size_t)G * kStreamRows * D * 2);
-    const size_t tail = stream_smem_bytes(0, 0, pl.QB, 0);
-    sa.stages = (int)std::min<size_t>(kStreamMaxStages, ((size_t)kSmemBudget - 1024 - tail) / sa.stage_bytes);
-    if (sa.stages < 2) return fail(KEMR_ERR_UNSUPPORTED, "stream kernel: a stage of %u bytes does not fit twice", sa.stage_bytes);
-    const size_t dyn = stream_smem_bytes(sa.stages, sa.stage_bytes, pl.QB, smem);
-    sa.tail_off = (unsigned)stream_tail_off(sa.stages, sa.stage_bytes, smem);
+    const size_t dyn = stream_smem_bytes(pl.QB, smem);
+    sa.cand_off = (unsigned)stream_cand_off(smem);
     if (dyn > (size_t)kSmemBudget) return fail(KEMR_ERR_UNSUPPORTED, "stream kernel needs %zu bytes of shared memory", dyn);
     if (pl.groups > 65535) return fail(KEMR_ERR_UNSUPPORTED, "warp path: too many query groups (%d)", pl.groups);
     if ((rc = stream_counters(pl.groups, &sa.done))) return rc;

@@ -53,6 +53,35 @@ __global__ void quantize_rows_vec_kernel(const float* __restrict__ src, uint16_t
   }
 }
 
+// ------------------------------------------------------------------ largest row norm of a bf16 matrix
+// The selection margin eps of the scan is proportional to max||q|| * max||g||: one streaming
+// pass, fp32 sum of squares per row (one warp per row), atomicMax on the bit pattern (norms are non-negative).
+__global__ void row_norm_max_kernel(const uint16_t* __restrict__ x, int64_t rows, int D, float* __restrict__ out_max) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nchunk = D >> 3;
+  float best = 0.f;
+  for (int64_t r = wid; r < rows; r += nw) {
+    const uint16_t* row = x + (size_t)r * D;
+    float ss = 0.f;
+    for (int c = lane; c < nchunk; c += 32) {
+      const uint4 v = ldg_stream(row + (size_t)c * 8);
+      const float a0 = bf16_lo(v.x), a1 = bf16_hi(v.x), a2 = bf16_lo(v.y), a3 = bf16_hi(v.y);
+      const float a4 = bf16_lo(v.z), a5 = bf16_hi(v.z), a6 = bf16_lo(v.w), a7 = bf16_hi(v.w);
+      ss = fmaf(a0, a0, ss); ss = fmaf(a1, a1, ss); ss = fmaf(a2, a2, ss); ss = fmaf(a3, a3, ss);
+      ss = fmaf(a4, a4, ss); ss = fmaf(a5, a5, ss); ss = fmaf(a6, a6, ss); ss = fmaf(a7, a7, ss);
+    }
+    ss = warp_sum(ss);
+    best = fmaxf(best, ss);
+  }
+  if (lane == 0) {
+    const float n = sqrtf(best) * (1.0f + 1e-6f);                 // fp32 summation slack: never under-report
+    if (isnan(n)) atomicMax(reinterpret_cast<unsigned int*>(out_max), 0x7f800000u);     // NaN rows: infinite margin
+    else atomicMax(reinterpret_cast<unsigned int*>(out_max), __float_as_uint(n));
+  }
+}
+
 // ------------------------------------------------------------------ synthetic gallery rows
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {          // splitmix64 finaliser
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;

@@ -43,7 +43,7 @@ def make_split(M, n_qb, units, gran):
 def stripe_begin(w, s):
     if s >= w["s_full"] and w["units"] == w["s_full"] * w["n_qb"]:
         return w["M"]
-    x = s * w["n_qb"] * w["M"] // w["units"]
+    x = s * w["n_qb"] * w["M"] * 2 // (2 * w["units"] - (w["units"] - w["s_full"] * w["n_qb"]))
     return min(x - x % w["gran"], w["M"])
 
 
@@ -147,7 +147,8 @@ def test_plan_tiles_the_work_without_slot_collisions(shape, sms, quads):
     if p["gran"] < p["n_tile"] and shape[1] >= 4 * p["n_tile"]:
         # partial tiles level the tensor work: no unit does more than the mean plus the rounding of its segments (a
         # remainder unit may walk every query block: one 32-row round-up and one snapped boundary per block)
-        assert max(work) <= sum(work) / len(work) * 1.05 + 32 * (2 * p["n_qb"] + 4), (max(work), sum(work) / len(work))
+        # (remainder units count as half a unit, so the full units carry up to units / (units - r / 2) of the mean)
+        assert max(work) <= sum(work) / len(work) * 1.10 + 32 * (2 * p["n_qb"] + 4), (max(work), sum(work) / len(work))
 
 
 def test_plan_random_shapes():
