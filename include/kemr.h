@@ -302,6 +302,9 @@ int kemr_store_write(const char* path, const uint16_t* rows_host, int64_t M, int
 int kemr_store_info(const char* path, int64_t* rows, int* dim);
 int kemr_store_load(const char* path, int64_t row_lo, int64_t row_hi, uint16_t* dst_device, kemr_stream_t stream);
 
+/* ---- debug build only: %globaltimer stamps (ns) of the phases of query 0's selection in the last launch */
+int kemr_debug_select_stamps(int64_t* out16_host);
+
 /* ---- introspection of the tcgen05 scan's work plan for a shape on a hypothetical device (no GPU needed): see
  * kemr_api.cu; used by the CPU property tests of the scheduling logic. */
 int kemr_debug_mma_plan(int Q, int64_t M, int D, int galleries, int k_sel, int equal_weights, int sms, int quads,

@@ -25,7 +25,7 @@ EXPORTS = (
     "kemr_store_write", "kemr_store_info", "kemr_store_load", "kemr_debug_mma_plan", "kemr_set_phase_stamps",
     "kemr_peer_create", "kemr_peer_connect", "kemr_peer_connect_pointers", "kemr_peer_local_buffer", "kemr_peer_destroy",
     "kemr_peer_begin", "kemr_peer_merge", "kemr_merge_topk_strided",
-    "kemr_hits_filter_csr", "kemr_hits_target_bonus", "kemr_matrix_mlp2", "kemr_infonce_rows", "kemr_row_norm_max",
+    "kemr_hits_filter_csr", "kemr_hits_target_bonus", "kemr_matrix_mlp2", "kemr_infonce_rows", "kemr_row_norm_max", "kemr_debug_select_stamps",
 )
 
 
@@ -69,6 +69,7 @@ def _declare(lib):
     lib.kemr_store_write.argtypes = [C.c_char_p, p, i64, i32]
     lib.kemr_store_info.argtypes = [C.c_char_p, C.POINTER(i64), C.POINTER(i32)]
     lib.kemr_store_load.argtypes = [C.c_char_p, i64, i64, p, p]
+    lib.kemr_debug_select_stamps.argtypes = [p]
     lib.kemr_debug_mma_plan.argtypes = [i32, i64, i32, i32, i32, i32, i32, i32, p]
     lib.kemr_rank_count.argtypes = [p, i32, p, p, i64, i32, f64, f64, f64, p, p, p, p, p, f64, i64,
                                     p, p, p, sz, i32, p]

@@ -124,6 +124,19 @@ extern "C" int kemr_device_info(int* sm_count, int* cc_major, int* cc_minor, int
 }
 
 static inline cudaStream_t S(kemr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// The tcgen05 scan needs the SM's whole shared-memory carve-out (227 KB).  The small kernels around it (quantise,
+// selection, merge) ask for the same carve-out, so that an SM does not have to re-partition L1 / shared memory
+// between the kernels of one search step.  Once per function and thread.
+template <class F>
+static inline void prefer_max_smem(F* func) {
+  static thread_local bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
+    done = true;
+  }
+}
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // ----------------------------------------------------------------------------- simple kernels
@@ -135,13 +148,14 @@ extern "C" int kemr_quantize_rows(const float* src, uint16_t* dst, int64_t rows,
   const int64_t blocks = std::min<int64_t>((rows + 7) / 8, 148 * 16);
   if (!normalize && D % 128 == 0 && D <= 1024 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
     switch (D / 128) {
-#define KEMR_QV(n) case n: quantize_rows_vec_kernel<n><<<(unsigned)blocks, threads, 0, S(stream)>>>(src, dst, rows); break;
+#define KEMR_QV(n) case n: prefer_max_smem(quantize_rows_vec_kernel<n>); quantize_rows_vec_kernel<n><<<(unsigned)blocks, threads, 0, S(stream)>>>(src, dst, rows); break;
       KEMR_QV(1) KEMR_QV(2) KEMR_QV(3) KEMR_QV(4) KEMR_QV(5) KEMR_QV(6) KEMR_QV(7) KEMR_QV(8)
 #undef KEMR_QV
     }
     LAUNCH_CHECK("quantize_rows_vec_kernel");
     return KEMR_OK;
   }
+  prefer_max_smem(quantize_rows_kernel);
   quantize_rows_kernel<<<(unsigned)blocks, threads, 0, S(stream)>>>(src, dst, rows, D, normalize);
   LAUNCH_CHECK("quantize_rows_kernel");
   return KEMR_OK;
@@ -291,7 +305,10 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
                           const int64_t* hit_rowptr, const int32_t* hit_col, const double* hit_bonus,
                           int64_t max_hits_per_query, int k, int k_sel, double eps, int64_t idx_base,
                           double* out_score64, float* out_score32, int64_t* out_idx, int32_t* out_flags,
-                          void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream) {
+                          void* workspace, size_t workspace_bytes, int path, kemr_stream_t stream,
+                          const float* q_f32 = nullptr, int q_normalize = 0) {
+  // q_f32 (internal, host-buffer search of small batches): the queries are still fp32 in device memory and the fused
+  // streaming kernel rounds them itself, storing the bf16 rows to `q`; only valid when that kernel is the one chosen
   int rc = check_common(q, Q, gal_a, M, D);
   if (rc) return rc;
   if ((wq_a != nullptr) != (wq_b != nullptr)) return fail(KEMR_ERR_ARG, "per-query weights need both arrays");
@@ -351,6 +368,7 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
     if (pl.groups > 65535) return fail(KEMR_ERR_UNSUPPORTED, "warp path: too many query groups (%d)", pl.groups);
     if ((rc = stream_counters(pl.groups, &sa.done))) return rc;
     sa.stamps = g_phase_stamps;
+    sa.q_f32 = q_f32; sa.q_normalize = q_normalize;
     if (sa.stamps) CUDA_TRY(cudaMemsetAsync(sa.stamps, 0x7f, 8, st));       // "first start" is an atomicMin
     dim3 grid(pl.P, pl.groups);
 #define KEMR_STREAM(QBV, CHV)                                                                                     \
@@ -374,6 +392,7 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
     return KEMR_OK;
   }
 
+  if (q_f32) return fail(KEMR_ERR_ARG, "internal: fp32 queries need the fused streaming kernel");
   if (!pl.mma.all_slots) CUDA_TRY(cudaMemsetAsync(part_keys, 0, need, st));   // unwritten slots must read as empty
   if ((rc = mma_launch(a, pl.mma, st))) return fail(KEMR_ERR_CUDA, "tcgen05 scan launch failed: %s", mma_last_error());
   if (g_scan_done_event) CUDA_TRY(cudaEventRecord(g_scan_done_event, st));
@@ -384,6 +403,7 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
   do {                                                                                                            \
     if (smem > 48 * 1024)                                                                                         \
       CUDA_TRY(cudaFuncSetAttribute(select_kernel<NPV, WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    prefer_max_smem(select_kernel<NPV, WV>);                                                                      \
     select_kernel<NPV, WV><<<Q, WV * 32, smem, st>>>(s);                                                          \
   } while (0)
 #define KEMR_SEL_NP(WV) switch (np) { case 1: KEMR_SEL(1, WV); break; case 2: KEMR_SEL(2, WV); break; \
@@ -856,6 +876,8 @@ extern "C" int kemr_peer_merge(kemr_peer_t* p, int Q, int k, double* out_score64
 }
 
 // ----------------------------------------------------------------------------- resident index, host-buffer search
+constexpr int kSmallBatch = 4;            // host-buffer searches up to this many queries take the one-copy, one-launch route
+
 struct kemr_index {
   uint16_t* gal[2] = {nullptr, nullptr};
   int64_t M = 0;
@@ -867,6 +889,8 @@ struct kemr_index {
   float* d_qf32 = nullptr; uint16_t* d_q = nullptr;
   double* d_score = nullptr; int64_t* d_idx = nullptr; int32_t* d_flags = nullptr;
   int64_t* d_rowptr = nullptr; int32_t* d_col = nullptr; double* d_bonus = nullptr; int64_t hit_cap = 0;
+  // one request blob for small batches: [q fp32 | hit rowptr | hit bonus | hit col] -> ONE host-to-device copy
+  unsigned char* h_blob = nullptr; unsigned char* d_blob = nullptr; size_t blob_bytes = 0;
   // pinned staging
   float* h_q = nullptr; double* h_score = nullptr; int64_t* h_idx = nullptr; int32_t* h_flags = nullptr;
   int64_t* h_rowptr = nullptr; int32_t* h_col = nullptr; double* h_bonus = nullptr;
@@ -880,6 +904,7 @@ extern "C" int kemr_index_destroy(kemr_index_t* ix) {
   cudaFree(ix->d_rowptr); cudaFree(ix->d_col); cudaFree(ix->d_bonus);
   cudaFreeHost(ix->h_q); cudaFreeHost(ix->h_score); cudaFreeHost(ix->h_idx); cudaFreeHost(ix->h_flags);
   cudaFreeHost(ix->h_rowptr); cudaFreeHost(ix->h_col); cudaFreeHost(ix->h_bonus);
+  cudaFreeHost(ix->h_blob); cudaFree(ix->d_blob);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
   return KEMR_OK;
@@ -914,6 +939,8 @@ extern "C" int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal
   IX_TRY(cudaMallocHost(&ix->h_idx, nq * max_k * 8)); IX_TRY(cudaMallocHost(&ix->h_flags, nq * 4));
   IX_TRY(cudaMallocHost(&ix->h_rowptr, (nq + 1) * 8)); IX_TRY(cudaMallocHost(&ix->h_col, (size_t)ix->hit_cap * 4));
   IX_TRY(cudaMallocHost(&ix->h_bonus, (size_t)ix->hit_cap * 8));
+  ix->blob_bytes = align_up((size_t)kSmallBatch * D * 4) + align_up((size_t)(kSmallBatch + 1) * 8) + (size_t)kSmallBatch * 256 * 12 + 256;
+  IX_TRY(cudaMallocHost(&ix->h_blob, ix->blob_bytes)); IX_TRY(cudaMalloc(&ix->d_blob, ix->blob_bytes));
   IX_TRY(cudaStreamSynchronize(ix->stream));
 #undef IX_TRY
   *out = ix;
@@ -928,6 +955,43 @@ extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int
   if (Q <= 0 || Q > ix->max_q || k <= 0 || k > ix->max_k) return fail(KEMR_ERR_ARG, "index_search_host: Q or k beyond the handle's limits");
   cudaStream_t st = ix->stream;
   const size_t qbytes = (size_t)Q * ix->D * 4;
+  if (Q <= kSmallBatch) {
+    // Serving-size batches: everything the request brings (queries, KG-hit CSR) goes over in ONE copy, and ONE kernel
+    // does the rest (quantise, scan, selection); results come back with one copy per array.  2 + 3 copies and two
+    // kernels cost 119 us for a batch of one; the scan itself is ~35 us.
+    int64_t nnz = 0, max_hits = 0;
+    if (hit_rowptr_host) {
+      nnz = hit_rowptr_host[Q];
+      if (nnz > (int64_t)kSmallBatch * 256) return fail(KEMR_ERR_ARG, "index_search_host: too many KG hits (%lld)", (long long)nnz);
+      for (int i = 0; i < Q; ++i) max_hits = std::max(max_hits, hit_rowptr_host[i + 1] - hit_rowptr_host[i]);
+    }
+    const size_t o_rp = align_up(qbytes), o_bo = o_rp + align_up((size_t)(Q + 1) * 8), o_co = o_bo + align_up((size_t)nnz * 8);
+    const size_t total = o_co + align_up((size_t)nnz * 4);
+    memcpy(ix->h_blob, q_host, qbytes);
+    if (hit_rowptr_host) {
+      memcpy(ix->h_blob + o_rp, hit_rowptr_host, (size_t)(Q + 1) * 8);
+      memcpy(ix->h_blob + o_bo, hit_bonus_host, (size_t)nnz * 8);
+      memcpy(ix->h_blob + o_co, hit_col_host, (size_t)nnz * 4);
+    }
+    CUDA_TRY(cudaMemcpyAsync(ix->d_blob, ix->h_blob, total, cudaMemcpyHostToDevice, st));
+    const int ksel = std::min(kMaxKSel, (k + 6 + 7) / 8 * 8);
+    int rc = scan_topk_impl(ix->d_q, Q, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, nullptr, nullptr, alpha,
+                            hit_rowptr_host ? reinterpret_cast<const int64_t*>(ix->d_blob + o_rp) : nullptr,
+                            reinterpret_cast<const int32_t*>(ix->d_blob + o_co), reinterpret_cast<const double*>(ix->d_blob + o_bo),
+                            max_hits, k, ksel, 2e-5, 0, ix->d_score, nullptr, ix->d_idx, ix->d_flags, ix->ws, ix->ws_bytes,
+                            KEMR_PATH_WARP, st, reinterpret_cast<const float*>(ix->d_blob), normalize);
+    if (rc) return rc;
+    // one device-to-host copy: score | idx | flags are adjacent in the handle's staging? they are separate arrays,
+    // small ones: three copies of <= 320 bytes each cost less than one extra kernel to pack them
+    CUDA_TRY(cudaMemcpyAsync(ix->h_idx, ix->d_idx, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ix->h_score, ix->d_score, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ix->h_flags, ix->d_flags, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(out_idx_host, ix->h_idx, (size_t)Q * k * 8);
+    memcpy(out_score64_host, ix->h_score, (size_t)Q * k * 8);
+    if (out_flags_host) memcpy(out_flags_host, ix->h_flags, (size_t)Q * 4);
+    return KEMR_OK;
+  }
   // Page-locked caller buffers are used IN PLACE by the kernels (the quantise kernel reads the fp32 queries over
   // PCIe, the select kernel stores the results straight into the caller's arrays): no copy engine hop in either
   // direction.  Pageable buffers are staged through the handle's page-locked memory.
@@ -1176,6 +1240,19 @@ extern "C" int kemr_store_load(const char* path, int64_t row_lo, int64_t row_hi,
   close(fd);
   if (!io_ok) return fail(KEMR_ERR_ARG, "store_load: short read from %s", path);
   if (e != cudaSuccess) return fail(KEMR_ERR_CUDA, "store_load: %s", cudaGetErrorString(e));
+  return KEMR_OK;
+}
+
+// %globaltimer (ns) at the phase boundaries of the selection of query 0 in the most recent launch: entry, lists merged
+// (A1), candidates cut (A2), pruned (A3), KG hits joined (B), re-scored (C), ordered and written (D).  Debug build
+// only (libkemr_debug.so); the release library reports zeros.
+extern "C" int kemr_debug_select_stamps(int64_t* out16_host) {
+  if (!out16_host) return fail(KEMR_ERR_ARG, "debug_select_stamps: null pointer");
+  memset(out16_host, 0, 16 * 8);
+#ifdef KEMR_DEBUG
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(out16_host, g_sel_stamps, 16 * 8));
+#endif
   return KEMR_OK;
 }
 

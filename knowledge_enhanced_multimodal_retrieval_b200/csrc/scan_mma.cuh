@@ -121,11 +121,12 @@ __host__ __device__ inline int unit_of(long long rtot, int units, long long len,
 }
 
 // How the units share the work (see the header comment): `s_full` = floor(units / n_qb) stripes, one unit per (stripe,
-// block); stripe s starts at row floor_gran(s * n_qb * M / (units - r / 2)), r = units mod n_qb (cumulative rounding:
+// block); stripe s starts at row floor_gran(s * n_qb * M / (units - 2 r / 3)), r = units mod n_qb (cumulative rounding:
 // stripe lengths differ by at most `gran`); the rows from the end of the last full stripe on are the remainder
-// stripe, shared by the r units past s_full * n_qb.  A remainder unit counts as HALF a unit: it walks several query
-// blocks (its lists restart cold each time) and nobody reads its rows at the same time (DRAM latency instead of L2
-// hits) -- with equal shares the remainder units of C1 ran 1.67x longer than the others and set the kernel time.
+// stripe, shared by the r units past s_full * n_qb.  A remainder unit counts as A THIRD of a unit: it walks several
+// query blocks (its lists restart cold each time) and nobody reads its rows at the same time (DRAM latency instead of
+// L2 hits) -- with equal shares the remainder units of C1 ran 1.67x longer than the others and set the kernel time,
+// with half shares still 1.14x.
 // Without remainder units the last full stripe ends at M.
 struct WorkSplit {
   long long M;        // gallery rows
@@ -133,13 +134,23 @@ struct WorkSplit {
   __host__ __device__ int full_units() const { return s_full * n_qb; }
   __host__ __device__ long long stripe_begin(int s) const {
     if (s >= s_full && units == s_full * n_qb) return M;
-    const long long x = (long long)s * n_qb * M * 2 / (2ll * units - (units - s_full * n_qb));
+    const long long x = (long long)s * n_qb * M * 3 / (3ll * units - 2ll * (units - s_full * n_qb));
     const long long b = x - x % gran;
     return b < M ? b : M;
   }
   __host__ __device__ long long rem_base() const { return stripe_begin(s_full); }
   __host__ __device__ long long rem_len() const { return M - rem_base(); }
 };
+// Rows per tile of a segment of `rows` rows: the fewest tiles of at most n_tile rows, of (nearly) EQUAL size -- a
+// 290-row segment is walked as 160 + 130 rows, not 256 + 34: the epilogue of the first tile then hides behind the
+// loads of the second, and the tail after the last byte arrives is one short tile (small batches at 43 k rows).
+__host__ __device__ inline int seg_tile_rows(long long rows, int n_tile, int gran) {
+  if (gran >= n_tile || rows <= 0) return n_tile;
+  const long long nt = (rows + n_tile - 1) / n_tile;
+  const long long t = ((rows + nt - 1) / nt + gran - 1) / gran * gran;
+  return (int)(t < n_tile ? t : n_tile);
+}
+
 // One unit's walk: positions [p_lo, p_hi) of a flat space of blocks of `mod` rows; position p is row base + p % mod of
 // query block qb0 + p / mod.
 struct UnitWalk { long long base, mod, p_lo, p_hi; int qb0; };
@@ -335,10 +346,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-// bring a box into L2 ahead of the load that will stage it (no shared memory, no barrier)
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -443,7 +450,6 @@ struct MmaArgs {
   int n_qb, n_t, stages, kc, kc_total, a_rows, parts, q_pad, q_blk, gran, vq;
   WorkSplit split;  // how the units share the (query block, gallery row) work
   long long* dbg;   // optional [ctas][16] cycle counters + stage trace (debug build, KEMR_MMA_DEBUG=1)
-  int prefetch;     // 1: the producer prefetches the next tile's boxes into L2 (KEMR_MMA_PREFETCH=0 switches it off)
   int epi_variant;  // short lists: 2 = per-lane predicated appends on RAW accumulators (one accumulator, positive weight), 1 = on weighted scores; 0 = max tree + vote (long scans); KEMR_MMA_EPI overrides.  (Measured and rejected: a survivor bit mask per 16 columns + select-tree extraction -- C2 107 -> 121 us, C1 318 -> 393 us in the same build.)
 };
 
@@ -556,11 +562,10 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int qb = uw.qb0 + (int)b__;                                                         \
     const long long blk0__ = b__ * uw.mod;                                                    \
     const long long rend__ = (p_hi < blk0__ + uw.mod ? p_hi : blk0__ + uw.mod) - blk0__;      \
-    for (long long r__ = p__ - blk0__; r__ < rend__; r__ += n_tile) {                         \
+    const int tsz__ = seg_tile_rows(rend__ - (p__ - blk0__), n_tile, partial_ok ? a.gran : n_tile); \
+    for (long long r__ = p__ - blk0__; r__ < rend__; r__ += tsz__) {                          \
       const long long row0 = uw.base + r__;                                                   \
-      const bool next_tile = r__ + n_tile < rend__;    /* another tile of this segment follows */ \
-      (void)next_tile;                                                                        \
-      const int ncols = (int)(rend__ - r__ < (long long)n_tile ? rend__ - r__ : (long long)n_tile); \
+      const int ncols = (int)(rend__ - r__ < (long long)tsz__ ? rend__ - r__ : (long long)tsz__); \
       __VA_ARGS__                                                                             \
     }                                                                                         \
     p__ = blk0__ + rend__;                                                                    \
@@ -612,13 +617,6 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               for (int gi = 0; gi < (ds ? 2 : 1); ++gi) {
                 const bool second = TWO ? rank != 0 : (ds ? gi : g) != 0;
                 unsigned char* sb = sa + a_bytes + (uint32_t)gi * b_bytes;
-                // the same chunk of the NEXT tile goes to L2 now: a whole tile (kc stages) of lookahead instead of the
-                // ring's few stages, so the staging loads of the next tile are L2 hits even for the unit that touches
-                // the rows first (the MMA warp waited 30 % of its time for data on C2)
-                if (a.prefetch && next_tile) {
-                  if (QUAD) ptx::tma_prefetch_2d(second ? &map_g1 : &map_g0, kx, (int)row0 + n_tile + (TWO ? 0 : (int)rank * 128) + (int)pc * 64);
-                  else ptx::tma_prefetch_2d(second ? &map_g1 : &map_g0, kx, (int)row0 + n_tile + (TWO ? 0 : (int)rank * 128));
-                }
                 if (QUAD) {
                   // this CTA's quarter of the chunk (64 rows), multicast to the CTA of the other pair holding the same half
                   ptx::tma_load_2d_pair_mc(sb + pc * (64u * 128u), second ? &map_g1 : &map_g0, lbar, kx, brow + (int)pc * 64,
@@ -633,10 +631,6 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             } else {
               ptx::mbar_expect_tx(&full_bar[stage], tx);
               ptx::tma_load_2d(sa, &map_q, &full_bar[stage], kx, qb * kBlockM);
-              if (a.prefetch && next_tile) {
-                ptx::tma_prefetch_2d((TWO || !g) ? &map_g0 : &map_g1, kx, (int)row0 + n_tile);
-                if (TWO) ptx::tma_prefetch_2d(&map_g1, kx, (int)row0 + n_tile);
-              }
               if (TWO) {
                 ptx::tma_load_2d(sa + a_bytes, &map_g0, &full_bar[stage], kx, brow);
                 ptx::tma_load_2d(sa + a_bytes + b_bytes, &map_g1, &full_bar[stage], kx, brow);
@@ -737,6 +731,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     float blo = 0.f, bhi = 0.f;
     int cur_qb = -1, cur_part = -1, c_first = 0, slot = 0;
     bool qvalid = false;
+    bool warp_active = false;                            // some lane of this warp holds a real query of the current block
     int qg = 0;
     long long it = 0;
     long long w_tfull = 0, t_fold = 0; const long long t_begin = dbg ? clock64() : 0;
@@ -810,6 +805,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         slot = ord * 2 + half;
         qg = qb * a.q_blk + qrow;
         qvalid = qg < a.s.Q;
+        warp_active = __any_sync(0xffffffffu, qvalid);   // small batches: the warps of empty lane quadrants only hand the buffer back
         list.reset();
         thr = qvalid ? -INFINITY : INFINITY;             // padded query rows never collect candidates
         thr_raw = thr;
@@ -892,8 +888,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
       // double-buffered TMEM reads: chunk i+1 is in flight while chunk i is processed
       uint32_t ra0[16], rb0[16], ra1[16], rb1[16];
-      if (nch > 0) load(cbeg, ra0, rb0);
-      for (int i = 0; i < nch; i += 2) {
+      if (warp_active && nch > 0) load(cbeg, ra0, rb0);
+      for (int i = 0; warp_active && i < nch; i += 2) {
         ptx::tmem_ld_wait();
         if (i + 1 < nch) load(cbeg + (i + 1) * 16, ra1, rb1);
         process(cbeg + i * 16, ra0, rb0);
@@ -1055,8 +1051,6 @@ inline int mma_launch(const ScanArgs& s, const MmaPlan& pl, cudaStream_t st, con
   ma.a_rows = pl.a_rows; ma.parts = pl.parts; ma.q_pad = pl.q_pad; ma.q_blk = pl.q_blk; ma.gran = pl.gran; ma.vq = pl.vq;
   ma.split = make_split(s.M, pl.n_qb, pl.ctas / std::max(1, pl.cl), pl.gran);
   ma.dbg = nullptr;
-  static const char* pf_env = getenv("KEMR_MMA_PREFETCH");
-  ma.prefetch = pf_env ? atoi(pf_env) : 1;
   // Short lists (a thread sees few scores: survivor probability K/n per element stays high) append per lane without
   // warp votes; long scans keep the vote that skips chunks without survivors.  Measured: C1 233 -> 212 us, C2 101.5 -> 99 us.
   static const char* epi_env = getenv("KEMR_MMA_EPI");

@@ -35,6 +35,11 @@ struct StreamArgs {
   unsigned int* done;       // [groups] arrival counters, zero on entry, reset by the last CTA
   long long* stamps;        // optional [3] globaltimer stamps of group 0: first CTA start, last scan arrival, select end
   unsigned int cand_off;    // offset of the candidate buffers behind the selection scratch
+  // optional: queries arrive as fp32 [Q][D] (device memory) and are rounded to bf16 in this kernel -- optionally
+  // L2-normalised first -- with exactly the arithmetic of quantize_rows_kernel; CTA 0 of a group stores the bf16 rows
+  // to s.q for the selection stage.  Saves the separate quantise launch of the host-buffer search.
+  const float* q_f32;
+  int q_normalize;
 };
 
 inline size_t stream_cand_off(size_t select_bytes) { return (select_bytes + 15) / 16 * 16; }
@@ -121,6 +126,29 @@ __global__ void __launch_bounds__(kStreamThreads, 2) scan_stream_kernel(StreamAr
   if (threadIdx.x < QB) { s_cnt[threadIdx.x] = 0; s_thr[threadIdx.x] = 0; }
 
   // queries -> fp32 registers (lane l keeps the d-slices it will meet in every row)
+  if (a.q_f32) {
+    // fp32 queries: warp w rounds query w of the group (quantize_rows_kernel's arithmetic: per-lane sum of squares over
+    // d = lane, lane + 32, ..., shuffle tree, v * (1 / sqrt(ss)), round to nearest even) into shared memory; the bf16
+    // rows also go to global memory once per group for the selection stage
+    uint16_t* qs = reinterpret_cast<uint16_t*>(cand);             // the candidate buffer is free until the scan starts
+    if (warp < nq) {
+      const float* src = a.q_f32 + (size_t)(q0 + warp) * D;
+      float scale = 1.f;
+      if (a.q_normalize) {
+        float ss = 0.f;
+        for (int d = lane; d < D; d += 32) { const float t = src[d]; ss = fmaf(t, t, ss); }
+        ss = warp_sum(ss);
+        scale = 1.f / sqrtf(ss);
+      }
+      for (int d = lane; d < D; d += 32) {
+        const uint16_t b16 = f32_to_bf16_rne(a.q_normalize ? src[d] * scale : src[d]);
+        qs[(size_t)warp * D + d] = b16;
+        if (blockIdx.x == 0) const_cast<uint16_t*>(a.s.q)[(size_t)(q0 + warp) * D + d] = b16;
+      }
+    }
+    __syncthreads();
+  }
+  const uint16_t* qsrc = a.q_f32 ? reinterpret_cast<const uint16_t*>(cand) : a.s.q + (size_t)q0 * D;
   float qr[QB][CH][8];
 #pragma unroll
   for (int qq = 0; qq < QB; ++qq) {
@@ -128,7 +156,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) scan_stream_kernel(StreamAr
     for (int c = 0; c < CH; ++c) {
       const int chunk = lane + 32 * c;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (qq < nq && chunk < nchunk) v = *reinterpret_cast<const uint4*>(a.s.q + (size_t)(q0 + qq) * D + chunk * 8);
+      if (qq < nq && chunk < nchunk) v = *reinterpret_cast<const uint4*>(qsrc + (size_t)qq * D + chunk * 8);
       qr[qq][c][0] = bf16_lo(v.x); qr[qq][c][1] = bf16_hi(v.x);
       qr[qq][c][2] = bf16_lo(v.y); qr[qq][c][3] = bf16_hi(v.y);
       qr[qq][c][4] = bf16_lo(v.z); qr[qq][c][5] = bf16_hi(v.z);

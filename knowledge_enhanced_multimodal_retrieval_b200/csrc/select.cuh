@@ -74,6 +74,15 @@ inline size_t select_smem_bytes(int P, int Kp, int K, int max_cand) {
 //   B   candidate table = scan candidates U KG hits;
 //   C   warp w re-scores candidates w, w+W, ...; the rows of its next candidate are in flight meanwhile;
 //   D   order by (score desc, row asc) by counting, write the first k;   E  certificate.
+// Debug build: %globaltimer at the phase boundaries of query 0's selection (kemr_debug_select_stamps).
+#ifdef KEMR_DEBUG
+__device__ unsigned long long g_sel_stamps[16];
+#define KEMR_SEL_STAMP(i)                                                                    \
+  do { if (threadIdx.x == 0 && qi == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); g_sel_stamps[i] = t__; } } while (0)
+#else
+#define KEMR_SEL_STAMP(i) do { } while (0)
+#endif
+
 // Body of the selection for ONE query, run by a whole CTA of W warps (every thread of the CTA must call it; it uses
 // __syncthreads).  `smem_raw`: select_smem_bytes(...) bytes of shared memory, 16-byte aligned.  Called by
 // select_kernel (one CTA per query) and by the last CTA of the fused small-batch scan (scan_stream.cuh).
@@ -95,6 +104,7 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
   __shared__ double s_kth;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __syncthreads();                                          // a previous query of this CTA is done with the static state
+  KEMR_SEL_STAMP(0);
 
   CanonQueryT<NP> cq;
   cq.load(a.q + (size_t)qi * a.D, a.D, lane);
@@ -114,6 +124,7 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
   }
   __syncthreads();
 
+  KEMR_SEL_STAMP(1);
   // A2
   const int nlist = s_nlist;                                // selected lists occupy s_lid[0..nlist), by head rank
   // A lower bound of the K-th best key: the first jc entries of every selected list are jc*nlist >= K keys, so the
@@ -193,6 +204,7 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
   }
   __syncthreads();
 
+  KEMR_SEL_STAMP(2);
   // A3 (keys fill s_selk[0..nsel) in descending order, so everything from the first dropped key on drops)
   int nsel = s_nsel;
   if (nsel > a.k) {
@@ -206,6 +218,7 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
     }
   }
 
+  KEMR_SEL_STAMP(3);
   // B
   for (int i = tid; i < nsel; i += T) { s_row[i] = (int32_t)key_row(s_selk[i]); s_bonus[i] = 0.0; s_has[i] = 0; }
   __syncthreads();
@@ -227,6 +240,7 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
     __syncthreads();
   }
   const int n = min(nsel + s_extra, MC);
+  KEMR_SEL_STAMP(4);
 
   // C (two register sets, roles alternate).  An item is two rows re-scored together with interleaved reduction
   //   chains: the T2I and T2T row of one candidate, or -- single gallery -- the rows of two candidates.
@@ -267,6 +281,7 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
   }
   __syncthreads();
 
+  KEMR_SEL_STAMP(5);
   // D (+ the fused all-gather: the same rows go to this rank's slot of every rank's exchange buffer)
   unsigned int epoch = 0;
   size_t peer_o = 0;
@@ -303,6 +318,7 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
   }
 
+  KEMR_SEL_STAMP(6);
   // E: nothing the scan or the stages above rejected can reach the k-th canonical score
   if (tid == 0) {
     int flag = 0;

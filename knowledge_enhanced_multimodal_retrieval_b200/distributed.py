@@ -191,6 +191,12 @@ class SearchPlan:
         dev = loc.device
         D = loc.image.shape[1]
         self.k_sel = engine.default_k_sel(self.k)
+        # selection margin: queries are L2-normalised by contract (the plan never reads them back), the shard's row
+        # norms and the weights scale it (engine.eps_for)
+        g_norm = engine.row_norm_max(loc.image) * abs(self.w_a)
+        if loc.target is not None:
+            g_norm += engine.row_norm_max(loc.target) * abs(self.w_b)
+        self.eps = engine.DEFAULT_EPS * max(1.0, g_norm * (1.0 + 2.0 ** -7))
         self.ws = torch.empty(int(engine._lib.load().kemr_workspace_bytes(self.Q, loc.image.shape[0], D, self.k_sel, 0)),
                               dtype=torch.uint8, device=dev)                # private workspace: plans may overlap other calls
         self.q = torch.empty((self.Q, D), dtype=torch.bfloat16, device=dev)
@@ -215,7 +221,7 @@ class SearchPlan:
         if self.peer is not None:
             self.peer.begin()
         e.scan_topk_raw(self.q, loc.image, loc.target, self.w_a, self.w_b, self.alpha, None, self.k, self.k_sel,
-                        e.DEFAULT_EPS, sg.lo, self.score, self.idx, self.flags, self.ws)
+                        self.eps, sg.lo, self.score, self.idx, self.flags, self.ws)
         if self.peer is not None:
             self.peer.merge(self.Q, self.k, self.out_score, self.out_idx)
         elif sg.world > 1:

@@ -16,7 +16,12 @@ import torch
 from . import _lib
 from ._lib import KemrError, PATH_AUTO, PATH_MMA, PATH_WARP, FLAG_OVERFLOW, FLAG_UNCERTIFIED  # noqa: F401  (PATH_* re-exported)
 
-DEFAULT_EPS = 2e-5      # assumed bound on |fp32 scan score - canonical binary64 score|
+# Bound on |fp32 scan score - canonical binary64 score| for ||q||, ||g|| <= 1 and |w_a| + |w_b| <= 1:
+# every accumulator update rounds (or truncates) once, relative to a running magnitude of at most sum_d |q_d g_d|
+# <= ||q|| ||g||, so |error| <= 2^-23 * (D_acc / 16 + 8) * S with D_acc the accumulated length (2 D when two galleries
+# share an accumulator) and S = max||q|| * max||g|| * (|w_a| + |w_b|); 1.25 * 2^-23 * (2048 / 16 + 8) = 2.03e-5 at the
+# largest supported shape (D = 1024, two galleries).  Un-normalised inputs scale it: see `eps_for`.
+DEFAULT_EPS = 2e-5
 MAX_K_SEL = 128
 
 ArrayLike = Union[np.ndarray, torch.Tensor]
@@ -99,6 +104,43 @@ def quantize(x: ArrayLike, normalize: bool = False) -> torch.Tensor:
         _lib.check(_lib.load().kemr_quantize_rows(_ptr(xd), _ptr(out), xd.shape[0], xd.shape[1],
                                                   int(normalize), _stream()))
     return out
+
+
+def row_norm_max(x: torch.Tensor) -> float:
+    """Largest Euclidean row norm of a bf16 CUDA matrix (kemr_row_norm_max), cached on the tensor object: galleries
+    are measured once, a query batch once per call (one 4-byte read-back)."""
+    cached = getattr(x, "_kemr_norm_max", None)
+    if cached is not None:
+        return cached
+    out = torch.zeros(1, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().kemr_row_norm_max(_ptr(x), x.shape[0], x.shape[1], _ptr(out), _stream()))
+    v = float(out.item())
+    try:
+        x._kemr_norm_max = v
+    except Exception:            # noqa: BLE001  (tensor subclasses without a __dict__)
+        pass
+    return v
+
+
+def eps_for(q: torch.Tensor, gal_a: torch.Tensor, gal_b: Optional[torch.Tensor] = None, w_a=1.0, w_b=0.0,
+            base: float = DEFAULT_EPS) -> float:
+    """Selection margin for THESE embeddings and weights: DEFAULT_EPS * max(1, S), S = max||q|| * (|w_a| max||g_a|| +
+    |w_b| max||g_b||) (per-query weights: their largest magnitudes).  L2-normalised embeddings with convex weights give
+    S <= 1 up to bf16 rounding, i.e. the default; projected galleries (BilinearFusionHead), raw features or weights
+    above one widen the margin instead of silently voiding the certificate."""
+    def wmax(w):
+        if isinstance(w, torch.Tensor):
+            return float(w.abs().max().item()) if w.numel() else 0.0
+        if isinstance(w, np.ndarray):
+            return float(np.abs(w).max()) if w.size else 0.0
+        return abs(float(w))
+    s = row_norm_max(gal_a) * wmax(w_a)
+    if gal_b is not None:
+        s += row_norm_max(gal_b) * wmax(w_b)
+    s *= row_norm_max(q)
+    if not np.isfinite(s):
+        raise KemrError("embeddings contain non-finite values: the scan paths need finite inputs")
+    return base * max(1.0, s * (1.0 + 2.0 ** -7))
 
 
 def synth_rows(rows: int, D: int, seed: int, row_base: int = 0, out: Optional[torch.Tensor] = None):
@@ -254,13 +296,16 @@ def scan_topk_raw(q, gal_a, gal_b, w_a, w_b, alpha, hits: Optional[KGHits], k, k
 
 def scan_topk(q: torch.Tensor, gal_a: torch.Tensor, gal_b: Optional[torch.Tensor] = None,
               w_a: float = 1.0, w_b: float = 0.0, alpha: float = 1.0, hits: Optional[KGHits] = None,
-              k: int = 10, k_sel: Optional[int] = None, eps: float = DEFAULT_EPS, idx_base: int = 0,
+              k: int = 10, k_sel: Optional[int] = None, eps: Optional[float] = None, idx_base: int = 0,
               path: int = PATH_AUTO, certify: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """Fused similarity scan + weighted fusion + KG boost + top-k.
 
     Returns (idx int64 [Q,k], score float64 [Q,k]) ordered by (canonical score desc, index asc).
     With certify=True the per-query certificate is read back and uncertified queries are re-run
     with a wider selection margin (raises if the margin cannot be certified at k_sel=128).
+    eps=None scales the selection margin with the embeddings' norms and the weights (`eps_for`; one small
+    read-back per new query batch); pass a float to skip that (DEFAULT_EPS holds for normalised embeddings and
+    convex weights).
     """
     _require_cuda()
     _check_pair(q, gal_a, gal_b)
@@ -268,6 +313,8 @@ def scan_topk(q: torch.Tensor, gal_a: torch.Tensor, gal_b: Optional[torch.Tensor
     M = gal_a.shape[0]
     k_sel = default_k_sel(k) if k_sel is None else k_sel
     mh = hits.max_per_query if hits else 0
+    if eps is None:
+        eps = eps_for(q, gal_a, gal_b, w_a, w_b)
     gated = _per_query(w_a) or _per_query(w_b)               # per-query weights (gated fusion heads)
     if gated:
         w_a, w_b = query_weights(w_a, w_b, Q, q.device)
@@ -281,7 +328,12 @@ def scan_topk(q: torch.Tensor, gal_a: torch.Tensor, gal_b: Optional[torch.Tensor
         ks = k_sel
         while bad.numel():
             if ks >= MAX_K_SEL:
-                raise KemrError(f"{bad.numel()} queries could not be certified at k_sel={ks}, eps={eps}")
+                # more rows than the widest selection holds sit within 2*eps of the k-th score (duplicated or
+                # degenerate embeddings): decide those queries exactly instead of giving up (the reference just
+                # returns a ranking)
+                _exact_topk(q, gal_a, gal_b, w_a, w_b, alpha, hits, k, eps, idx_base, bad, gated, score, idx, path)
+                flags[bad] = 0
+                break
             ks = min(MAX_K_SEL, ks * 2)
             sub_hits = hits.subset(bad) if hits is not None else None
             qs = q[bad].contiguous()
@@ -298,6 +350,39 @@ def scan_topk(q: torch.Tensor, gal_a: torch.Tensor, gal_b: Optional[torch.Tensor
             bad = bad[torch.nonzero(f2 & FLAG_UNCERTIFIED).flatten()]
     _LAST_FLAGS[0] = flags
     return idx, score
+
+
+def _exact_topk(q, gal_a, gal_b, w_a, w_b, alpha, hits, k, eps, idx_base, bad, gated, score, idx, path):
+    """Exact top-k of the queries `bad` whatever the data: every row whose fp32 scan score lies within 2*eps of the
+    k-th best fp32 score (plus every KG hit) is re-scored canonically and ordered by (score desc, index asc).  Slow
+    path for degenerate inputs only (hundreds of rows tied around the k-th score)."""
+    M = gal_a.shape[0]
+    for qi in bad.tolist():
+        qs = q[qi:qi + 1].contiguous()
+        wa1, wb1 = (w_a[qi:qi + 1].contiguous(), w_b[qi:qi + 1].contiguous()) if gated else (w_a, w_b)
+        wa32, wb32 = (float(wa1[0]), float(wb1[0])) if gated else (float(w_a), float(w_b))
+        dense = score_matrix(qs, gal_a, gal_b, wa32, wb32, path=path)[0]
+        kk = min(k, M)
+        thr = torch.topk(dense, kk).values[-1] - 2.0 * eps * (1.0 + 1.0 / 64.0) - 1e-30
+        rows = torch.nonzero(dense >= thr).flatten()
+        bonus = None
+        if hits is not None:
+            h0, h1 = int(hits.rowptr[qi]), int(hits.rowptr[qi + 1])
+            hc = hits.col[h0:h1].to(torch.int64)
+            rows = torch.unique(torch.cat([rows, hc[(hc >= 0) & (hc < M)]]))
+            b = torch.zeros(M, dtype=torch.float64, device=q.device)
+            b[hc[(hc >= 0) & (hc < M)]] = hits.bonus[h0:h1][(hc >= 0) & (hc < M)]
+            bonus = b[rows]
+        sc = score_pairs(qs, gal_a, gal_b, torch.zeros_like(rows, dtype=torch.int32), rows, wa1 if gated else w_a,
+                         wb1 if gated else w_b, alpha, bonus)
+        order = torch.argsort(rows)                                    # rows ascending, then a STABLE sort by score desc
+        rows, sc = rows[order], sc[order]
+        order = torch.sort(-sc, stable=True).indices[:kk]
+        score[qi, :kk] = sc[order]
+        idx[qi, :kk] = rows[order] + idx_base
+        if kk < k:
+            score[qi, kk:] = float("-inf")
+            idx[qi, kk:] = -1
 
 
 _LAST_FLAGS: List[Optional[torch.Tensor]] = [None]
@@ -351,10 +436,12 @@ def target_bonus(hits: Optional[KGHits], target_idx: torch.Tensor) -> Optional[t
 
 
 def rank_count(q, gal_a, gal_b, t_score: torch.Tensor, t_gidx: torch.Tensor, w_a=1.0, w_b=0.0, alpha=1.0,
-               hits: Optional[KGHits] = None, eps: float = DEFAULT_EPS, idx_base: int = 0,
+               hits: Optional[KGHits] = None, eps: Optional[float] = None, idx_base: int = 0,
                path: int = PATH_AUTO) -> torch.Tensor:
-    """#rows of this shard ranked strictly ahead of each query's target (int64 [Q])."""
+    """#rows of this shard ranked strictly ahead of each query's target (int64 [Q]).  eps=None: `eps_for`."""
     _check_pair(q, gal_a, gal_b)
+    if eps is None:
+        eps = eps_for(q, gal_a, gal_b, w_a, w_b)
     Q, D = q.shape
     M = gal_a.shape[0]
     scale = 1
@@ -380,7 +467,7 @@ def rank_count(q, gal_a, gal_b, t_score: torch.Tensor, t_gidx: torch.Tensor, w_a
 
 
 def rank_targets(q, gal_a, gal_b, target_idx: torch.Tensor, w_a=1.0, w_b=0.0, alpha=1.0,
-                 hits: Optional[KGHits] = None, eps: float = DEFAULT_EPS, path: int = PATH_AUTO) -> torch.Tensor:
+                 hits: Optional[KGHits] = None, eps: Optional[float] = None, path: int = PATH_AUTO) -> torch.Tensor:
     """1-based rank of gallery row target_idx[i] for query i under the canonical ordering."""
     Q = q.shape[0]
     tidx = target_idx.to(device=q.device, dtype=torch.int64).contiguous()

@@ -425,6 +425,78 @@ def test_prepared_sharded_search_on_one_rank(small_set):
             plan.close()
 
 
+def test_degenerate_gallery_falls_back_to_an_exact_ranking():
+    """Hundreds of identical rows around the k-th score cannot be certified by any finite selection: the
+    search then decides those queries exactly instead of raising -- lowest index first among equal scores, like a
+    stable argsort of the reference's matrix."""
+    rng = np.random.default_rng(2)
+    base = synth.make_gallery(8, 64, 3)
+    img = np.repeat(base, 400, axis=0)                                 # 3200 rows, 8 distinct: every score is tied 400 times
+    q = synth.round_to_bf16(synth.l2_normalize(base[:6] + 0.1 * rng.standard_normal((6, 64), dtype=np.float32)))
+    idx, sc = engine.scan_topk(dev(q), dev(img), k=10)
+    can = O.canon_dot64(q, img)
+    widx, wsc = O.canon_topk(can, 10)
+    assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(sc.cpu().numpy(), wsc)
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_eps_bound_holds_on_adversarial_inputs(path):
+    """The certificate rests on |fp32 scan score - canonical| <= eps (engine.DEFAULT_EPS for unit-norm inputs, derived
+    in DESIGN.md §2 from one rounding per accumulator update).  Worst cases for fp32 accumulation: same-sign vectors
+    (no cancellation, the running sum grows monotonically), the largest supported D, two galleries sharing one
+    accumulator, near-duplicate rows."""
+    D, M, Q = 1024, 4096, 130
+    if not path_ok(path, D, Q=Q, M=M, G=2, equal=True):
+        pytest.skip("tcgen05 path unavailable")
+    rng = np.random.default_rng(5)
+    pos = np.abs(rng.standard_normal((M, D), dtype=np.float32)) + 0.5            # all components positive
+    img = synth.round_to_bf16(synth.l2_normalize(pos))
+    tgt = synth.round_to_bf16(synth.l2_normalize(pos[::-1] * 0.9 + 0.1))
+    img[1::64] = img[0::64]                                                      # exact duplicates
+    nxt = img[2::64].copy()
+    img[3::64] = synth.round_to_bf16(nxt + np.float32(2.0 ** -9) * (nxt > 0.03))  # near duplicates: a few bf16 ulps away
+    q = synth.round_to_bf16(synth.l2_normalize(np.abs(rng.standard_normal((Q, D), dtype=np.float32)) + 0.5))
+    qd, a, b = dev(q), dev(img), dev(tgt)
+    for wa, wb in ((0.5, 0.5), (0.1, 0.9), (1.0, 0.0)):
+        two = wb != 0.0
+        can = O.canon_fused64(O.canon_dot64(q, img), O.canon_dot64(q, tgt) if two else None, wa, wb)
+        dense = engine.score_matrix(qd, a, b if two else None, wa, wb, path=path).cpu().numpy()
+        err = float(np.abs(dense.astype(np.float64) - can).max())
+        assert err < engine.DEFAULT_EPS, (wa, wb, err)
+        idx, sc = engine.scan_topk(qd, a, b if two else None, wa, wb, k=10, path=path)
+        widx, wsc = O.canon_topk(can, 10)
+        assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(sc.cpu().numpy(), wsc)
+        print(f"path {path} weights {(wa, wb)}: max |fp32 - canonical| = {err:.3e} (eps {engine.DEFAULT_EPS:.1e})")
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_unnormalised_embeddings_scale_the_margin(path):
+    """Rows of norm ~10 and weights above one: the margin follows eps_for = DEFAULT_EPS * max||q|| *
+    (|w_a| max||g_a|| + |w_b| max||g_b||); top-k and ranks stay exact against the oracle, and the fp32 scan scores stay
+    inside that margin."""
+    D, M, Q = 256, 3000, 150
+    if not path_ok(path, D, Q=Q, M=M, G=2):
+        pytest.skip("tcgen05 path unavailable")
+    rng = np.random.default_rng(9)
+    img = synth.round_to_bf16(rng.standard_normal((M, D), dtype=np.float32) * np.float32(10.0 / np.sqrt(D)))
+    tgt = synth.round_to_bf16(rng.standard_normal((M, D), dtype=np.float32) * np.float32(7.0 / np.sqrt(D)))
+    q = synth.round_to_bf16(img[:Q] * np.float32(0.3) + rng.standard_normal((Q, D), dtype=np.float32) * np.float32(3.0 / np.sqrt(D)))
+    qd, a, b = dev(q), dev(img), dev(tgt)
+    wa, wb = 1.5, 2.25
+    eps = engine.eps_for(qd, a, b, wa, wb)
+    nq, na, nb = (float(np.linalg.norm(x.astype(np.float64), axis=1).max()) for x in (q, img, tgt))
+    assert eps >= engine.DEFAULT_EPS * nq * (wa * na + wb * nb) and eps < 1.02 * engine.DEFAULT_EPS * nq * (wa * na + wb * nb)
+    can = O.canon_fused64(O.canon_dot64(q, img), O.canon_dot64(q, tgt), wa, wb)
+    dense = engine.score_matrix(qd, a, b, wa, wb, path=path).cpu().numpy()
+    assert float(np.abs(dense.astype(np.float64) - can).max()) < eps
+    idx, sc = engine.scan_topk(qd, a, b, wa, wb, k=10, path=path)                # eps=None: scaled automatically
+    widx, wsc = O.canon_topk(can, 10)
+    assert np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(sc.cpu().numpy(), wsc)
+    assert int((engine.last_flags() != 0).sum()) == 0
+    ranks = engine.rank_targets(qd, a, b, torch.arange(Q, device="cuda"), wa, wb, path=path)
+    assert np.array_equal(ranks.cpu().numpy(), O.canon_rank(can, np.arange(Q)))
+
+
 def test_sharded_index_maps_global_ids_to_its_own_uuid_slice(small_set):
     """A shard with idx_base > 0 returns GLOBAL row ids; CLIPRetriever.search must look them up in the shard's own
     uuid slice."""

@@ -43,7 +43,7 @@ def make_split(M, n_qb, units, gran):
 def stripe_begin(w, s):
     if s >= w["s_full"] and w["units"] == w["s_full"] * w["n_qb"]:
         return w["M"]
-    x = s * w["n_qb"] * w["M"] * 2 // (2 * w["units"] - (w["units"] - w["s_full"] * w["n_qb"]))
+    x = s * w["n_qb"] * w["M"] * 3 // (3 * w["units"] - 2 * (w["units"] - w["s_full"] * w["n_qb"]))
     return min(x - x % w["gran"], w["M"])
 
 
@@ -75,6 +75,13 @@ def unit_ordinal(w, u, qb):
     return w["s_full"] + (u - full - first)
 
 
+def seg_tile_rows(rows, n_tile, gran):
+    if gran >= n_tile or rows <= 0:
+        return n_tile
+    nt = -(-rows // n_tile)
+    return min(n_tile, -(-(-(-rows // nt)) // gran) * gran)
+
+
 def simulate(p, M):
     """(covered[qb, row] count, owner[(qb, ord)] -> unit, MMA rows per unit) exactly as the kernel's roles walk a unit's
     share of the work (unit_walk, KEMR_FOR_TILES) and as its epilogue derives the part slots."""
@@ -98,9 +105,10 @@ def simulate(p, M):
             rend = min(p_hi, blk0 + mod) - blk0
             ordinal = unit_ordinal(w, unit, qb)
             r = pos - blk0
+            tsz = seg_tile_rows(rend - r, n_tile, gran if partial_ok else n_tile)
             while r < rend:
                 row0 = base + r
-                ncols = min(n_tile, rend - r)
+                ncols = min(tsz, rend - r)
                 assert row0 + ncols <= M
                 g_ = 32 if p["cl"] >= 2 else 16
                 nmma = min(256, (ncols + g_ - 1) // g_ * g_) if partial_ok else 256
@@ -110,7 +118,7 @@ def simulate(p, M):
                 o = (row0 * vq // M if vq > 1 else 0) + ordinal
                 assert 0 <= 2 * o + 1 < p["parts"], f"slot {2 * o + 1} outside the {p['parts']} parts"
                 assert owner.setdefault((qb, o), unit) == unit, "two units write the same part slot"
-                r += n_tile
+                r += tsz
             pos = blk0 + rend
         work.append(mma_rows)
     # the units of one full stripe scan the same rows (that is what keeps the gallery reads of the blocks together)
@@ -148,7 +156,7 @@ def test_plan_tiles_the_work_without_slot_collisions(shape, sms, quads):
         # partial tiles level the tensor work: no unit does more than the mean plus the rounding of its segments (a
         # remainder unit may walk every query block: one 32-row round-up and one snapped boundary per block)
         # (remainder units count as half a unit, so the full units carry up to units / (units - r / 2) of the mean)
-        assert max(work) <= sum(work) / len(work) * 1.10 + 32 * (2 * p["n_qb"] + 4), (max(work), sum(work) / len(work))
+        assert max(work) <= sum(work) / len(work) * 1.12 + 32 * (2 * p["n_qb"] + 4), (max(work), sum(work) / len(work))
 
 
 def test_plan_random_shapes():
