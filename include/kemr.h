@@ -259,6 +259,15 @@ int kemr_index_search_host(kemr_index_t* index, const float* q_host, int Q, int 
                            int k, int64_t* out_idx_host, double* out_score64_host,
                            int32_t* out_flags_host);
 
+/* the same with queries that are already bf16 bit patterns [Q, D] (e.g. the output of a bf16 encoder): half the bytes
+ * cross PCIe and no quantise kernel runs. */
+int kemr_index_search_host_bf16(kemr_index_t* index, const uint16_t* q_bf16_host, int Q,
+                                double w_a, double w_b, double alpha,
+                                const int64_t* hit_rowptr_host, const int32_t* hit_col_host,
+                                const double* hit_bonus_host,
+                                int k, int64_t* out_idx_host, double* out_score64_host,
+                                int32_t* out_flags_host);
+
 /* ---- the data path either side of the scan ------------------------------------
 
  * KG-hit CSR builder on the device.  Input: per query the LIST of gallery rows the knowledge graph returned, in

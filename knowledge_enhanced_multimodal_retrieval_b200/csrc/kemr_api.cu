@@ -212,7 +212,7 @@ static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, 
     // (enough gallery tiles for the candidate lists k_sel needs); warp-dot for the latency-bound tiny
     // batches and as the general fallback
     pl->path = KEMR_PATH_WARP;
-    if (dv.major == 10 && Q >= 5 && mma_supported(D, K) && mma_make_plan(Q, M, D, G, K, mode, dv.sms, dv.quads, equal_weights, &pl->mma) == 0)
+    if (dv.major == 10 && Q >= 3 && mma_supported(D, K) && mma_make_plan(Q, M, D, G, K, mode, dv.sms, dv.quads, equal_weights, &pl->mma) == 0)
       pl->path = KEMR_PATH_MMA;
   }
   if (pl->path == KEMR_PATH_MMA) {
@@ -947,15 +947,28 @@ extern "C" int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal
   return KEMR_OK;
 }
 
-extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int Q, int normalize,
-                                      double w_a, double w_b, double alpha, const int64_t* hit_rowptr_host,
-                                      const int32_t* hit_col_host, const double* hit_bonus_host, int k,
-                                      int64_t* out_idx_host, double* out_score64_host, int32_t* out_flags_host) {
-  if (!ix || !q_host || !out_idx_host || !out_score64_host) return fail(KEMR_ERR_ARG, "index_search_host: null pointer");
+// q_bf16 != null: the queries arrive as bf16 bit patterns (half the bytes over PCIe, no quantise kernel)
+static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const uint16_t* q_bf16, int Q, int normalize,
+                                  double w_a, double w_b, double alpha, const int64_t* hit_rowptr_host,
+                                  const int32_t* hit_col_host, const double* hit_bonus_host, int k,
+                                  int64_t* out_idx_host, double* out_score64_host, int32_t* out_flags_host) {
+  if (!ix || (!q_host && !q_bf16) || !out_idx_host || !out_score64_host) return fail(KEMR_ERR_ARG, "index_search_host: null pointer");
   if (Q <= 0 || Q > ix->max_q || k <= 0 || k > ix->max_k) return fail(KEMR_ERR_ARG, "index_search_host: Q or k beyond the handle's limits");
   cudaStream_t st = ix->stream;
   const size_t qbytes = (size_t)Q * ix->D * 4;
-  if (Q <= kSmallBatch) {
+  // Page-locked caller buffers are used IN PLACE by the kernels (the quantise kernel reads the fp32 queries over
+  // PCIe, the select kernel stores the results straight into the caller's arrays): no copy engine hop in either
+  // direction.  Pageable buffers are staged through the handle's page-locked memory.
+  auto mapped = [](const void* p) -> void* {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost) return nullptr;
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return d;
+  };
+  static const bool no_zero_copy = getenv("KEMR_NO_ZERO_COPY") != nullptr;
+  if (Q <= kSmallBatch && !q_bf16) {
     // Serving-size batches: everything the request brings (queries, KG-hit CSR) goes over in ONE copy, and ONE kernel
     // does the rest (quantise, scan, selection); results come back with one copy per array.  2 + 3 copies and two
     // kernels cost 119 us for a batch of one; the scan itself is ~35 us.
@@ -975,42 +988,46 @@ extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int
     }
     CUDA_TRY(cudaMemcpyAsync(ix->d_blob, ix->h_blob, total, cudaMemcpyHostToDevice, st));
     const int ksel = std::min(kMaxKSel, (k + 6 + 7) / 8 * 8);
+    // results: the selection stage stores straight into page-locked host memory (the caller's arrays when they are
+    // page-locked, else the handle's staging arrays) -- no device-to-host copy, the stream synchronise is the fence
+    int64_t* oi = static_cast<int64_t*>(mapped(out_idx_host));
+    double* os = static_cast<double*>(mapped(out_score64_host));
+    int32_t* of = out_flags_host ? static_cast<int32_t*>(mapped(out_flags_host)) : nullptr;
+    const bool direct = !no_zero_copy && oi && os && (!out_flags_host || of);
+    if (!direct) {
+      oi = static_cast<int64_t*>(mapped(ix->h_idx)); os = static_cast<double*>(mapped(ix->h_score));
+      of = static_cast<int32_t*>(mapped(ix->h_flags));
+      if (!oi || !os || !of) return fail(KEMR_ERR_CUDA, "index_search_host: staging buffers are not mapped");
+    } else if (!of) {
+      of = static_cast<int32_t*>(mapped(ix->h_flags));
+    }
     int rc = scan_topk_impl(ix->d_q, Q, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, nullptr, nullptr, alpha,
                             hit_rowptr_host ? reinterpret_cast<const int64_t*>(ix->d_blob + o_rp) : nullptr,
                             reinterpret_cast<const int32_t*>(ix->d_blob + o_co), reinterpret_cast<const double*>(ix->d_blob + o_bo),
-                            max_hits, k, ksel, 2e-5, 0, ix->d_score, nullptr, ix->d_idx, ix->d_flags, ix->ws, ix->ws_bytes,
+                            max_hits, k, ksel, 2e-5, 0, os, nullptr, oi, of, ix->ws, ix->ws_bytes,
                             KEMR_PATH_WARP, st, reinterpret_cast<const float*>(ix->d_blob), normalize);
     if (rc) return rc;
-    // one device-to-host copy: score | idx | flags are adjacent in the handle's staging? they are separate arrays,
-    // small ones: three copies of <= 320 bytes each cost less than one extra kernel to pack them
-    CUDA_TRY(cudaMemcpyAsync(ix->h_idx, ix->d_idx, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(ix->h_score, ix->d_score, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(ix->h_flags, ix->d_flags, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    memcpy(out_idx_host, ix->h_idx, (size_t)Q * k * 8);
-    memcpy(out_score64_host, ix->h_score, (size_t)Q * k * 8);
-    if (out_flags_host) memcpy(out_flags_host, ix->h_flags, (size_t)Q * 4);
+    if (!direct) {
+      memcpy(out_idx_host, ix->h_idx, (size_t)Q * k * 8);
+      memcpy(out_score64_host, ix->h_score, (size_t)Q * k * 8);
+      if (out_flags_host) memcpy(out_flags_host, ix->h_flags, (size_t)Q * 4);
+    }
     return KEMR_OK;
   }
-  // Page-locked caller buffers are used IN PLACE by the kernels (the quantise kernel reads the fp32 queries over
-  // PCIe, the select kernel stores the results straight into the caller's arrays): no copy engine hop in either
-  // direction.  Pageable buffers are staged through the handle's page-locked memory.
-  auto mapped = [](const void* p) -> void* {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    if (at.type != cudaMemoryTypeHost) return nullptr;
-    void* d = nullptr;
-    if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return d;
-  };
-  static const bool no_zero_copy = getenv("KEMR_NO_ZERO_COPY") != nullptr;
-  const float* q_dev_view = no_zero_copy ? nullptr : static_cast<const float*>(mapped(q_host));
+  const float* q_dev_view = (no_zero_copy || q_bf16) ? nullptr : static_cast<const float*>(mapped(q_host));
   int64_t* oi_view = no_zero_copy ? nullptr : static_cast<int64_t*>(mapped(out_idx_host));
   double* os_view = no_zero_copy ? nullptr : static_cast<double*>(mapped(out_score64_host));
   int32_t* of_view = (no_zero_copy || !out_flags_host) ? nullptr : static_cast<int32_t*>(mapped(out_flags_host));
   const bool q_pinned = q_dev_view != nullptr;
   const bool out_pinned = oi_view && os_view && (!out_flags_host || of_view);
-  if (!q_pinned) {
+  if (q_bf16) {
+    // bf16 bit patterns: one copy-engine transfer of Q*D*2 bytes straight into the scan's query buffer (page-locked
+    // caller memory is read in place by the copy engine, pageable memory is staged)
+    const void* src = q_bf16;
+    if (!mapped(q_bf16)) { memcpy(ix->h_q, q_bf16, qbytes / 2); src = ix->h_q; }
+    CUDA_TRY(cudaMemcpyAsync(ix->d_q, src, qbytes / 2, cudaMemcpyHostToDevice, st));
+  } else if (!q_pinned) {
     memcpy(ix->h_q, q_host, qbytes);
     CUDA_TRY(cudaMemcpyAsync(ix->d_qf32, ix->h_q, qbytes, cudaMemcpyHostToDevice, st));
   }
@@ -1030,7 +1047,7 @@ extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int
     }
     d_rowptr = ix->d_rowptr;
   }
-  int rc = kemr_quantize_rows(q_pinned ? q_dev_view : ix->d_qf32, ix->d_q, Q, ix->D, normalize, st);
+  int rc = q_bf16 ? KEMR_OK : kemr_quantize_rows(q_pinned ? q_dev_view : ix->d_qf32, ix->d_q, Q, ix->D, normalize, st);
   if (rc) return rc;
   const int ksel = std::min(kMaxKSel, (k + 6 + 7) / 8 * 8);
   rc = kemr_scan_topk(ix->d_q, Q, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, alpha, d_rowptr, ix->d_col,
@@ -1050,6 +1067,24 @@ extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int
   memcpy(out_score64_host, ix->h_score, (size_t)Q * k * 8);
   if (out_flags_host) memcpy(out_flags_host, ix->h_flags, (size_t)Q * 4);
   return KEMR_OK;
+}
+
+extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int Q, int normalize,
+                                      double w_a, double w_b, double alpha, const int64_t* hit_rowptr_host,
+                                      const int32_t* hit_col_host, const double* hit_bonus_host, int k,
+                                      int64_t* out_idx_host, double* out_score64_host, int32_t* out_flags_host) {
+  if (!q_host) return fail(KEMR_ERR_ARG, "index_search_host: null query pointer");
+  return index_search_host_impl(ix, q_host, nullptr, Q, normalize, w_a, w_b, alpha, hit_rowptr_host, hit_col_host, hit_bonus_host, k,
+                                out_idx_host, out_score64_host, out_flags_host);
+}
+
+extern "C" int kemr_index_search_host_bf16(kemr_index_t* ix, const uint16_t* q_bf16_host, int Q,
+                                           double w_a, double w_b, double alpha, const int64_t* hit_rowptr_host,
+                                           const int32_t* hit_col_host, const double* hit_bonus_host, int k,
+                                           int64_t* out_idx_host, double* out_score64_host, int32_t* out_flags_host) {
+  if (!q_bf16_host) return fail(KEMR_ERR_ARG, "index_search_host_bf16: null query pointer");
+  return index_search_host_impl(ix, nullptr, q_bf16_host, Q, 0, w_a, w_b, alpha, hit_rowptr_host, hit_col_host, hit_bonus_host, k,
+                                out_idx_host, out_score64_host, out_flags_host);
 }
 
 // ----------------------------------------------------------------------------- KG-hit CSR builder (device)

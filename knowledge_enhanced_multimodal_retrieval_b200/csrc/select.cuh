@@ -101,6 +101,7 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
   __shared__ unsigned long long s_bound;     // largest key any stage rejected (0 = nothing rejected)
   __shared__ unsigned long long s_cut;
   __shared__ int s_nlist, s_extra, s_nsurv, s_nsel, s_first;
+  __shared__ long long s_h0, s_h1;           // this query's range of the KG-hit CSR, fetched while the lists merge
   __shared__ double s_kth;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __syncthreads();                                          // a previous query of this CTA is done with the static state
@@ -113,14 +114,27 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
   for (int p = tid; p < P; p += T) s_heads[p] = a.part_keys[((size_t)p * a.Q + qi) * Kp];
   for (int i = tid; i < K; i += T) { s_selk[i] = 0; s_lid[i] = -1; }
   if (tid == 0) { s_bound = 0; s_cut = 0; s_nlist = 0; s_extra = 0; s_nsurv = 0; s_nsel = 0; s_first = K; s_kth = -INFINITY; }
+  if (tid == 32 % T && a.hit_rowptr) { s_h0 = a.hit_rowptr[qi]; s_h1 = a.hit_rowptr[qi + 1]; }
   __syncthreads();
-  for (int p = tid; p < P; p += T) {
-    const uint64_t x = s_heads[p];
-    if (!x) continue;
-    int r = 0;
-    for (int j = 0; j < P; ++j) r += s_heads[j] > x ? 1 : 0;
-    if (r < K) { s_lid[r] = p; atomicAdd(&s_nlist, 1); }
-    else atomicMax(&s_bound, (unsigned long long)x);       // whole list rejected: nothing in it beats its head
+  {
+    // (a 64-bit atomicMax in shared memory is a compare-and-swap loop: hundreds of rejected heads hammering one word
+    // cost 6 us of a batch-1 selection -- reduce per warp first, one atomic per warp)
+    unsigned long long rej = 0;
+    for (int p0 = 0; p0 < P; p0 += T) {
+      const int p = p0 + tid;
+      const uint64_t x = p < P ? s_heads[p] : 0;
+      if (x) {
+        int r = 0;
+        for (int j = 0; j < P; ++j) r += s_heads[j] > x ? 1 : 0;
+        if (r < K) { s_lid[r] = p; atomicAdd(&s_nlist, 1); }
+        else if (x > rej) rej = x;                          // whole list rejected: nothing in it beats its head
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, rej, o);
+      rej = other > rej ? other : rej;
+    }
+    if (lane == 0 && rej) atomicMax(&s_bound, rej);
   }
   __syncthreads();
 
@@ -223,7 +237,7 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
   for (int i = tid; i < nsel; i += T) { s_row[i] = (int32_t)key_row(s_selk[i]); s_bonus[i] = 0.0; s_has[i] = 0; }
   __syncthreads();
   if (a.hit_rowptr) {
-    const int64_t h0 = a.hit_rowptr[qi], h1 = a.hit_rowptr[qi + 1];
+    const int64_t h0 = s_h0, h1 = s_h1;
     for (int64_t h = h0 + tid; h < h1; h += T) {
       const int32_t col = a.hit_col[h];
       if (col < 0 || (int64_t)col >= a.M) continue;
@@ -240,6 +254,16 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
     __syncthreads();
   }
   const int n = min(nsel + s_extra, MC);
+  // every candidate row goes to L2 now, in one wave: the re-scoring below then walks the candidates two at a time per
+  // warp with L2 latency instead of a DRAM round trip per step
+  {
+    const int lines = (a.D * 2 + 127) >> 7;                 // 128-byte lines per row
+    for (int i = tid; i < n * lines * a.G; i += T) {
+      const int c = i / (lines * a.G), rest = i - c * lines * a.G, g = rest / lines, l = rest - g * lines;
+      const unsigned char* ptr = reinterpret_cast<const unsigned char*>(a.gal[g] + (size_t)s_row[c] * a.D) + (size_t)l * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+  }
   KEMR_SEL_STAMP(4);
 
   // C (two register sets, roles alternate).  An item is two rows re-scored together with interleaved reduction

@@ -109,8 +109,12 @@ class HostIndex:
     def search(self, queries_f32: np.ndarray, k: int = 10, t2i_weight: float = 1.0, t2t_weight: float = 0.0,
                alpha: float = 1.0, hits_csr=None, normalize: bool = False, out=None):
         """queries fp32 [Q, D] (host) -> (idx int64 [Q,k], score float64 [Q,k], flags int32 [Q]) host arrays.
-        hits_csr = (rowptr int64, col int32, bonus float64) host arrays or None."""
-        q = np.ascontiguousarray(queries_f32, dtype=np.float32)
+        hits_csr = (rowptr int64, col int32, bonus float64) host arrays or None.  A uint16 array is taken as bf16 bit
+        patterns (kemr_index_search_host_bf16: half the PCIe bytes, no quantise kernel; `normalize` must be False)."""
+        bf16 = isinstance(queries_f32, np.ndarray) and queries_f32.dtype == np.uint16
+        if bf16 and normalize:
+            raise KemrError("bf16 queries cannot be re-normalised")
+        q = np.ascontiguousarray(queries_f32) if bf16 else np.ascontiguousarray(queries_f32, dtype=np.float32)
         Q = q.shape[0]
         if out is None:
             out = (np.empty((Q, k), np.int64), np.empty((Q, k), np.float64), np.empty((Q,), np.int32))
@@ -120,7 +124,11 @@ class HostIndex:
             rp, cc, bb = (np.ascontiguousarray(hits_csr[0], np.int64), np.ascontiguousarray(hits_csr[1], np.int32),
                           np.ascontiguousarray(hits_csr[2], np.float64))
         vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
-        _lib.check(self._lib.kemr_index_search_host(self._h, vp(q), Q, int(normalize), float(t2i_weight),
-                                                    float(t2t_weight), float(alpha), vp(rp), vp(cc), vp(bb), k,
-                                                    vp(idx), vp(score), vp(flags)))
+        if bf16:
+            _lib.check(self._lib.kemr_index_search_host_bf16(self._h, vp(q), Q, float(t2i_weight), float(t2t_weight),
+                                                             float(alpha), vp(rp), vp(cc), vp(bb), k, vp(idx), vp(score), vp(flags)))
+        else:
+            _lib.check(self._lib.kemr_index_search_host(self._h, vp(q), Q, int(normalize), float(t2i_weight),
+                                                        float(t2t_weight), float(alpha), vp(rp), vp(cc), vp(bb), k,
+                                                        vp(idx), vp(score), vp(flags)))
         return idx, score, flags
