@@ -240,8 +240,8 @@ def workload_config(args, cfg, world):
             "queries_per_step": cfg["Q"] * world, "gallery_rows": cfg["M"], "dim": cfg["D"],
             "galleries": 2 if cfg["fused"] else 1, "k": cfg["k"],
             "kg_boost": f"alpha {KG_ALPHA} / beta {KG_BETA}, ~Poisson(20) KG hits per query (CSR in the step)" if cfg.get("kg") else None,
-            "parallelism": "single GPU" if world == 1 else f"query-sharded x{world}, gallery replicated, "
-                                                           "NCCL all-gather of top-k",
+            "parallelism": "single GPU" if world == 1 else f"query-sharded x{world}, gallery replicated, results "
+                                                           f"exchanged by {'NVLink peer stores fused into the selection kernel' if getattr(args, 'exchange', 'peer') == 'peer' else 'one NCCL all-gather'}",
             "l2": "L2 flushed (512 MiB memset) before every timed step"}
 
 
@@ -538,10 +538,24 @@ def run_ours(args, cfg):
     score, idx = packed[0], packed[1].view(torch.int64)                        # the select kernel writes straight into it
     gathered = torch.empty((world, 2, Q, k), dtype=torch.float64, device="cuda") if world > 1 else None
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    # N > 1: every rank searches ITS queries on its replica and all ranks end with all results.  The exchange is fused
+    # into the selection kernel: rows go straight into every rank's buffer over NVLink peer memory (kemr_peer_*), a
+    # small gather kernel waits for the flags; `--exchange nccl` times ONE NCCL all-gather instead.
+    peer = None
+    g_score = g_idx = None
+    if world > 1 and args.exchange == "peer":
+        from knowledge_enhanced_multimodal_retrieval_b200.distributed import PeerExchange
+        peer = PeerExchange(Q, k)
+        g_score = torch.empty((world, Q, k), dtype=torch.float64, device="cuda")
+        g_idx = torch.empty((world, Q, k), dtype=torch.int64, device="cuda")
 
     def step():
+        if peer is not None:
+            peer.begin()
         engine.scan_topk_raw(q, img, tgt, wi, wt, alpha, hits, k, k_sel, engine.DEFAULT_EPS, 0, score, idx, flags, ws)
-        if world > 1:
+        if peer is not None:
+            peer.gather(Q, k, g_score, g_idx)
+        elif world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
 
     sampler = ClockSampler(local)
@@ -581,6 +595,10 @@ def run_ours(args, cfg):
         e2e_s = float(t.item())
     assert np.array_equal(out[0], idx.cpu().numpy()), "host-buffer path disagrees with the device path"
     hi.close()
+    if peer is not None:
+        # the gathered copy of this rank's own rows must be the rows it computed
+        assert torch.equal(g_idx[rank], idx) and torch.equal(g_score[rank], score), "peer gather disagrees with the local result"
+        peer.close()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the north_star multi-GPU layout beside the headline: a fixed 10 M x 768 gallery, row-sharded over the ranks
@@ -631,7 +649,9 @@ def run_ours(args, cfg):
                         "api": "kemr_index_search_host (HostIndex.search): fp32 host queries in, top-k host arrays out; "
                                "gallery resident in HBM; the page-locked step buffers are read / written in place by "
                                "the kernels over PCIe (no staging copy)", "ms_per_step": e2e_s / args.steps * 1e3},
-                "gpu_launches": 2 * args.steps, "launch": "one CUDA graph per step" if graphed else "eager launches",
+                "gpu_launches": ((1 if engine.scan_plan(Q, M, D, G, k_sel, wi == wt)["path"] != _lib.PATH_MMA else 2)
+                                 + (2 if peer is not None else 0)) * args.steps,
+                "launch": "one CUDA graph per step" if graphed else "eager launches",
                 "roofline": roof, "clocks": clocks,
                 "uncertified_queries": n_uncert, "sm_count": info["sm_count"],
                 "scan_path": "tcgen05" if engine.scan_plan(Q, M, D, G, k_sel, wi == wt)["path"] == _lib.PATH_MMA else "warp-dot"}
@@ -653,6 +673,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: result exchange of the default workload (NVLink peer stores fused into the selection kernel, or one NCCL all-gather)")
     ap.add_argument("--no-sharded", action="store_true", help="skip the row-sharded 10 M-row record of the default workload")
     ap.add_argument("--sharded-rows", type=int, default=10_000_000, help="total gallery rows of the row-sharded record")
     ap.add_argument("--rows-per-gpu", type=int, default=0, help="override the gallery shard size of the sharded workloads")

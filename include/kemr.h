@@ -241,6 +241,9 @@ void* kemr_peer_local_buffer(kemr_peer_t* peer);
 int kemr_peer_destroy(kemr_peer_t* peer);
 int kemr_peer_begin(kemr_peer_t* peer, kemr_stream_t stream);
 int kemr_peer_merge(kemr_peer_t* peer, int Q, int k, double* out_score64, int64_t* out_idx, kemr_stream_t stream);
+/* instead of the merge: the ranks' rows as they are, out_*[rank][Q][k] (every rank searched its OWN queries against a
+ * replica of the gallery and wants everybody's results: an all-gather without a collective launch) */
+int kemr_peer_gather(kemr_peer_t* peer, int Q, int k, double* out_score64, int64_t* out_idx, kemr_stream_t stream);
 
 /* ---- resident gallery handle with HOST-buffer search: the serving-side drop-in for
  * CLIPRetriever.search (clip_retrieval.py:39-40 -> retrieval.py:80,98).  The handle owns its

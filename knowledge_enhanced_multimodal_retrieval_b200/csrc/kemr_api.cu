@@ -226,10 +226,10 @@ static int make_plan(int Q, int64_t M, int D, int G, int K, int mode, int path, 
   }
   pl->CH = (D + 255) / 256;
   if (mode == kModeTopk) {
-    // fused streaming search (scan_stream.cuh): two CTAs per SM and query group of 1, 2 or 4 queries
+    // fused streaming search (scan_stream.cuh): one 16-warp CTA per SM and query group of 1, 2 or 4 queries
     pl->QB = Q == 1 ? 1 : ((Q == 2 || pl->CH >= 3) ? 2 : 4);      // four queries x 768-d do not fit the registers of 2 CTAs / SM
     pl->groups = (Q + pl->QB - 1) / pl->QB;
-    pl->P = (int)std::min<int64_t>(2 * (dv.sms > 0 ? dv.sms : 1), std::max<int64_t>(1, (M + 31) / 32));
+    pl->P = (int)std::min<int64_t>(dv.sms > 0 ? dv.sms : 1, std::max<int64_t>(1, (M + 31) / 32));
     pl->Kp = K;
     return KEMR_OK;
   }
@@ -855,6 +855,18 @@ extern "C" int kemr_peer_begin(kemr_peer_t* p, kemr_stream_t stream) {
   peer_bump_kernel<<<1, 1, 0, S(stream)>>>(reinterpret_cast<unsigned int*>(p->local + p->epoch_off));
   LAUNCH_CHECK("peer_bump_kernel");
   g_push_peer = p;
+  return KEMR_OK;
+}
+
+extern "C" int kemr_peer_gather(kemr_peer_t* p, int Q, int k, double* out_score64, int64_t* out_idx, kemr_stream_t stream) {
+  if (!p || !out_score64 || !out_idx || Q <= 0 || k <= 0 || Q > p->max_q || k > p->max_k)
+    return fail(KEMR_ERR_ARG, "peer_gather: bad argument (Q <= %d, k <= %d)", p ? p->max_q : 0, p ? p->max_k : 0);
+  if (g_push_peer == p) return fail(KEMR_ERR_ARG, "peer_gather: no kemr_scan_topk call since kemr_peer_begin");
+  const size_t block = (size_t)p->max_q * p->max_k;
+  gather_peer_kernel<<<dim3(Q, p->world), 32, 0, S(stream)>>>(p->local, (long long)p->idx_region, (long long)p->flag_region,
+                                                              (long long)block, p->world, p->max_q, Q, k, out_score64, out_idx,
+                                                              reinterpret_cast<const unsigned int*>(p->local + p->epoch_off));
+  LAUNCH_CHECK("gather_peer_kernel");
   return KEMR_OK;
 }
 

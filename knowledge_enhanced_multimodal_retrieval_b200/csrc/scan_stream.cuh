@@ -1,7 +1,7 @@
 // HBM-streaming warp-dot search for small, latency-bound query batches, scan + selection in ONE launch
 // (north_star kernel 1b + 2 for batch 1..4; BASELINE config 3).
 //
-// Two CTAs of eight warps per SM; a CTA owns a contiguous range of gallery rows.  A warp takes two rows per step:
+// One CTA of sixteen warps per SM; a CTA owns a contiguous range of gallery rows.  A warp takes two rows per step:
 // fully coalesced 16-byte loads that bypass L1 (lane l owns pieces l, l+32, ...), all issued before the first use, so
 // sixteen warps keep ~100 KB per SM in flight -- for a 132 MB gallery (43 000 x 768-d x 2) a plain read kernel of
 // this shape is the fastest way through the data (tools/microbench/stream_floor.cu: 28.8 us, against 32.8 us for a
@@ -22,7 +22,7 @@
 
 namespace kemr {
 
-constexpr int kStreamWarps = 8;
+constexpr int kStreamWarps = 16;                          // one 512-thread CTA per SM: half as many lists to merge as 2 x 8 warps, twice the threads in the selection
 constexpr int kStreamThreads = kStreamWarps * 32;
 constexpr int kStreamRW = 2;                              // rows per warp and step
 constexpr int kStreamRows = kStreamWarps * kStreamRW;     // rows per CTA and step
@@ -102,7 +102,7 @@ __device__ __forceinline__ int stream_value_of(int lane) {
 }
 
 template <int QB, int CH, int NP>
-__global__ void __launch_bounds__(kStreamThreads, 2) scan_stream_kernel(StreamArgs a) {
+__global__ void __launch_bounds__(kStreamThreads, 1) scan_stream_kernel(StreamArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* cand = reinterpret_cast<uint64_t*>(smem + a.cand_off);     // [QB][kStreamCand]
   uint64_t* best = cand + (size_t)QB * kStreamCand;                     // [QB][kMaxKSel]

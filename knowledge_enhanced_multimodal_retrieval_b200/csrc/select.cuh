@@ -119,13 +119,22 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
   {
     // (a 64-bit atomicMax in shared memory is a compare-and-swap loop: hundreds of rejected heads hammering one word
     // cost 6 us of a batch-1 selection -- reduce per warp first, one atomic per warp)
+    // Only the K largest heads matter.  A warp first finds the K-th largest head of the whole set by looking at its
+    // own slice: every thread counts how many heads beat its head with four independent accumulators (the loop is
+    // latency-bound otherwise).
     unsigned long long rej = 0;
     for (int p0 = 0; p0 < P; p0 += T) {
       const int p = p0 + tid;
       const uint64_t x = p < P ? s_heads[p] : 0;
       if (x) {
-        int r = 0;
-        for (int j = 0; j < P; ++j) r += s_heads[j] > x ? 1 : 0;
+        int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+        int j = 0;
+        for (; j + 3 < P; j += 4) {
+          r0 += s_heads[j] > x ? 1 : 0; r1 += s_heads[j + 1] > x ? 1 : 0;
+          r2 += s_heads[j + 2] > x ? 1 : 0; r3 += s_heads[j + 3] > x ? 1 : 0;
+        }
+        for (; j < P; ++j) r0 += s_heads[j] > x ? 1 : 0;
+        const int r = (r0 + r1) + (r2 + r3);
         if (r < K) { s_lid[r] = p; atomicAdd(&s_nlist, 1); }
         else if (x > rej) rej = x;                          // whole list rejected: nothing in it beats its head
       }
@@ -254,16 +263,6 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
     __syncthreads();
   }
   const int n = min(nsel + s_extra, MC);
-  // every candidate row goes to L2 now, in one wave: the re-scoring below then walks the candidates two at a time per
-  // warp with L2 latency instead of a DRAM round trip per step
-  {
-    const int lines = (a.D * 2 + 127) >> 7;                 // 128-byte lines per row
-    for (int i = tid; i < n * lines * a.G; i += T) {
-      const int c = i / (lines * a.G), rest = i - c * lines * a.G, g = rest / lines, l = rest - g * lines;
-      const unsigned char* ptr = reinterpret_cast<const unsigned char*>(a.gal[g] + (size_t)s_row[c] * a.D) + (size_t)l * 128;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-    }
-  }
   KEMR_SEL_STAMP(4);
 
   // C (two register sets, roles alternate).  An item is two rows re-scored together with interleaved reduction
@@ -323,12 +322,15 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
       reinterpret_cast<int64_t*>(a.peer_base[d] + a.peer_idx_region)[peer_o + r] = gi;
     }
   };
-  for (int c = tid; c < n; c += T) {
+  // rank by counting, one warp per candidate with the lanes spread over the rivals (a thread per candidate walking
+  // all rivals is a chain of ~n dependent shared-memory compares: 2.7 us for 33 candidates at batch 1)
+  for (int c = warp; c < n; c += W) {
     const double sc = s_score[c];
     const int32_t rc = s_row[c];
     int r = 0;
-    for (int j = 0; j < n; ++j) r += ahead64(s_score[j], s_row[j], sc, rc) ? 1 : 0;
-    if (r < a.k) {
+    for (int j = lane; j < n; j += 32) r += ahead64(s_score[j], s_row[j], sc, rc) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (lane == 0 && r < a.k) {
       emit(r, sc, a.idx_base + rc);
       if (r == a.k - 1) s_kth = sc;
     }
@@ -544,6 +546,38 @@ __global__ void merge_topk_kernel(const double* in_s, const int64_t* in_i, long 
                                   long long flag_stride, const unsigned int* epoch_ptr) {
   (void)Q;
   merge_lists(in_s, in_i, rank_stride, R, k, out_s, out_i, flags, flag_stride, flags ? *epoch_ptr : 0u);
+}
+
+// plain gather out of this rank's exchange buffer: waits for rank r's flag of query qi, then copies its k rows to
+// out[r][qi][:] (query-sharded replicas: every rank ends with every rank's results, no merge)
+__global__ void gather_peer_kernel(const unsigned char* base, long long idx_region, long long flag_region, long long block,
+                                   int world, int max_q, int Q, int k, double* __restrict__ out_s,
+                                   int64_t* __restrict__ out_i, const unsigned int* epoch_ptr) {
+  const int qi = blockIdx.x, r = blockIdx.y;
+  const unsigned int epoch = *epoch_ptr;
+  const size_t half = (size_t)(epoch & 1u) * world;
+  if (threadIdx.x == 0) {
+    const unsigned int* f = reinterpret_cast<const unsigned int*>(base + flag_region) + (half + r) * max_q + qi;
+    unsigned long long t0 = 0;
+    for (unsigned int spins = 0;; ++spins) {
+      unsigned int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v == epoch) break;
+      if ((spins & 0xfffu) == 0xfffu) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (!t0) t0 = t;
+        else if (t - t0 > 20000000000ull) __trap();
+      }
+    }
+  }
+  __syncthreads();
+  const double* ss = reinterpret_cast<const double*>(base) + (half + r) * block + (size_t)qi * k;
+  const long long* si = reinterpret_cast<const long long*>(base + idx_region) + (half + r) * block + (size_t)qi * k;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    out_s[((size_t)r * Q + qi) * k + j] = __ldcg(ss + j);
+    out_i[((size_t)r * Q + qi) * k + j] = (int64_t)__ldcg(si + j);
+  }
 }
 
 // merge of the lists the ranks pushed into this rank's exchange buffer (kemr_peer_*): the epoch picks the buffer half

@@ -66,6 +66,12 @@ class PeerExchange:
         _lib.check(self._lib.kemr_peer_merge(self._h, int(Q), int(k), C.c_void_p(out_score.data_ptr()),
                                              C.c_void_p(out_idx.data_ptr()), torch.cuda.current_stream().cuda_stream))
 
+    def gather(self, Q: int, k: int, out_score: torch.Tensor, out_idx: torch.Tensor):
+        """out_*[rank][Q][k]: every rank's own rows, unmerged (query-sharded replicas)."""
+        from . import _lib
+        _lib.check(self._lib.kemr_peer_gather(self._h, int(Q), int(k), C.c_void_p(out_score.data_ptr()),
+                                              C.c_void_p(out_idx.data_ptr()), torch.cuda.current_stream().cuda_stream))
+
     def close(self):
         if getattr(self, "_h", None):
             if self.world > 1 and dist.is_initialized():

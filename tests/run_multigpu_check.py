@@ -45,6 +45,30 @@ def main():
                     print(f"rank {rank}: plan exchange={exchange} graph={graph} step {step} MISMATCH", flush=True)
                 ok = ok and good
             plan.close()
+    # unmerged gather over peer memory (query-sharded replicas): slot r of every rank = rank r's rows
+    from knowledge_enhanced_multimodal_retrieval_b200.distributed import PeerExchange
+    peer = PeerExchange(q.shape[0], 10)
+    Qn = q.shape[0]
+    qs = torch.roll(q, shifts=rank, dims=0).contiguous()                     # every rank searches different queries
+    ws_ = engine.workspace_for(Qn, img.shape[0], q.shape[1], 16)
+    for step in range(3):
+        sc = torch.empty((Qn, 10), dtype=torch.float64, device="cuda")
+        ix = torch.empty((Qn, 10), dtype=torch.int64, device="cuda")
+        fl = torch.empty((Qn,), dtype=torch.int32, device="cuda")
+        gs = torch.empty((world, Qn, 10), dtype=torch.float64, device="cuda")
+        gi = torch.empty((world, Qn, 10), dtype=torch.int64, device="cuda")
+        peer.begin()
+        engine.scan_topk_raw(qs, img, tgt, 0.5, 0.5, 1.0, None, 10, 16, engine.DEFAULT_EPS, 0, sc, ix, fl, ws_)
+        peer.gather(Qn, 10, gs, gi)
+        ref_s = [torch.empty_like(sc) for _ in range(world)]
+        ref_i = [torch.empty_like(ix) for _ in range(world)]
+        dist.all_gather(ref_s, sc)
+        dist.all_gather(ref_i, ix)
+        good = torch.equal(gs, torch.stack(ref_s)) and torch.equal(gi, torch.stack(ref_i))
+        if not good:
+            print(f"rank {rank}: peer gather step {step} MISMATCH", flush=True)
+        ok = ok and good
+    peer.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
