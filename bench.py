@@ -585,8 +585,11 @@ def run_ours(args, cfg):
         hi.search(qh, k=k, t2i_weight=wi, t2t_weight=wt, alpha=alpha, hits_csr=hits_csr, out=out)
     if world > 1:
         dist.barrier()
+    # serving-size batches take ~60 us per call: K of them are over in a millisecond and one scheduler hiccup on the host
+    # would decide the figure, so they are timed over 10 K calls
+    e2e_steps = args.steps * (10 if Q <= 64 else 1)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         hi.search(qh, k=k, t2i_weight=wi, t2t_weight=wt, alpha=alpha, hits_csr=hits_csr, out=out)
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -644,11 +647,11 @@ def run_ours(args, cfg):
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(args, cfg, world),
-                "e2e": {"value": world * Q * args.steps / e2e_s, "unit": "queries/s",
+                "e2e": {"value": world * Q * e2e_steps / e2e_s, "unit": "queries/s", "steps": e2e_steps,
                         "h2d_bytes_per_step": int(Q * D * 4), "d2h_bytes_per_step": int(Q * k * 16 + Q * 4),
                         "api": "kemr_index_search_host (HostIndex.search): fp32 host queries in, top-k host arrays out; "
                                "gallery resident in HBM; the page-locked step buffers are read / written in place by "
-                               "the kernels over PCIe (no staging copy)", "ms_per_step": e2e_s / args.steps * 1e3},
+                               "the kernels over PCIe (no staging copy)", "ms_per_step": e2e_s / e2e_steps * 1e3},
                 "gpu_launches": ((1 if engine.scan_plan(Q, M, D, G, k_sel, wi == wt)["path"] != _lib.PATH_MMA else 2)
                                  + (2 if peer is not None else 0)) * args.steps,
                 "launch": "one CUDA graph per step" if graphed else "eager launches",

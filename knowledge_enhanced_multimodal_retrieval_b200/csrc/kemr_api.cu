@@ -130,12 +130,13 @@ static inline cudaStream_t S(kemr_stream_t s) { return reinterpret_cast<cudaStre
 // between the kernels of one search step.  Once per function and thread.
 template <class F>
 static inline void prefer_max_smem(F* func) {
-  static thread_local bool done = false;
-  if (!done) {
-    cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaGetLastError();
-    done = true;
-  }
+  // per kernel (instantiations of one template share F, so the flag cannot be a static of this function template)
+  static thread_local std::vector<const void*> done;
+  const void* key = reinterpret_cast<const void*>(func);
+  for (const void* p : done) if (p == key) return;
+  cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaGetLastError();
+  done.push_back(key);
 }
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -259,7 +260,6 @@ extern "C" int kemr_scan_plan(int Q, int64_t M, int D, int galleries, int k_sel,
 static size_t parts_bytes(int P, int Q, int K) { return align_up((size_t)P * Q * K * sizeof(uint64_t)); }
 
 extern "C" size_t kemr_workspace_bytes(int Q, int64_t M, int D, int k_sel, int64_t max_hits_per_query) {
-  (void)max_hits_per_query;
   DevInfo dv;
   int sms = 148;
   if (dev_info(&dv) == KEMR_OK && dv.sms > 0) sms = dv.sms;
@@ -270,7 +270,9 @@ extern "C" size_t kemr_workspace_bytes(int Q, int64_t M, int D, int k_sel, int64
   size_t count = align_up((size_t)Q * 8) + align_up((size_t)Q * 8) + align_up((size_t)P * Qp * 4) + 256 +
                  align_up(((size_t)1 << 20) * 8 + (size_t)Q * 256 * 8);
   (void)M; (void)D;
-  return std::max(topk, count) + 2 * align_up((size_t)Q * 4) + 4096;
+  // + per-query weights as fp32, + canonical scores of the KG hits (fused streaming search)
+  const size_t hits = align_up((size_t)std::max<int64_t>(0, std::min<int64_t>(max_hits_per_query, 4096)) * (size_t)Q * 8);
+  return std::max(topk, count) + 2 * align_up((size_t)Q * 4) + hits + 4096;
 }
 
 template <int QB, int CH>
@@ -369,6 +371,11 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
     if ((rc = stream_counters(pl.groups, &sa.done))) return rc;
     sa.stamps = g_phase_stamps;
     sa.q_f32 = q_f32; sa.q_normalize = q_normalize;
+    // canonical scores of the KG hits, computed by the CTAs as they finish their scan (scratch behind the part lists;
+    // skipped when the caller's workspace has no room for it)
+    const size_t hit_bytes = hit_rowptr ? align_up((size_t)Q * (size_t)max_hits_per_query * 8) : 0;
+    if (hit_bytes && workspace_bytes >= need + need_w + hit_bytes)
+      sa.sel.hit_score = reinterpret_cast<const double*>(reinterpret_cast<unsigned char*>(workspace) + need + need_w);
     if (sa.stamps) CUDA_TRY(cudaMemsetAsync(sa.stamps, 0x7f, 8, st));       // "first start" is an atomicMin
     dim3 grid(pl.P, pl.groups);
 #define KEMR_STREAM(QBV, CHV)                                                                                     \
@@ -399,12 +406,23 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
 
   // one CTA per query: 4 warps for the common small case, 8 when there are many candidates to re-score
   const bool small = s.max_cand <= kSelSmallCand && Q > 64;   // tiny batches leave the GPU empty: 8 warps per query
+  // Programmatic dependent launch: the selection's CTAs become resident while the scan drains (they block in
+  // griddepcontrol.wait), so its launch latency and ramp hide behind the scan's tail.  Not when an event has to be
+  // recorded between the two kernels (scan timing hook) -- anything between them in the stream makes it an ordinary launch.
+  static const bool no_pdl = getenv("KEMR_NO_PDL") != nullptr;
+  const bool pdl = !no_pdl && !g_scan_done_event;
 #define KEMR_SEL(NPV, WV)                                                                                         \
   do {                                                                                                            \
     if (smem > 48 * 1024)                                                                                         \
       CUDA_TRY(cudaFuncSetAttribute(select_kernel<NPV, WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     prefer_max_smem(select_kernel<NPV, WV>);                                                                      \
-    select_kernel<NPV, WV><<<Q, WV * 32, smem, st>>>(s);                                                          \
+    cudaLaunchConfig_t cfg = {};                                                                                  \
+    cfg.gridDim = dim3((unsigned)Q); cfg.blockDim = dim3(WV * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;  \
+    cudaLaunchAttribute at[1];                                                                                    \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                \
+    at[0].val.programmaticStreamSerializationAllowed = 1;                                                         \
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;                                                                   \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, select_kernel<NPV, WV>, s));                                                \
   } while (0)
 #define KEMR_SEL_NP(WV) switch (np) { case 1: KEMR_SEL(1, WV); break; case 2: KEMR_SEL(2, WV); break; \
                                       case 3: KEMR_SEL(3, WV); break; default: KEMR_SEL(4, WV); break; }
@@ -888,13 +906,44 @@ extern "C" int kemr_peer_merge(kemr_peer_t* p, int Q, int k, double* out_score64
 }
 
 // ----------------------------------------------------------------------------- resident index, host-buffer search
-constexpr int kSmallBatch = 4;            // host-buffer searches up to this many queries take the one-copy, one-launch route
+constexpr int kSmallBatch = 2;            // host-buffer searches up to this many queries take the one-launch route (the fused streaming
+                                          // kernel wins up to two queries; from three on the tcgen05 scan does: profiles/r02_sweep_batch.jsonl)
+constexpr int kMaxChunks = 4;             // large batches: query chunks whose PCIe transfer overlaps the previous chunk's scan
+constexpr int kChunkUnit = 256;           // chunk boundaries sit on the tcgen05 scan's query blocks (one CTA pair = 256 queries)
+
+// Chunk sizes of a large host-buffer batch whose queries sit in PAGEABLE memory: the staging memcpy of chunk i+1 runs
+// on the calling thread while the copy engine moves chunk i and the SMs scan chunk i-1 (1000 queries: 411 -> 388 us).
+// For page-locked caller buffers chunking was measured and rejected: only the first chunk's transfer stays exposed
+// (57 -> 26 us at 1000 queries), but the scans of 256 + 744 queries take 115 us instead of 98 (fewer query blocks share
+// a gallery stripe) and a second selection adds 10 us -- 216 us against 205 us for one quantise kernel reading the
+// page-locked queries in place; three chunks: 250 us (profiles/r02_session_k_stdout.txt).  KEMR_E2E_CHUNKS="256,256"
+// forces leading chunk sizes for either kind of buffer (experiments; "0" = never).
+static int plan_chunks(int Q, bool page_locked, int* sizes) {
+  static const char* env = getenv("KEMR_E2E_CHUNKS");
+  int n = 0, left = Q;
+  if (env) {
+    const char* p = env;
+    while (*p && n < kMaxChunks - 1) {
+      const int v = atoi(p);
+      if (v <= 0 || v >= left) break;
+      sizes[n++] = v; left -= v;
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+  } else if (!page_locked && Q >= 2 * kChunkUnit) {
+    sizes[n++] = kChunkUnit; left -= kChunkUnit;
+  }
+  sizes[n++] = left;
+  return n;
+}
 
 struct kemr_index {
   uint16_t* gal[2] = {nullptr, nullptr};
   int64_t M = 0;
   int D = 0, max_q = 0, max_k = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;           // query chunks travel here while the previous chunk is scanned
+  cudaEvent_t chunk_ev[kMaxChunks] = {};
   void* ws = nullptr;
   size_t ws_bytes = 0;
   // device staging
@@ -918,6 +967,8 @@ extern "C" int kemr_index_destroy(kemr_index_t* ix) {
   cudaFreeHost(ix->h_rowptr); cudaFreeHost(ix->h_col); cudaFreeHost(ix->h_bonus);
   cudaFreeHost(ix->h_blob); cudaFree(ix->d_blob);
   if (ix->stream) cudaStreamDestroy(ix->stream);
+  if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
+  for (int i = 0; i < kMaxChunks; ++i) if (ix->chunk_ev[i]) cudaEventDestroy(ix->chunk_ev[i]);
   delete ix;
   return KEMR_OK;
 }
@@ -934,6 +985,8 @@ extern "C" int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal
 #define IX_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { kemr_index_destroy(ix); \
     return fail(KEMR_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } } while (0)
   IX_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+  IX_TRY(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < kMaxChunks; ++i) IX_TRY(cudaEventCreateWithFlags(&ix->chunk_ev[i], cudaEventDisableTiming));
   IX_TRY(cudaMalloc(&ix->gal[0], gbytes));
   IX_TRY(cudaMemcpyAsync(ix->gal[0], gal_a_host, gbytes, cudaMemcpyHostToDevice, ix->stream));
   if (gal_b_host) {
@@ -992,6 +1045,8 @@ static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const u
     }
     const size_t o_rp = align_up(qbytes), o_bo = o_rp + align_up((size_t)(Q + 1) * 8), o_co = o_bo + align_up((size_t)nnz * 8);
     const size_t total = o_co + align_up((size_t)nnz * 4);
+    // (Measured and rejected: the request as a kernel PARAMETER of 8 KB instead of this copy -- 63.1 vs 62.6 us per
+    // call, the copy's DMA latency and the larger launch cancel; profiles/r02_session_k_stdout.txt.)
     memcpy(ix->h_blob, q_host, qbytes);
     if (hit_rowptr_host) {
       memcpy(ix->h_blob + o_rp, hit_rowptr_host, (size_t)(Q + 1) * 8);
@@ -1033,16 +1088,6 @@ static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const u
   int32_t* of_view = (no_zero_copy || !out_flags_host) ? nullptr : static_cast<int32_t*>(mapped(out_flags_host));
   const bool q_pinned = q_dev_view != nullptr;
   const bool out_pinned = oi_view && os_view && (!out_flags_host || of_view);
-  if (q_bf16) {
-    // bf16 bit patterns: one copy-engine transfer of Q*D*2 bytes straight into the scan's query buffer (page-locked
-    // caller memory is read in place by the copy engine, pageable memory is staged)
-    const void* src = q_bf16;
-    if (!mapped(q_bf16)) { memcpy(ix->h_q, q_bf16, qbytes / 2); src = ix->h_q; }
-    CUDA_TRY(cudaMemcpyAsync(ix->d_q, src, qbytes / 2, cudaMemcpyHostToDevice, st));
-  } else if (!q_pinned) {
-    memcpy(ix->h_q, q_host, qbytes);
-    CUDA_TRY(cudaMemcpyAsync(ix->d_qf32, ix->h_q, qbytes, cudaMemcpyHostToDevice, st));
-  }
   int64_t max_hits = 0;
   const int64_t* d_rowptr = nullptr;
   if (hit_rowptr_host) {
@@ -1059,13 +1104,62 @@ static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const u
     }
     d_rowptr = ix->d_rowptr;
   }
-  int rc = q_bf16 ? KEMR_OK : kemr_quantize_rows(q_pinned ? q_dev_view : ix->d_qf32, ix->d_q, Q, ix->D, normalize, st);
-  if (rc) return rc;
   const int ksel = std::min(kMaxKSel, (k + 6 + 7) / 8 * 8);
-  rc = kemr_scan_topk(ix->d_q, Q, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, alpha, d_rowptr, ix->d_col,
-                      ix->d_bonus, max_hits, k, ksel, 2e-5, 0, out_pinned ? os_view : ix->d_score, nullptr,
-                      out_pinned ? oi_view : ix->d_idx, out_pinned ? (of_view ? of_view : ix->d_flags) : ix->d_flags,
-                      ix->ws, ix->ws_bytes, KEMR_PATH_AUTO, st);
+  double* os_dev = out_pinned ? os_view : ix->d_score;
+  int64_t* oi_dev = out_pinned ? oi_view : ix->d_idx;
+  int32_t* of_dev = (out_pinned && of_view) ? of_view : ix->d_flags;
+  int rc = KEMR_OK;
+  int sizes[kMaxChunks];
+  const int nchunk = plan_chunks(Q, q_bf16 ? mapped(q_bf16) != nullptr : q_pinned, sizes);
+  if (nchunk > 1) {
+    // Pipelined: the copy engine brings chunk i+1 (page-locked caller memory is read in place, pageable memory goes
+    // through the handle's page-locked buffer chunk by chunk) while the SMs quantise, scan and select chunk i; the
+    // selection stores every chunk's rows straight into the caller's page-locked result arrays.
+    const size_t esz = q_bf16 ? 2 : 4;                           // bytes per query element on the host
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(q_bf16 ? (const void*)q_bf16 : (const void*)q_host);
+    const bool src_locked = mapped(src) != nullptr;
+    unsigned char* dst = q_bf16 ? reinterpret_cast<unsigned char*>(ix->d_q) : reinterpret_cast<unsigned char*>(ix->d_qf32);
+    int starts[kMaxChunks + 1];
+    starts[0] = 0;
+    for (int c = 0; c < nchunk; ++c) starts[c + 1] = starts[c] + sizes[c];
+    auto send = [&](int c) -> cudaError_t {
+      const size_t off = (size_t)starts[c] * ix->D * esz, bytes = (size_t)sizes[c] * ix->D * esz;
+      const unsigned char* from = src + off;
+      if (!src_locked) { from = reinterpret_cast<unsigned char*>(ix->h_q) + off; memcpy(const_cast<unsigned char*>(from), src + off, bytes); }
+      cudaError_t e = cudaMemcpyAsync(dst + off, from, bytes, cudaMemcpyHostToDevice, ix->copy_stream);
+      return e != cudaSuccess ? e : cudaEventRecord(ix->chunk_ev[c], ix->copy_stream);
+    };
+    // page-locked source: all transfers are queued at once (the copy engine runs them back to back); pageable source:
+    // the staging memcpy of chunk i+1 runs on this thread while chunk i is in flight
+    if (src_locked) for (int c = 0; c < nchunk; ++c) CUDA_TRY(send(c));
+    for (int c = 0; c < nchunk; ++c) {
+      const int q0 = starts[c], nq = sizes[c];
+      if (!src_locked) CUDA_TRY(send(c));
+      CUDA_TRY(cudaStreamWaitEvent(st, ix->chunk_ev[c], 0));
+      uint16_t* qc = ix->d_q + (size_t)q0 * ix->D;
+      if (!q_bf16 && (rc = kemr_quantize_rows(ix->d_qf32 + (size_t)q0 * ix->D, qc, nq, ix->D, normalize, st))) return rc;
+      rc = kemr_scan_topk(qc, nq, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, alpha, d_rowptr ? d_rowptr + q0 : nullptr,
+                          ix->d_col, ix->d_bonus, max_hits, k, ksel, 2e-5, 0, os_dev + (size_t)q0 * k, nullptr,
+                          oi_dev + (size_t)q0 * k, of_dev + q0, ix->ws, ix->ws_bytes, KEMR_PATH_AUTO, st);
+      if (rc) return rc;
+    }
+  } else {
+    if (q_bf16) {
+      // bf16 bit patterns: one copy-engine transfer of Q*D*2 bytes straight into the scan's query buffer (page-locked
+      // caller memory is read in place by the copy engine, pageable memory is staged)
+      const void* src = q_bf16;
+      if (!mapped(q_bf16)) { memcpy(ix->h_q, q_bf16, qbytes / 2); src = ix->h_q; }
+      CUDA_TRY(cudaMemcpyAsync(ix->d_q, src, qbytes / 2, cudaMemcpyHostToDevice, st));
+    } else if (!q_pinned) {
+      memcpy(ix->h_q, q_host, qbytes);
+      CUDA_TRY(cudaMemcpyAsync(ix->d_qf32, ix->h_q, qbytes, cudaMemcpyHostToDevice, st));
+    }
+    rc = q_bf16 ? KEMR_OK : kemr_quantize_rows(q_pinned ? q_dev_view : ix->d_qf32, ix->d_q, Q, ix->D, normalize, st);
+    if (rc) return rc;
+    rc = kemr_scan_topk(ix->d_q, Q, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, alpha, d_rowptr, ix->d_col,
+                        ix->d_bonus, max_hits, k, ksel, 2e-5, 0, os_dev, nullptr, oi_dev, of_dev,
+                        ix->ws, ix->ws_bytes, KEMR_PATH_AUTO, st);
+  }
   if (rc) return rc;
   if (out_pinned) {
     CUDA_TRY(cudaStreamSynchronize(st));

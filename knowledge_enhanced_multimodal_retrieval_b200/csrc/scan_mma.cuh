@@ -586,6 +586,9 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (PAIR) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // programmatic dependent launch: the selection kernel queued behind this scan may take its SM slots as they free up
+  // (its CTAs block in griddepcontrol.wait until this whole grid has finished and its lists are visible)
+  if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ================================================================= TMA producer
@@ -942,7 +945,30 @@ inline PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// Encoding a tensor map is a driver call of ~1.5 us and a scan needs five; the map is a pure function of (address, rows,
+// D, box), so the last few are kept per thread (a serving loop scans the same galleries from the same query buffer).
+struct TmapCacheEntry { const void* base; int64_t rows; int D, box; int dev; CUtensorMap map; };
+constexpr int kTmapCache = 16;
+
+inline int make_tmap_2d_uncached(CUtensorMap* map, const void* base, int64_t rows, int D, int box_rows);
 inline int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int D, int box_rows) {
+  static thread_local TmapCacheEntry cache[kTmapCache];
+  static thread_local int used = 0, next = 0;
+  int dev = -1;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < used; ++i) {
+    const TmapCacheEntry& e = cache[i];
+    if (e.base == base && e.rows == rows && e.D == D && e.box == box_rows && e.dev == dev) { *map = e.map; return 0; }
+  }
+  if (make_tmap_2d_uncached(map, base, rows, D, box_rows)) return 1;
+  TmapCacheEntry& e = cache[next];
+  e.base = base; e.rows = rows; e.D = D; e.box = box_rows; e.dev = dev; e.map = *map;
+  next = (next + 1) % kTmapCache;
+  if (used < kTmapCache) ++used;
+  return 0;
+}
+
+inline int make_tmap_2d_uncached(CUtensorMap* map, const void* base, int64_t rows, int D, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) { snprintf(g_mma_error, sizeof g_mma_error, "cuTensorMapEncodeTiled unavailable"); return 1; }
   cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};

@@ -43,8 +43,9 @@ struct StreamArgs {
 };
 
 inline size_t stream_cand_off(size_t select_bytes) { return (select_bytes + 15) / 16 * 16; }
+// layout behind the selection scratch: cand[QB][kStreamCand] u64 | best[QB][kMaxKSel] u64 | bf16 queries [QB][kMaxD]
 inline size_t stream_smem_bytes(int QB, size_t select_bytes) {
-  return stream_cand_off(select_bytes) + (size_t)QB * kStreamCand * 8 + (size_t)QB * kMaxKSel * 8 + 64;
+  return stream_cand_off(select_bytes) + (size_t)QB * kStreamCand * 8 + (size_t)QB * kMaxKSel * 8 + (size_t)QB * kMaxD * 2 + 64;
 }
 
 namespace ptx {
@@ -102,10 +103,11 @@ __device__ __forceinline__ int stream_value_of(int lane) {
 }
 
 template <int QB, int CH, int NP>
-__global__ void __launch_bounds__(kStreamThreads, 1) scan_stream_kernel(StreamArgs a) {
+__global__ void __launch_bounds__(kStreamThreads, 1) scan_stream_kernel(const __grid_constant__ StreamArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* cand = reinterpret_cast<uint64_t*>(smem + a.cand_off);     // [QB][kStreamCand]
   uint64_t* best = cand + (size_t)QB * kStreamCand;                     // [QB][kMaxKSel]
+  uint16_t* qs = reinterpret_cast<uint16_t*>(best + (size_t)QB * kMaxKSel);   // [QB][D] bf16 queries (fp32-query mode)
   __shared__ unsigned int s_cnt[QB];
   __shared__ unsigned long long s_thr[QB];
   __shared__ int s_last;
@@ -126,13 +128,16 @@ __global__ void __launch_bounds__(kStreamThreads, 1) scan_stream_kernel(StreamAr
   if (threadIdx.x < QB) { s_cnt[threadIdx.x] = 0; s_thr[threadIdx.x] = 0; }
 
   // queries -> fp32 registers (lane l keeps the d-slices it will meet in every row)
-  if (a.q_f32) {
+  const float* q_f32 = a.q_f32;
+  const int64_t* hit_rowptr = a.sel.hit_rowptr;
+  const int32_t* hit_col = a.sel.hit_col;
+  const double* hit_bonus = a.sel.hit_bonus;
+  if (q_f32) {
     // fp32 queries: warp w rounds query w of the group (quantize_rows_kernel's arithmetic: per-lane sum of squares over
     // d = lane, lane + 32, ..., shuffle tree, v * (1 / sqrt(ss)), round to nearest even) into shared memory; the bf16
     // rows also go to global memory once per group for the selection stage
-    uint16_t* qs = reinterpret_cast<uint16_t*>(cand);             // the candidate buffer is free until the scan starts
     if (warp < nq) {
-      const float* src = a.q_f32 + (size_t)(q0 + warp) * D;
+      const float* src = q_f32 + (size_t)(q0 + warp) * D;
       float scale = 1.f;
       if (a.q_normalize) {
         float ss = 0.f;
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) scan_stream_kernel(StreamAr
     }
     __syncthreads();
   }
-  const uint16_t* qsrc = a.q_f32 ? reinterpret_cast<const uint16_t*>(cand) : a.s.q + (size_t)q0 * D;
+  const uint16_t* qsrc = q_f32 ? qs : a.s.q + (size_t)q0 * D;
   float qr[QB][CH][8];
 #pragma unroll
   for (int qq = 0; qq < QB; ++qq) {
@@ -271,6 +276,32 @@ __global__ void __launch_bounds__(kStreamThreads, 1) scan_stream_kernel(StreamAr
       if (r < K) dst[r] = xk;
     }
     for (int i = n + threadIdx.x; i < K; i += kStreamThreads) dst[i] = 0;     // fewer than K rows seen: empty tail
+  }
+
+  // KG hits are known before the scan: their canonical final scores are computed here, one hit per warp, spread over
+  // the CTAs (hit j of the group -> CTA j mod P), so the selection of the last CTA finds them ready instead of
+  // re-scoring ~20 extra rows on its own (batch 1, 43 k rows: 6 us of a 16 us selection)
+  if (a.sel.hit_score && hit_rowptr) {
+    const long long hb = hit_rowptr[q0], he = hit_rowptr[q0 + nq];
+    for (long long j = hb + blockIdx.x + (long long)warp * P; j < he; j += (long long)P * kStreamWarps) {
+      int qq = 0;
+      while (qq + 1 < nq && hit_rowptr[q0 + qq + 1] <= j) ++qq;
+      const int32_t col = hit_col[j];
+      double f = __longlong_as_double(0x7ff8000000000000ll);
+      if (col >= 0 && (int64_t)col < a.s.M) {                  // warp-uniform
+        CanonQueryT<NP> cq;
+        cq.load(qsrc + (size_t)qq * D, D, lane);
+        CanonRow<NP> ra, rb;
+        const size_t off = (size_t)col * D;
+        ra.load(a.s.gal[0] + off, D, lane);
+        rb.load(a.s.gal[a.s.G > 1 ? 1 : 0] + off, D, lane);
+        double sa, sb;
+        cq.dot2_lane0(ra, rb, D, lane, sa, sb);
+        const double wa = a.sel.wq[0] ? a.sel.wq[0][q0 + qq] : a.sel.w[0], wb = a.sel.wq[0] ? a.sel.wq[1][q0 + qq] : a.sel.w[1];
+        f = canon_fuse(sa, sb, a.s.G > 1, wa, wb, a.sel.alpha, hit_bonus[j], true);
+      }
+      if (lane == 0) const_cast<double*>(a.sel.hit_score)[j] = f;
+    }
   }
 
   // ------------------------------------------------------------------- last CTA of the group runs the selection

@@ -25,6 +25,8 @@ struct SelectArgs {
   const int64_t* hit_rowptr;   // [Q+1] or null
   const int32_t* hit_col;
   const double* hit_bonus;
+  const double* hit_score;     // optional [nnz]: canonical FINAL score (bonus included) of every CSR entry, computed ahead of
+                               // the selection (fused streaming search: by the CTAs that finish their scan early)
   int k;
   double eps;
   int64_t idx_base;
@@ -259,10 +261,12 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
       }
       s_bonus[found] = a.hit_bonus[h];
       s_has[found] = 1;
+      if (a.hit_score) { s_score[found] = __ldcg(a.hit_score + h); s_has[found] = 2; }     // already re-scored
     }
     __syncthreads();
   }
   const int n = min(nsel + s_extra, MC);
+  const int nc = a.hit_score ? nsel : n;                    // candidates phase C still has to re-score
   KEMR_SEL_STAMP(4);
 
   // C (two register sets, roles alternate).  An item is two rows re-scored together with interleaved reduction
@@ -276,28 +280,29 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
       const size_t off = (size_t)s_row[c] * a.D;
       ra[set].load(a.gal[0] + off, a.D, lane);
       if (two) rb[set].load(a.gal[1] + off, a.D, lane);
-      else rb[set].load(a.gal[0] + (size_t)s_row[min(c + W, n - 1)] * a.D, a.D, lane);
+      else rb[set].load(a.gal[0] + (size_t)s_row[min(c + W, nc - 1)] * a.D, a.D, lane);
     };
     auto score = [&](int set, int c) {
       double sa, sb;
       cq.dot2_lane0(ra[set], rb[set], a.D, lane, sa, sb);
       if (lane == 0) {
         if (two) {
-          s_score[c] = canon_fuse(sa, sb, true, wa, wb, a.alpha, s_bonus[c], s_has[c] != 0);
+          if (s_has[c] != 2) s_score[c] = canon_fuse(sa, sb, true, wa, wb, a.alpha, s_bonus[c], s_has[c] != 0);
         } else {
-          s_score[c] = canon_fuse(sa, 0.0, false, wa, wb, a.alpha, s_bonus[c], s_has[c] != 0);
-          if (c + W < n) s_score[c + W] = canon_fuse(sb, 0.0, false, wa, wb, a.alpha, s_bonus[c + W], s_has[c + W] != 0);
+          if (s_has[c] != 2) s_score[c] = canon_fuse(sa, 0.0, false, wa, wb, a.alpha, s_bonus[c], s_has[c] != 0);
+          if (c + W < nc && s_has[c + W] != 2)
+            s_score[c + W] = canon_fuse(sb, 0.0, false, wa, wb, a.alpha, s_bonus[c + W], s_has[c + W] != 0);
         }
       }
     };
     int c = warp;
-    if (c < n) fetch(0, c);
-    while (c < n) {
-      if (c + step < n) fetch(1, c + step);
+    if (c < nc) fetch(0, c);
+    while (c < nc) {
+      if (c + step < nc) fetch(1, c + step);
       score(0, c);
       c += step;
-      if (c >= n) break;
-      if (c + step < n) fetch(0, c + step);
+      if (c >= nc) break;
+      if (c + step < nc) fetch(0, c + step);
       score(1, c);
       c += step;
     }
@@ -360,6 +365,9 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
 template <int NP, int W>
 __global__ void __launch_bounds__(W * 32) select_kernel(SelectArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // launched behind the scan with programmatic stream serialisation: wait here until the scan grid has completed and
+  // its candidate lists are visible (returns at once for an ordinary launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   select_query<NP, W>(a, blockIdx.x, smem_raw);
 }
 

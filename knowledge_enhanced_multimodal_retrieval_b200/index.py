@@ -114,21 +114,33 @@ class HostIndex:
         bf16 = isinstance(queries_f32, np.ndarray) and queries_f32.dtype == np.uint16
         if bf16 and normalize:
             raise KemrError("bf16 queries cannot be re-normalised")
-        q = np.ascontiguousarray(queries_f32) if bf16 else np.ascontiguousarray(queries_f32, dtype=np.float32)
+        q = _as(queries_f32, np.uint16 if bf16 else np.float32)
         Q = q.shape[0]
         if out is None:
             out = (np.empty((Q, k), np.int64), np.empty((Q, k), np.float64), np.empty((Q,), np.int32))
         idx, score, flags = out
         rp = cc = bb = None
         if hits_csr is not None:
-            rp, cc, bb = (np.ascontiguousarray(hits_csr[0], np.int64), np.ascontiguousarray(hits_csr[1], np.int32),
-                          np.ascontiguousarray(hits_csr[2], np.float64))
-        vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+            rp, cc, bb = _as(hits_csr[0], np.int64), _as(hits_csr[1], np.int32), _as(hits_csr[2], np.float64)
         if bf16:
-            _lib.check(self._lib.kemr_index_search_host_bf16(self._h, vp(q), Q, float(t2i_weight), float(t2t_weight),
-                                                             float(alpha), vp(rp), vp(cc), vp(bb), k, vp(idx), vp(score), vp(flags)))
+            _lib.check(self._lib.kemr_index_search_host_bf16(self._h, _addr(q), Q, float(t2i_weight), float(t2t_weight),
+                                                             float(alpha), _addr(rp), _addr(cc), _addr(bb), k,
+                                                             _addr(idx), _addr(score), _addr(flags)))
         else:
-            _lib.check(self._lib.kemr_index_search_host(self._h, vp(q), Q, int(normalize), float(t2i_weight),
-                                                        float(t2t_weight), float(alpha), vp(rp), vp(cc), vp(bb), k,
-                                                        vp(idx), vp(score), vp(flags)))
+            _lib.check(self._lib.kemr_index_search_host(self._h, _addr(q), Q, int(normalize), float(t2i_weight),
+                                                        float(t2t_weight), float(alpha), _addr(rp), _addr(cc), _addr(bb), k,
+                                                        _addr(idx), _addr(score), _addr(flags)))
         return idx, score, flags
+
+
+def _as(x, dtype):
+    """x as a C-contiguous array of `dtype` (no copy when it already is: the serving path calls this per request)."""
+    if type(x) is np.ndarray and x.dtype == dtype and x.flags.c_contiguous:
+        return x
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+def _addr(x):
+    """Address of a numpy array's buffer for a `void*` argument (`arr.ctypes.data_as` builds two Python objects per
+    call -- 17 us of an 83 us batch-1 request went to seven of them)."""
+    return None if x is None else x.__array_interface__["data"][0]

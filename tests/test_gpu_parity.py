@@ -346,6 +346,39 @@ def test_host_index_equals_device_index(small_set):
     hi.close()
 
 
+@pytest.mark.parametrize("locked", [True, False])
+def test_host_search_pipelined_chunks_and_small_batches_equal_the_device_search(locked):
+    """kemr_index_search_host: pageable batches of 512 queries and more travel as chunks (staging memcpy, PCIe transfer and
+    scan of consecutive chunks overlap); one or two queries take the one-copy, one-launch route with their KG hits
+    pre-scored by the scanning CTAs.  Every route must return what the device-resident search returns, bit for bit
+    (page-locked caller buffers are used in place, pageable ones staged)."""
+    s = synth.make_retrieval_set(Q=1100, M=9000, D=256, seed=21, fused=True, lam=0.2, diagonal=False, with_kg=True)
+    gi = index.GalleryIndex(s.image, s.target, uuids=s.uuids)
+    hi = index.HostIndex(s.image, s.target, max_queries=1100, max_k=10)
+    alpha, hits = fusion.kg_hits_for_strategy(s.kg_results, s.query_uuids, s.uuids, "weighted", {"alpha": 0.8, "sparql_weight": 0.2})
+    rp, cc, bb = hits.rowptr.cpu().numpy(), hits.col.cpu().numpy(), hits.bonus.cpu().numpy()
+    mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()) if locked else (lambda a: np.ascontiguousarray(a))
+    for Q in (1, 2, 3, 300, 512, 777, 1100):
+        qh = mk(s.query[:Q])
+        out = (mk(np.zeros((Q, 10), np.int64)), mk(np.zeros((Q, 10), np.float64)), mk(np.zeros((Q,), np.int32)))
+        # plain fused scan
+        want_i, want_s = gi.search(s.query[:Q], k=10, t2i_weight=0.4, t2t_weight=0.6)
+        got_i, got_s, fl = hi.search(qh, k=10, t2i_weight=0.4, t2t_weight=0.6, out=out)
+        assert np.array_equal(want_i.cpu().numpy(), got_i) and np.array_equal(want_s.cpu().numpy(), got_s) and not fl.any(), Q
+        # with the KG boost (CSR rows of the first Q queries)
+        sub = engine.KGHits(hits.rowptr[:Q + 1].clone(), hits.col[:int(rp[Q])].clone(), hits.bonus[:int(rp[Q])].clone(),
+                            hits.max_per_query) if hasattr(engine, "KGHits") else None
+        want_i, want_s = gi.search(s.query[:Q], k=10, t2i_weight=0.5, t2t_weight=0.5, alpha=alpha, hits=sub)
+        csr = (rp[:Q + 1].copy(), cc[:int(rp[Q])].copy(), bb[:int(rp[Q])].copy())
+        got_i, got_s, fl = hi.search(qh, k=10, t2i_weight=0.5, t2t_weight=0.5, alpha=alpha, hits_csr=csr, out=out)
+        assert np.array_equal(want_i.cpu().numpy(), got_i) and np.array_equal(want_s.cpu().numpy(), got_s) and not fl.any(), Q
+        if Q >= 512:                                          # bf16 bit patterns take the same chunked route
+            qb = mk(synth.f32_to_bf16_bits(s.query[:Q]))
+            got_i, got_s, fl = hi.search(qb, k=10, t2i_weight=0.5, t2t_weight=0.5, alpha=alpha, hits_csr=csr, out=out)
+            assert np.array_equal(want_i.cpu().numpy(), got_i) and np.array_equal(want_s.cpu().numpy(), got_s), Q
+    hi.close()
+
+
 def test_retrieval_engine_end_to_end(small_set):
     q, img, tgt = small_set["query"], small_set["image"], small_set["target"]
     gi = index.GalleryIndex(img, tgt, uuids=small_set["uuids"])

@@ -27,7 +27,10 @@ def per_call(fn, n):
 
 def main():
     lib = _lib.load()
-    for name, Q, kg in (("c3", 1, True), ("b4", 4, True), ("c2", 1000, False), ("q512", 512, False), ("q256", 256, False)):
+    cases = (("c3", 1, True), ("b2", 2, True), ("b4", 4, True), ("c2", 1000, False), ("q512", 512, False), ("q256", 256, False))
+    if len(sys.argv) > 1:
+        cases = [c for c in cases if c[0] in sys.argv[1:]]
+    for name, Q, kg in cases:
         s = synth.make_retrieval_set(Q=Q, M=43000, D=768, seed=1, fused=True, lam=0.1, diagonal=False, with_kg=kg)
         hits_csr = None
         alpha = 1.0
