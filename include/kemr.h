@@ -254,7 +254,13 @@ int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal_b_host, in
                       int max_queries, int max_k, kemr_index_t** out);
 int kemr_index_destroy(kemr_index_t* index);
 /* queries: fp32 [Q, D] host (quantised to bf16 on the device; set normalize=1 to L2-normalise).
- * Copies in, scans, copies the k results out and synchronises.  hits_* host CSR or NULL. */
+ * Copies in, scans, copies the k results out and synchronises.  hits_* host CSR or NULL.
+ * Routes (same results on every one): one or two queries -> ONE host-to-device copy of the request (queries + CSR) and
+ * ONE kernel (quantise, scan, KG hits, selection), results stored straight into page-locked host memory; larger
+ * batches with page-locked caller buffers -> the quantise kernel reads the queries in place over PCIe and the
+ * selection kernel writes the caller's arrays in place; pageable caller buffers -> staged through the handle's
+ * page-locked buffers, batches of 512 queries and more in chunks (memcpy, transfer and scan of consecutive chunks
+ * overlap). */
 int kemr_index_search_host(kemr_index_t* index, const float* q_host, int Q, int normalize,
                            double w_a, double w_b, double alpha,
                            const int64_t* hit_rowptr_host, const int32_t* hit_col_host,
