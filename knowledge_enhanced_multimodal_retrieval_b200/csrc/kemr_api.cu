@@ -272,7 +272,7 @@ extern "C" size_t kemr_workspace_bytes(int Q, int64_t M, int D, int k_sel, int64
   (void)M; (void)D;
   // + per-query weights as fp32, + canonical scores of the KG hits (fused streaming search)
   const size_t hits = align_up((size_t)std::max<int64_t>(0, std::min<int64_t>(max_hits_per_query, 4096)) * (size_t)Q * 8);
-  return std::max(topk, count) + 2 * align_up((size_t)Q * 4) + hits + 4096;
+  return std::max(topk, count) + 2 * align_up((size_t)Q * 4) + hits + align_up((size_t)Qp * 4) + 4096;
 }
 
 template <int QB, int CH>
@@ -401,6 +401,19 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
 
   if (q_f32) return fail(KEMR_ERR_ARG, "internal: fp32 queries need the fused streaming kernel");
   if (!pl.mma.all_slots) CUDA_TRY(cudaMemsetAsync(part_keys, 0, need, st));   // unwritten slots must read as empty
+  // per-query threshold shared by the lists of a query (scan_mma.cuh): zero = nothing published; behind the part lists
+  // and the fp32 weights, when the caller's workspace has the room
+  // Measured (profiles/r02_session_l2_stdout.txt): +4.4 % on 4096 queries x 1.25 M rows, top-100 (short lists that
+  // restart at virtual part boundaries start warm: 5.78 -> 5.53 ms); no gain where every list of a query lives for the
+  // whole scan (C1: 198.4 us without, 200.4 us with; C2 the same to 0.2 us) -- all lists warm up at the same pace, so
+  // the neighbours' thresholds are no better than a list's own and the loads are overhead.  So: plans with virtual parts.
+  static const char* share_env = getenv("KEMR_THR_SHARE");          // experiments: 0 = never, 1 = always
+  const bool share = share_env ? share_env[0] == '1' : pl.mma.vq > 1;
+  const size_t thr_bytes = align_up((size_t)Qrows * 4);
+  if (share && workspace_bytes >= need + need_w + thr_bytes) {
+    a.thr_pub = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(workspace) + need + need_w);
+    CUDA_TRY(cudaMemsetAsync(a.thr_pub, 0, (size_t)Qrows * 4, st));
+  }
   if ((rc = mma_launch(a, pl.mma, st))) return fail(KEMR_ERR_CUDA, "tcgen05 scan launch failed: %s", mma_last_error());
   if (g_scan_done_event) CUDA_TRY(cudaEventRecord(g_scan_done_event, st));
 

@@ -31,6 +31,13 @@
 // buffer is half full the whole warp folds its buffers into per-thread sorted top-K lists that live
 // in REGISTERS (K <= 32, branch-free compare/select insert), so list maintenance runs in lock-step
 // instead of diverging per lane, and the score matrix never exists outside TMEM.
+// Shared threshold: a list that starts from -inf takes ~K ln(n / K) inserts for n scores, and a query has dozens of
+// lists (two per unit touching its block).  Every FULL list publishes its K-th score per query in global memory
+// (red.max on the order-preserving image); every list prunes with the maximum it has seen there (re-read once per
+// tile, the load in flight while the warp waits for the accumulator).  A row dropped that way has K better rows in ONE
+// list whose final last key is at least the threshold used -- exactly the event "a list rejected rows below its last
+// key" that the selection's certificate already accounts for (select.cuh: every full list's last key enters the
+// rejection bound), so which rows a list keeps now depends on timing, the certified top-k does not.
 // Roofline: tensor pipe for batch >= ~250 (2*B*G*M*D flop), HBM below (G*M*D*2 bytes).
 //
 // CTA pairs (PAIR = true, batches above 128 queries): two CTAs of one cluster run ONE
@@ -277,7 +284,9 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
   const int seg_cap = (int)std::min<int64_t>(std::max<int64_t>(span, (int64_t)p->n_t), kPlanMaxParts / 2 - span + 1);
   int Ksel = 0, vq = 1;
   long long best_keys = 1ll << 60;
+  static const char* force_k = getenv("KEMR_MMA_KLIST");            // experiments: list length 8 / 16 / 32
   for (int Kc = 8; Kc <= 32; Kc *= 2) {
+    if (force_k && atoi(force_k) != Kc) continue;
     if (Kc == 32 && Ksel) break;
     for (int seg = span; seg <= std::max(span, seg_cap); ++seg) {
       const int segs = seg == span ? span : seg + span - 1;            // list slots when virtual parts are added
@@ -507,6 +516,32 @@ __device__ __forceinline__ void ld_shared_v2(uint32_t addr, float& s, uint32_t& 
   s = __uint_as_float(u);
 }
 
+// Smallest of the K group maxima of one lane's HALF tile of fused scores (HC columns from `acc`, cut into K groups of
+// HC / K columns): at least K of these scores reach it.
+template <int K, bool TWO, int HC>
+__device__ __forceinline__ float warm_floor(uint32_t acc, float w0, float w1) {
+  constexpr int g = (HC % K == 0 && HC / K >= 1 && HC / K <= 16) ? HC / K : 1;     // columns per group
+  float v = INFINITY;
+  for (int c0 = 0; c0 < HC; c0 += 16) {
+    uint32_t xa[16], xb[16];
+    tmem_ld16(acc + (uint32_t)c0, xa);
+    if (TWO) tmem_ld16(acc + 128u + (uint32_t)c0, xb);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j0 = 0; j0 < 16; j0 += g) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < g; ++j) {
+        float s = w0 * __uint_as_float(xa[j0 + j]);
+        if (TWO) s = fmaf(w1, __uint_as_float(xb[j0 + j]), s);
+        m = fmaxf(m, s);
+      }
+      v = fminf(v, m);
+    }
+  }
+  return v;
+}
+
 // K = register list length; PAIR = CTA pairs (cta_group::2, 256 queries per block); TWO = two
 // accumulators (T2I, T2T) of 128 columns each, fused in the epilogue with their own weights
 // (otherwise ONE accumulator of 256 gallery rows: single gallery, or both galleries with equal
@@ -728,11 +763,16 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     RegList<K> list;
     list.reset();
     float thr = INFINITY;
+    float tshare = -INFINITY;                            // largest K-th score published by any full list of this query
+    // (the kernels that sit at the register limit -- K = 32, K = 16 with two accumulators -- keep the plain epilogue)
+    constexpr bool kLean = K > 16 || (TWO && K >= 16);
+    unsigned int* const thr_pub = (mode == kModeTopk && !kLean) ? a.s.thr_pub : nullptr;
     float thr_raw = INFINITY;                            // thr / w0 rounded down: raw accumulator <= thr_raw  =>  w0*acc <= thr
     int bcnt = 0;                                        // entries in this thread's append buffer
     int32_t cnt = 0;
     float blo = 0.f, bhi = 0.f;
     int cur_qb = -1, cur_part = -1, c_first = 0, slot = 0;
+    bool cold = false;                                   // the part has just begun: its list is empty
     bool qvalid = false;
     bool warp_active = false;                            // some lane of this warp holds a real query of the current block
     int qg = 0;
@@ -745,18 +785,32 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     auto fold = [&]() {
       const long long tf0 = dbg ? clock64() : 0;
       const int nmax = __reduce_max_sync(0xffffffffu, bcnt);
-      for (int i = 0; i < nmax; ++i) {
-        if (i < bcnt) {
-          float s; uint32_t r;
-          ld_shared_v2(my_buf + (uint32_t)i * (kEpiThreads * 8u), s, r);
-          if (s > thr) {
+      // the next entry's shared-memory load is in flight while the current one is inserted (ONE insert body: four
+      // entries per round, unrolled, cost C1 20 % -- the epilogue loop has to stay inside the instruction cache)
+      if (kLean) {
+        for (int i = 0; i < nmax; ++i) {
+          if (i < bcnt) {
+            float s; uint32_t r;
+            ld_shared_v2(my_buf + (uint32_t)i * (kEpiThreads * 8u), s, r);
+            if (s > thr) { list.insert(s, r); thr = list.threshold(); }
+          }
+        }
+      } else {
+        float s_n = -INFINITY; uint32_t r_n = 0;
+        if (nmax > 0) ld_shared_v2(my_buf, s_n, r_n);
+        for (int i = 0; i < nmax; ++i) {
+          const float s = s_n; const uint32_t r = r_n;
+          if (i + 1 < nmax) ld_shared_v2(my_buf + (uint32_t)(i + 1) * (kEpiThreads * 8u), s_n, r_n);
+          if (i < bcnt && s > thr) {
             list.insert(s, r);
-            thr = list.threshold();
+            thr = fmaxf(list.threshold(), tshare);
           }
         }
       }
       thr_raw = __fdiv_rd(thr, w0);
       bcnt = 0;
+      // a full list offers its K-th score to the other lists of the query (fire and forget)
+      if (thr_pub && qvalid && list.threshold() > -INFINITY) atomicMax(thr_pub + qg, order_f32(list.threshold()));
       if (dbg) t_fold += clock64() - tf0;
     };
     // predicated, unrolled: every survivor of an 8-column run goes to the append buffer
@@ -810,6 +864,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         qvalid = qg < a.s.Q;
         warp_active = __any_sync(0xffffffffu, qvalid);   // small batches: the warps of empty lane quadrants only hand the buffer back
         list.reset();
+        cold = true;
+        tshare = -INFINITY;
         thr = qvalid ? -INFINITY : INFINITY;             // padded query rows never collect candidates
         thr_raw = thr;
         if (a.s.wq[0] && qvalid) { w0 = a.s.wq[0][qg]; w1 = a.s.wq[1][qg]; }   // per-query gate (two accumulators)
@@ -818,8 +874,18 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       const int buf = (int)(it & 1);
       const uint32_t bphase = (uint32_t)((it >> 1) & 1);
+      // the query's shared threshold, fetched while the warp waits for the accumulator
+      unsigned int tp = 0;
+      if (thr_pub && qvalid) tp = __ldcg(thr_pub + qg);
       mbar_wait_dbg(&tfull_bar[buf], bphase, dbg, w_tfull);
       ptx::tc_fence_after();
+      if (tp) {
+        const float t = unorder_f32(tp);
+        if (t > tshare) {
+          tshare = t;
+          if (t > thr) { thr = t; thr_raw = __fdiv_rd(thr, w0); }
+        }
+      }
       const bool full_tile = ncols == n_tile;            // warp-uniform
       const uint32_t acc0 = lane_addr + (uint32_t)buf * 256u;
       const int cbeg = half * kHalfCols;
@@ -889,6 +955,24 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       };
 
+      // Warm start.  A list that begins at -inf lets the whole first tile through: ~3/4 of all the inserts a short
+      // scan ever makes happen in its first tile and the MMA warp waits for the accumulator (C2: 16 k of 139 k cycles).
+      // Before the first FULL tile of a part is filtered, its columns are cut into K groups and the smallest of the K
+      // group maxima is taken: at least K of this tile's scores reach it, so everything BELOW it is outside the list's
+      // top K whatever follows -- a valid first threshold for the price of one extra pass over the accumulator (no list,
+      // no branches), and the rows it drops lie below the list's final last key like any other the list rejects.
+      // (single-accumulator kernels with K = 8 / 16: in the others the extra live values spill the steady-state loop)
+      if (mode == kModeTopk && !TWO && K <= 16 && cold && full_tile && warp_active && kHalfCols % K == 0 && kHalfCols / K <= 16) {
+        const float v = warm_floor<K, TWO, kHalfCols>(acc0 + (uint32_t)cbeg, w0, w1);
+        if (qvalid && v > -INFINITY && v < INFINITY) {
+          // the next float below v (v is finite): rows EQUAL to v must still pass
+          const uint32_t vb = __float_as_uint(v);
+          const float below = v > 0.f ? __uint_as_float(vb - 1u) : (v < 0.f ? __uint_as_float(vb + 1u) : __uint_as_float(0x80000001u));
+          tshare = fmaxf(tshare, below);
+          if (tshare > thr) { thr = tshare; thr_raw = __fdiv_rd(thr, w0); }
+        }
+      }
+      cold = false;
       // double-buffered TMEM reads: chunk i+1 is in flight while chunk i is processed
       uint32_t ra0[16], rb0[16], ra1[16], rb1[16];
       if (warp_active && nch > 0) load(cbeg, ra0, rb0);

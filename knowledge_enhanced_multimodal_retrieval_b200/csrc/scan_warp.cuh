@@ -30,6 +30,8 @@ struct ScanArgs {
   // TOPK
   int K;
   uint64_t* part_keys;      // [P][Q][K], descending, 0 = empty
+  unsigned int* thr_pub;    // optional [Q rows], zero on entry: per query the largest K-th score any FULL list has published
+                            // (order_f32 image, 0 = none) -- a pruning threshold shared by all lists of the query (scan_mma.cuh)
   // COUNT
   const float* band_lo;     // [Q]
   const float* band_hi;     // [Q]

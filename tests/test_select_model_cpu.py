@@ -131,3 +131,40 @@ def test_prescreen_margin_keeps_near_ties_of_the_kth_candidate():
     # the dropped candidate comes back through the hit list when the knowledge graph boosts it past the leader
     out, flag = select_model(lists, Kp=8, K=3, k=1, eps=eps, alpha=1.0, canon=canon, hits={2: 0.7})
     assert (out, flag) == ([2], 0)
+
+
+@st.composite
+def shared_threshold_scenario(draw):
+    sc = draw(scenario())
+    M = sc[0]
+    order = draw(st.permutations(list(range(M))))
+    stale = draw(st.lists(st.integers(0, 3), min_size=M, max_size=M))      # how many publications a reader lags behind
+    return sc, order, stale
+
+
+@settings(max_examples=600, deadline=None)
+@given(shared_threshold_scenario())
+def test_shared_threshold_between_lists_keeps_the_certificate_sound(arg):
+    """The tcgen05 epilogue prunes every list of a query with the largest K-th score any FULL list has published so
+    far (scan_mma.cuh: thr_pub), read with arbitrary staleness, rows of different lists arriving in any interleaving.
+    A row dropped that way has Kp better rows in one list whose final last key is at least the threshold used, and the
+    select stage puts every full list's last key into its rejection bound -- so a clear certificate must still imply
+    the exact top-k, although the lists are no longer the exact top-Kp of their rows."""
+    (M, P, Kp, K, k, eps, canon, score32, part, alpha, hits), order, stale = arg
+    lists = [[] for _ in range(P)]
+    published = [float("-inf")]                                   # history of the shared threshold (monotone)
+    for n, r in enumerate(order):
+        seen = published[max(0, len(published) - 1 - stale[n])]   # a possibly stale view
+        p = int(part[r])
+        own = lists[p][-1][0] if len(lists[p]) == Kp else float("-inf")
+        if not float(score32[r]) > max(seen, own):                # strict compare on the fp32 score, as the kernel does
+            continue
+        lists[p] = sorted(lists[p] + [key(score32[r], r)], reverse=True)[:Kp]
+        if len(lists[p]) == Kp:
+            published.append(max(published[-1], lists[p][-1][0]))
+    out, flag = select_model(lists, Kp, K, k, eps, alpha, canon, hits)
+    truth = sorted((-(alpha * canon[r] + hits.get(r, 0.0)), r) for r in range(M))[:k]
+    if flag == 0:
+        assert out == [r for _, r in truth][:len(out)], (out, truth)
+        if M >= k:
+            assert len(out) == k
