@@ -292,9 +292,11 @@ inline int mma_make_plan(int Q, int64_t M, int D, int G, int K, int mode, int sm
       const int segs = seg == span ? span : seg + span - 1;            // list slots when virtual parts are added
       if (2 * segs > kPlanMaxParts) break;
       if (overflow_prob(K, 2 * seg, Kc) <= 2e-6) {
-        // cost ~ keys the selection reads (L * K) times the insert cost (~K); virtual parts restart the lists (cold
-        // thresholds again: C1 went 218 -> 254 us with 16 restarts per block), so they must win by a clear margin
-        const long long keys = 2ll * segs * Kc * Kc * (seg == span ? 4 : 5) / 4;
+        // cost ~ keys the selection reads (L * K) times the insert cost (~K).  Virtual parts restart the lists, but not
+        // cold: the per-query shared threshold (thr_pub) hands a restarted list the best K-th score any list of the
+        // query has reached.  C1 (4300 q x 43 k x 512): K = 16 with 12 natural lists 199 us; K = 8 with 40 lists 181 us
+        // with the shared threshold, 211 us without it (profiles/r02_session_m_stdout.txt).
+        const long long keys = 2ll * segs * Kc * Kc;
         if (keys < best_keys || (keys == best_keys && seg == span)) { best_keys = keys; Ksel = Kc; vq = seg == span ? 1 : seg; }
         break;
       }

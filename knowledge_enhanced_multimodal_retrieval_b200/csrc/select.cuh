@@ -362,6 +362,10 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
   }
 }
 
+// (The body keeps the query widened to binary64 plus two sets of candidate rows in registers: 128 per thread, four
+// 4-warp CTAs per SM, so 1000 queries take two waves.  Measured and rejected: a register cap for 6 / 8 CTAs per SM --
+// the spills cost more than the extra resident warps bring: C2 selection 26.8 -> 57.8 / 26.6 us, C1 56.3 -> 53.5 /
+// 75.4 us, profiles/r02_session_m_stdout.txt.)
 template <int NP, int W>
 __global__ void __launch_bounds__(W * 32) select_kernel(SelectArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
