@@ -1059,7 +1059,9 @@ static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const u
     const size_t o_rp = align_up(qbytes), o_bo = o_rp + align_up((size_t)(Q + 1) * 8), o_co = o_bo + align_up((size_t)nnz * 8);
     const size_t total = o_co + align_up((size_t)nnz * 4);
     // (Measured and rejected: the request as a kernel PARAMETER of 8 KB instead of this copy -- 63.1 vs 62.6 us per
-    // call, the copy's DMA latency and the larger launch cancel; profiles/r02_session_k_stdout.txt.)
+    // call, the copy's DMA latency and the larger launch cancel; profiles/r02_session_k_stdout.txt.  Also rejected: a
+    // completion word in page-locked memory that the kernel writes last and the host spins on instead of the stream
+    // synchronise below -- 63.1 us with the spin, 61.1 us with the synchronise; profiles/r02_session_o_stdout.txt.)
     memcpy(ix->h_blob, q_host, qbytes);
     if (hit_rowptr_host) {
       memcpy(ix->h_blob + o_rp, hit_rowptr_host, (size_t)(Q + 1) * 8);
