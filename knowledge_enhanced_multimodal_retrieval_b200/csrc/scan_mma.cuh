@@ -815,6 +815,9 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (thr_pub && qvalid && list.threshold() > -INFINITY) atomicMax(thr_pub + qg, order_f32(list.threshold()));
       if (dbg) t_fold += clock64() - tf0;
     };
+    // (Measured and rejected, A/B on one box, profiles/r02_session_ab_epilogue_microopts.txt: the append position as a
+    // running shared-memory address instead of counter + multiply-add, and no per-score column bound (rows past the
+    // gallery dropped at fold time instead) -- two instructions fewer per score, C2 unchanged, C1 181.7 -> 192.2 us.)
     // predicated, unrolled: every survivor of an 8-column run goes to the append buffer
     auto append8 = [&](const float* v, uint32_t row) {
 #pragma unroll
