@@ -439,7 +439,13 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
   } while (0)
 #define KEMR_SEL_NP(WV) switch (np) { case 1: KEMR_SEL(1, WV); break; case 2: KEMR_SEL(2, WV); break; \
                                       case 3: KEMR_SEL(3, WV); break; default: KEMR_SEL(4, WV); break; }
-  if (small) { KEMR_SEL_NP(4) } else { KEMR_SEL_NP(8) }
+  // Many queries (several waves of 4-warp CTAs at four CTAs per SM): two warps per query -- the selection is a chain
+  // of dependent phases, so narrower CTAs in twice the number keep more queries in flight.  A/B on one box
+  // (profiles/r02_session_ab_select_warps.txt): C1 (4300 queries) 52.7 -> 40.5 us; C2 (1000 queries, under two waves)
+  // 26.8 -> 33.0 us, so it stays at four.
+  static const int sel_w = getenv("KEMR_SEL_W") ? atoi(getenv("KEMR_SEL_W")) : 0;               // experiments: 2 / 4 / 8
+  const int W = sel_w ? sel_w : (small ? (Q > 12 * dv.sms ? 2 : 4) : 8);
+  if (W == 2) { KEMR_SEL_NP(2) } else if (W == 4) { KEMR_SEL_NP(4) } else { KEMR_SEL_NP(8) }
 #undef KEMR_SEL_NP
 #undef KEMR_SEL
   LAUNCH_CHECK("select_kernel");
