@@ -1044,12 +1044,11 @@ static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const u
   // PCIe, the select kernel stores the results straight into the caller's arrays): no copy engine hop in either
   // direction.  Pageable buffers are staged through the handle's page-locked memory.
   auto mapped = [](const void* p) -> void* {
+    // page-locked host memory: its device view comes with the attributes (one driver call, not two)
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (at.type != cudaMemoryTypeHost) return nullptr;
-    void* d = nullptr;
-    if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return d;
+    return at.devicePointer;
   };
   static const bool no_zero_copy = getenv("KEMR_NO_ZERO_COPY") != nullptr;
   if (Q <= kSmallBatch && !q_bf16) {

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) scan_stream_kernel(const __
         const double wa = a.sel.wq[0] ? a.sel.wq[0][q0 + qq] : a.sel.w[0], wb = a.sel.wq[0] ? a.sel.wq[1][q0 + qq] : a.sel.w[1];
         f = canon_fuse(sa, sb, a.s.G > 1, wa, wb, a.sel.alpha, hit_bonus[j], true);
       }
-      if (lane == 0) const_cast<double*>(a.sel.hit_score)[j] = f;
+      if (lane == 0) const_cast<double*>(a.sel.hit_score)[j - hit_rowptr[0]] = f;     // slots count from the CSR's first entry
     }
   }
 

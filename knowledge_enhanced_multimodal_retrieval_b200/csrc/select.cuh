@@ -25,7 +25,7 @@ struct SelectArgs {
   const int64_t* hit_rowptr;   // [Q+1] or null
   const int32_t* hit_col;
   const double* hit_bonus;
-  const double* hit_score;     // optional [nnz]: canonical FINAL score (bonus included) of every CSR entry, computed ahead of
+  const double* hit_score;     // optional [nnz], entry h - hit_rowptr[0]: canonical FINAL score (bonus included) of CSR entry h, computed ahead of
                                // the selection (fused streaming search: by the CTAs that finish their scan early)
   int k;
   double eps;
@@ -261,7 +261,7 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
       }
       s_bonus[found] = a.hit_bonus[h];
       s_has[found] = 1;
-      if (a.hit_score) { s_score[found] = __ldcg(a.hit_score + h); s_has[found] = 2; }     // already re-scored
+      if (a.hit_score) { s_score[found] = __ldcg(a.hit_score + (h - a.hit_rowptr[0])); s_has[found] = 2; }     // already re-scored
     }
     __syncthreads();
   }

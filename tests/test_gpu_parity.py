@@ -379,6 +379,31 @@ def test_host_search_pipelined_chunks_and_small_batches_equal_the_device_search(
     hi.close()
 
 
+def test_fused_search_accepts_a_csr_window_of_a_larger_hit_table(small_set):
+    """One or two queries take the fused streaming kernel, whose scanning CTAs pre-score the KG hits into a scratch array
+    indexed from the CSR's FIRST entry: a window `rowptr[a:b+1]` into a larger table (absolute offsets, as the chunked
+    host-buffer search passes it) must give the same result as a re-based CSR of the same queries."""
+    q, img, tgt = small_set["query"], small_set["image"], small_set["target"]
+    gi = index.GalleryIndex(img, tgt, uuids=small_set["uuids"])
+    lists = [small_set["kg_results"].get(u, []) for u in small_set["query_uuids"]]
+    hits = gi.hits_from_uuid_lists(lists, 0.2)
+    for a0, n in ((7, 1), (20, 2), (len(lists) - 2, 2)):
+        window = engine.KGHits(hits.rowptr[a0:a0 + n + 1], hits.col, hits.bonus, hits.max_per_query)
+        rebased = hits.subset(torch.arange(a0, a0 + n, device="cuda"))
+        assert int(window.rowptr[0]) > 0 and int(rebased.rowptr[0]) == 0
+        i1, s1 = gi.search(q[a0:a0 + n], k=10, t2i_weight=0.5, t2t_weight=0.5, alpha=0.8, hits=window)
+        i2, s2 = gi.search(q[a0:a0 + n], k=10, t2i_weight=0.5, t2t_weight=0.5, alpha=0.8, hits=rebased)
+        assert torch.equal(i1, i2) and torch.equal(s1, s2)
+        can = O.canon_fused64(O.canon_dot64(q[a0:a0 + n], img), O.canon_dot64(q[a0:a0 + n], tgt), 0.5, 0.5)
+        final = 0.8 * can
+        rp, cc, bb = (x.cpu().numpy() for x in (rebased.rowptr, rebased.col, rebased.bonus))
+        for i in range(n):
+            for h in range(int(rp[i]), int(rp[i + 1])):
+                final[i, cc[h]] = final[i, cc[h]] + bb[h]
+        widx, wscore = O.canon_topk(final, 10)
+        assert np.array_equal(i1.cpu().numpy(), widx) and np.array_equal(s1.cpu().numpy(), wscore)
+
+
 def test_retrieval_engine_end_to_end(small_set):
     q, img, tgt = small_set["query"], small_set["image"], small_set["target"]
     gi = index.GalleryIndex(img, tgt, uuids=small_set["uuids"])
