@@ -268,6 +268,20 @@ int kemr_index_search_host(kemr_index_t* index, const float* q_host, int Q, int 
                            int k, int64_t* out_idx_host, double* out_score64_host,
                            int32_t* out_flags_host);
 
+/* Pipelined use: kemr_index_submit_host queues the same search and returns; kemr_index_wait blocks until the results
+ * are in the caller's arrays.  One search per handle at a time; kemr_index_share makes a second LANE over the same
+ * resident galleries (own stream, workspace and staging buffers; the source handle must outlive it), so that the next
+ * batch's queries cross PCIe while this batch is scanned.  Page-locked caller buffers are used in place and must stay
+ * untouched until the wait returns. */
+int kemr_index_share(kemr_index_t* source, kemr_index_t** out_lane);
+int kemr_index_submit_host(kemr_index_t* index, const float* q_host, int Q, int normalize,
+                           double w_a, double w_b, double alpha,
+                           const int64_t* hit_rowptr_host, const int32_t* hit_col_host,
+                           const double* hit_bonus_host,
+                           int k, int64_t* out_idx_host, double* out_score64_host,
+                           int32_t* out_flags_host);
+int kemr_index_wait(kemr_index_t* index);
+
 /* the same with queries that are already bf16 bit patterns [Q, D] (e.g. the output of a bf16 encoder): half the bytes
  * cross PCIe and no quantise kernel runs. */
 int kemr_index_search_host_bf16(kemr_index_t* index, const uint16_t* q_bf16_host, int Q,

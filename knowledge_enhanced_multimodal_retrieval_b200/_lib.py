@@ -26,6 +26,7 @@ EXPORTS = (
     "kemr_peer_create", "kemr_peer_connect", "kemr_peer_connect_pointers", "kemr_peer_local_buffer", "kemr_peer_destroy",
     "kemr_peer_begin", "kemr_peer_merge", "kemr_merge_topk_strided",
     "kemr_hits_filter_csr", "kemr_hits_target_bonus", "kemr_matrix_mlp2", "kemr_infonce_rows", "kemr_row_norm_max", "kemr_debug_select_stamps", "kemr_index_search_host_bf16", "kemr_peer_gather",
+    "kemr_index_share", "kemr_index_submit_host", "kemr_index_wait",
 )
 
 
@@ -97,6 +98,9 @@ def _declare(lib):
     lib.kemr_peer_merge.argtypes = [p, i32, i32, p, p, p]
     lib.kemr_peer_gather.argtypes = [p, i32, i32, p, p, p]
     lib.kemr_index_search_host.argtypes = [p, p, i32, i32, f64, f64, f64, p, p, p, i32, p, p, p]
+    lib.kemr_index_submit_host.argtypes = [p, p, i32, i32, f64, f64, f64, p, p, p, i32, p, p, p]
+    lib.kemr_index_wait.argtypes = [p]
+    lib.kemr_index_share.argtypes = [p, C.POINTER(C.c_void_p)]
     lib.kemr_index_search_host_bf16.argtypes = [p, p, i32, f64, f64, f64, p, p, p, i32, p, p, p]
     for name in EXPORTS:
         fn = getattr(lib, name)

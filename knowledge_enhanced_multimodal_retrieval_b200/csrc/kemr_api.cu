@@ -957,6 +957,12 @@ static int plan_chunks(int Q, bool page_locked, int* sizes) {
 }
 
 struct kemr_index {
+  bool owns_gal = true;                         // false: a lane created by kemr_index_share (the galleries belong to the source)
+  // a submitted search that has not been waited for: what kemr_index_wait still has to do
+  int pending = 0;                              // 0 none, 1 synchronise only (results already land in the caller's arrays),
+                                                // 2 + copy the handle's page-locked result arrays out, 3 + device-to-host copies first
+  int p_Q = 0, p_k = 0;
+  int64_t* p_idx = nullptr; double* p_score = nullptr; int32_t* p_flags = nullptr;
   uint16_t* gal[2] = {nullptr, nullptr};
   int64_t M = 0;
   int D = 0, max_q = 0, max_k = 0;
@@ -979,7 +985,8 @@ struct kemr_index {
 extern "C" int kemr_index_destroy(kemr_index_t* ix) {
   if (!ix) return KEMR_OK;
   if (ix->stream) cudaStreamSynchronize(ix->stream);
-  cudaFree(ix->gal[0]); cudaFree(ix->gal[1]); cudaFree(ix->ws);
+  if (ix->owns_gal) { cudaFree(ix->gal[0]); cudaFree(ix->gal[1]); }
+  cudaFree(ix->ws);
   cudaFree(ix->d_qf32); cudaFree(ix->d_q); cudaFree(ix->d_score); cudaFree(ix->d_idx); cudaFree(ix->d_flags);
   cudaFree(ix->d_rowptr); cudaFree(ix->d_col); cudaFree(ix->d_bonus);
   cudaFreeHost(ix->h_q); cudaFreeHost(ix->h_score); cudaFreeHost(ix->h_idx); cudaFreeHost(ix->h_flags);
@@ -992,26 +999,17 @@ extern "C" int kemr_index_destroy(kemr_index_t* ix) {
   return KEMR_OK;
 }
 
-extern "C" int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal_b_host, int64_t M, int D,
-                                 int max_queries, int max_k, kemr_index_t** out) {
-  if (!gal_a_host || !out || M <= 0 || D <= 0 || D % 8 || D > kMaxD || max_queries <= 0 || max_k <= 0 || max_k > kMaxKSel - 8)
-    return fail(KEMR_ERR_ARG, "index_create: bad argument");
-  kemr_index* ix = new kemr_index();
-  ix->M = M; ix->D = D; ix->max_q = max_queries; ix->max_k = max_k; ix->hit_cap = (int64_t)max_queries * 256;
-  const size_t gbytes = (size_t)M * D * 2;
+// everything a handle needs besides the galleries: streams, workspace, device and page-locked staging
+static int index_alloc_buffers(kemr_index* ix) {
+  const int64_t M = ix->M; const int D = ix->D; const int max_queries = ix->max_q, max_k = ix->max_k;
+  ix->hit_cap = (int64_t)max_queries * 256;
   const int ksel = std::min(kMaxKSel, (max_k + 6 + 7) / 8 * 8);
   ix->ws_bytes = kemr_workspace_bytes(max_queries, M, D, ksel, 256);
-#define IX_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { kemr_index_destroy(ix); \
-    return fail(KEMR_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } } while (0)
+#define IX_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) \
+    return fail(KEMR_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } while (0)
   IX_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
   IX_TRY(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < kMaxChunks; ++i) IX_TRY(cudaEventCreateWithFlags(&ix->chunk_ev[i], cudaEventDisableTiming));
-  IX_TRY(cudaMalloc(&ix->gal[0], gbytes));
-  IX_TRY(cudaMemcpyAsync(ix->gal[0], gal_a_host, gbytes, cudaMemcpyHostToDevice, ix->stream));
-  if (gal_b_host) {
-    IX_TRY(cudaMalloc(&ix->gal[1], gbytes));
-    IX_TRY(cudaMemcpyAsync(ix->gal[1], gal_b_host, gbytes, cudaMemcpyHostToDevice, ix->stream));
-  }
   IX_TRY(cudaMalloc(&ix->ws, ix->ws_bytes));
   const size_t nq = (size_t)max_queries;
   IX_TRY(cudaMalloc(&ix->d_qf32, nq * D * 4)); IX_TRY(cudaMalloc(&ix->d_q, nq * D * 2));
@@ -1025,9 +1023,66 @@ extern "C" int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal
   IX_TRY(cudaMallocHost(&ix->h_bonus, (size_t)ix->hit_cap * 8));
   ix->blob_bytes = align_up((size_t)kSmallBatch * D * 4) + align_up((size_t)(kSmallBatch + 1) * 8) + (size_t)kSmallBatch * 256 * 12 + 256;
   IX_TRY(cudaMallocHost(&ix->h_blob, ix->blob_bytes)); IX_TRY(cudaMalloc(&ix->d_blob, ix->blob_bytes));
+#undef IX_TRY
+  return KEMR_OK;
+}
+
+extern "C" int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal_b_host, int64_t M, int D,
+                                 int max_queries, int max_k, kemr_index_t** out) {
+  if (!gal_a_host || !out || M <= 0 || D <= 0 || D % 8 || D > kMaxD || max_queries <= 0 || max_k <= 0 || max_k > kMaxKSel - 8)
+    return fail(KEMR_ERR_ARG, "index_create: bad argument");
+  kemr_index* ix = new kemr_index();
+  ix->M = M; ix->D = D; ix->max_q = max_queries; ix->max_k = max_k;
+  const size_t gbytes = (size_t)M * D * 2;
+  int rc = index_alloc_buffers(ix);
+  if (rc) { kemr_index_destroy(ix); return rc; }
+#define IX_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { kemr_index_destroy(ix); \
+    return fail(KEMR_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } } while (0)
+  IX_TRY(cudaMalloc(&ix->gal[0], gbytes));
+  IX_TRY(cudaMemcpyAsync(ix->gal[0], gal_a_host, gbytes, cudaMemcpyHostToDevice, ix->stream));
+  if (gal_b_host) {
+    IX_TRY(cudaMalloc(&ix->gal[1], gbytes));
+    IX_TRY(cudaMemcpyAsync(ix->gal[1], gal_b_host, gbytes, cudaMemcpyHostToDevice, ix->stream));
+  }
   IX_TRY(cudaStreamSynchronize(ix->stream));
 #undef IX_TRY
   *out = ix;
+  return KEMR_OK;
+}
+
+// A second LANE over the same resident galleries: its own stream, workspace and staging buffers, so that a search
+// submitted on one lane overlaps the transfers of the next batch on the other (kemr_index_submit_host / kemr_index_wait).
+// The source handle must outlive its lanes.
+extern "C" int kemr_index_share(kemr_index_t* src, kemr_index_t** out) {
+  if (!src || !out) return fail(KEMR_ERR_ARG, "index_share: null argument");
+  kemr_index* ix = new kemr_index();
+  ix->owns_gal = false;
+  ix->gal[0] = src->gal[0]; ix->gal[1] = src->gal[1];
+  ix->M = src->M; ix->D = src->D; ix->max_q = src->max_q; ix->max_k = src->max_k;
+  int rc = index_alloc_buffers(ix);
+  if (rc) { kemr_index_destroy(ix); return rc; }
+  *out = ix;
+  return KEMR_OK;
+}
+
+// what a submitted search still owes its caller: wait for the stream, bring the results home
+static int index_finish(kemr_index_t* ix) {
+  if (!ix->pending) return KEMR_OK;
+  const int kind = ix->pending;
+  ix->pending = 0;
+  cudaStream_t st = ix->stream;
+  const size_t n = (size_t)ix->p_Q * ix->p_k;
+  if (kind == 3) {
+    CUDA_TRY(cudaMemcpyAsync(ix->h_idx, ix->d_idx, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ix->h_score, ix->d_score, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ix->h_flags, ix->d_flags, (size_t)ix->p_Q * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (kind >= 2) {
+    memcpy(ix->p_idx, ix->h_idx, n * 8);
+    memcpy(ix->p_score, ix->h_score, n * 8);
+    if (ix->p_flags) memcpy(ix->p_flags, ix->h_flags, (size_t)ix->p_Q * 4);
+  }
   return KEMR_OK;
 }
 
@@ -1035,8 +1090,9 @@ extern "C" int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal
 static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const uint16_t* q_bf16, int Q, int normalize,
                                   double w_a, double w_b, double alpha, const int64_t* hit_rowptr_host,
                                   const int32_t* hit_col_host, const double* hit_bonus_host, int k,
-                                  int64_t* out_idx_host, double* out_score64_host, int32_t* out_flags_host) {
+                                  int64_t* out_idx_host, double* out_score64_host, int32_t* out_flags_host, bool wait = true) {
   if (!ix || (!q_host && !q_bf16) || !out_idx_host || !out_score64_host) return fail(KEMR_ERR_ARG, "index_search_host: null pointer");
+  if (ix->pending) return fail(KEMR_ERR_ARG, "index_search_host: a submitted search is still pending on this handle (kemr_index_wait)");
   if (Q <= 0 || Q > ix->max_q || k <= 0 || k > ix->max_k) return fail(KEMR_ERR_ARG, "index_search_host: Q or k beyond the handle's limits");
   cudaStream_t st = ix->stream;
   const size_t qbytes = (size_t)Q * ix->D * 4;
@@ -1094,13 +1150,9 @@ static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const u
                             max_hits, k, ksel, 2e-5, 0, os, nullptr, oi, of, ix->ws, ix->ws_bytes,
                             KEMR_PATH_WARP, st, reinterpret_cast<const float*>(ix->d_blob), normalize);
     if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (!direct) {
-      memcpy(out_idx_host, ix->h_idx, (size_t)Q * k * 8);
-      memcpy(out_score64_host, ix->h_score, (size_t)Q * k * 8);
-      if (out_flags_host) memcpy(out_flags_host, ix->h_flags, (size_t)Q * 4);
-    }
-    return KEMR_OK;
+    ix->pending = direct ? 1 : 2;
+    ix->p_Q = Q; ix->p_k = k; ix->p_idx = out_idx_host; ix->p_score = out_score64_host; ix->p_flags = out_flags_host;
+    return wait ? index_finish(ix) : KEMR_OK;
   }
   const float* q_dev_view = (no_zero_copy || q_bf16) ? nullptr : static_cast<const float*>(mapped(q_host));
   int64_t* oi_view = no_zero_copy ? nullptr : static_cast<int64_t*>(mapped(out_idx_host));
@@ -1173,26 +1225,42 @@ static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const u
     } else if (!q_pinned) {
       memcpy(ix->h_q, q_host, qbytes);
       CUDA_TRY(cudaMemcpyAsync(ix->d_qf32, ix->h_q, qbytes, cudaMemcpyHostToDevice, st));
+    } else if (!wait) {
+      // submitted (pipelined) search: the COPY ENGINE brings the page-locked queries, so the transfer runs beside the
+      // other lane's scan -- the quantise kernel reading them in place cannot: a scan CTA leaves an SM too few
+      // registers for its blocks, and it queued behind the scan (C2: 180 us per step, the sum of transfer and compute)
+      CUDA_TRY(cudaMemcpyAsync(ix->d_qf32, q_host, qbytes, cudaMemcpyHostToDevice, st));
     }
-    rc = q_bf16 ? KEMR_OK : kemr_quantize_rows(q_pinned ? q_dev_view : ix->d_qf32, ix->d_q, Q, ix->D, normalize, st);
+    const bool q_in_place = q_pinned && wait;
+    rc = q_bf16 ? KEMR_OK : kemr_quantize_rows(q_in_place ? q_dev_view : ix->d_qf32, ix->d_q, Q, ix->D, normalize, st);
     if (rc) return rc;
     rc = kemr_scan_topk(ix->d_q, Q, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, alpha, d_rowptr, ix->d_col,
                         ix->d_bonus, max_hits, k, ksel, 2e-5, 0, os_dev, nullptr, oi_dev, of_dev,
                         ix->ws, ix->ws_bytes, KEMR_PATH_AUTO, st);
   }
   if (rc) return rc;
-  if (out_pinned) {
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return KEMR_OK;
-  }
-  CUDA_TRY(cudaMemcpyAsync(ix->h_idx, ix->d_idx, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(ix->h_score, ix->d_score, (size_t)Q * k * 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(ix->h_flags, ix->d_flags, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  memcpy(out_idx_host, ix->h_idx, (size_t)Q * k * 8);
-  memcpy(out_score64_host, ix->h_score, (size_t)Q * k * 8);
-  if (out_flags_host) memcpy(out_flags_host, ix->h_flags, (size_t)Q * 4);
-  return KEMR_OK;
+  ix->pending = out_pinned ? 1 : 3;
+  ix->p_Q = Q; ix->p_k = k; ix->p_idx = out_idx_host; ix->p_score = out_score64_host; ix->p_flags = out_flags_host;
+  return wait ? index_finish(ix) : KEMR_OK;
+}
+
+// The same search without the wait: everything is queued on the handle's stream and the call returns; kemr_index_wait
+// blocks until the results are in the caller's arrays.  One search per handle at a time -- a second lane
+// (kemr_index_share) takes the next batch meanwhile, so its queries cross PCIe while this scan runs.  The caller's
+// buffers (queries, hit CSR, results) must stay untouched until the wait returns when they are page-locked (they are
+// used in place); pageable query / CSR buffers are copied before the call returns.
+extern "C" int kemr_index_submit_host(kemr_index_t* ix, const float* q_host, int Q, int normalize,
+                                      double w_a, double w_b, double alpha, const int64_t* hit_rowptr_host,
+                                      const int32_t* hit_col_host, const double* hit_bonus_host, int k,
+                                      int64_t* out_idx_host, double* out_score64_host, int32_t* out_flags_host) {
+  if (!q_host) return fail(KEMR_ERR_ARG, "index_submit_host: null query pointer");
+  return index_search_host_impl(ix, q_host, nullptr, Q, normalize, w_a, w_b, alpha, hit_rowptr_host, hit_col_host, hit_bonus_host, k,
+                                out_idx_host, out_score64_host, out_flags_host, false);
+}
+
+extern "C" int kemr_index_wait(kemr_index_t* ix) {
+  if (!ix) return fail(KEMR_ERR_ARG, "index_wait: null handle");
+  return index_finish(ix);
 }
 
 extern "C" int kemr_index_search_host(kemr_index_t* ix, const float* q_host, int Q, int normalize,

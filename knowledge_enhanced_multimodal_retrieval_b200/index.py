@@ -94,11 +94,52 @@ class HostIndex:
                                          self.M, self.D, max_queries, max_k, C.byref(h)))
         self._h = h
         self._lib = lib
+        self._source = None
+        self._lanes = []
 
     def close(self):
+        for lane in getattr(self, "_lanes", []):
+            lane.close()
+        self._lanes = []
         if getattr(self, "_h", None):
             self._lib.kemr_index_destroy(self._h)
             self._h = None
+
+    def lane(self) -> "HostIndex":
+        """A second lane over the same resident galleries (`kemr_index_share`): own stream, workspace and staging
+        buffers.  `submit` on one lane while the other is still scanning and the next batch's queries cross PCIe
+        meanwhile; closed together with this index."""
+        if getattr(self, "_source", None) is not None:
+            raise KemrError("lanes are created from the index that owns the galleries")
+        h = C.c_void_p()
+        _lib.check(self._lib.kemr_index_share(self._h, C.byref(h)))
+        other = HostIndex.__new__(HostIndex)
+        other._lib, other._h, other._source, other._lanes = self._lib, h, self, []
+        other.M, other.D, other.max_queries, other.max_k = self.M, self.D, self.max_queries, self.max_k
+        self._lanes = getattr(self, "_lanes", []) + [other]
+        return other
+
+    def submit(self, queries_f32: np.ndarray, k: int = 10, t2i_weight: float = 1.0, t2t_weight: float = 0.0,
+               alpha: float = 1.0, hits_csr=None, normalize: bool = False, out=None):
+        """`search` without the wait (`kemr_index_submit_host`): returns the result arrays at once; they are valid after
+        `wait()`.  One submitted search per lane; page-locked buffers must stay untouched until then."""
+        q = _as(queries_f32, np.float32)
+        Q = q.shape[0]
+        if out is None:
+            out = (np.empty((Q, k), np.int64), np.empty((Q, k), np.float64), np.empty((Q,), np.int32))
+        idx, score, flags = out
+        rp = cc = bb = None
+        if hits_csr is not None:
+            rp, cc, bb = _as(hits_csr[0], np.int64), _as(hits_csr[1], np.int32), _as(hits_csr[2], np.float64)
+        _lib.check(self._lib.kemr_index_submit_host(self._h, _addr(q), Q, int(normalize), float(t2i_weight),
+                                                    float(t2t_weight), float(alpha), _addr(rp), _addr(cc), _addr(bb), k,
+                                                    _addr(idx), _addr(score), _addr(flags)))
+        self._keep = (q, rp, cc, bb, out)                 # the C side reads / writes them until wait()
+        return idx, score, flags
+
+    def wait(self):
+        _lib.check(self._lib.kemr_index_wait(self._h))
+        self._keep = None
 
     def __del__(self):
         try:

@@ -404,6 +404,44 @@ def test_fused_search_accepts_a_csr_window_of_a_larger_hit_table(small_set):
         assert np.array_equal(i1.cpu().numpy(), widx) and np.array_equal(s1.cpu().numpy(), wscore)
 
 
+def test_submit_wait_on_two_lanes_equals_the_blocking_search(small_set):
+    """kemr_index_share / kemr_index_submit_host / kemr_index_wait: two lanes over one resident index, searches kept two
+    deep; every result equals the blocking call's, for page-locked and pageable buffers, with KG hits, and a second
+    submit on a busy lane is refused."""
+    q, img, tgt = small_set["query"], small_set["image"], small_set["target"]
+    hi = index.HostIndex(img, tgt, max_queries=128, max_k=10)
+    lanes = [hi, hi.lane()]
+    gi = index.GalleryIndex(img, tgt, uuids=small_set["uuids"])
+    lists = [small_set["kg_results"].get(u, []) for u in small_set["query_uuids"]]
+    hits = gi.hits_from_uuid_lists(lists, 0.2)
+    rp, cc, bb = hits.rowptr.cpu().numpy(), hits.col.cpu().numpy(), hits.bonus.cpu().numpy()
+    batches = [(0, 1), (1, 2), (3, 40), (43, 50), (10, 3), (60, 1)]
+    for locked in (True, False):
+        mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()) if locked else (lambda a: np.ascontiguousarray(a))
+        pending = [None, None]
+        want_idx, want_score = {}, {}
+        for i, (a0, n) in enumerate(batches):
+            csr = (rp[a0:a0 + n + 1] - rp[a0], cc[int(rp[a0]):int(rp[a0 + n])].copy(), bb[int(rp[a0]):int(rp[a0 + n])].copy())
+            L = lanes[i & 1]
+            if pending[i & 1] is not None:
+                j, res = pending[i & 1]
+                L.wait()
+                assert np.array_equal(res[0], want_idx[j]) and np.array_equal(res[1], want_score[j]), (locked, j)
+            out = (mk(np.zeros((n, 10), np.int64)), mk(np.zeros((n, 10), np.float64)), mk(np.zeros((n,), np.int32)))
+            sub = engine.KGHits(torch.from_numpy(csr[0]).cuda(), torch.from_numpy(csr[1]).cuda(), torch.from_numpy(csr[2]).cuda(), hits.max_per_query)
+            wi, ws = gi.search(q[a0:a0 + n], k=10, t2i_weight=0.5, t2t_weight=0.5, alpha=0.8, hits=sub)
+            want_idx[i], want_score[i] = wi.cpu().numpy(), ws.cpu().numpy()
+            res = L.submit(mk(q[a0:a0 + n]), k=10, t2i_weight=0.5, t2t_weight=0.5, alpha=0.8, hits_csr=csr, out=out)
+            pending[i & 1] = (i, res)
+        with pytest.raises(_lib.KemrError):
+            lanes[0].submit(mk(q[:2]), k=10)                    # lane 0 still has a search in flight
+        for lane_no in (0, 1):
+            j, res = pending[lane_no]
+            lanes[lane_no].wait()
+            assert np.array_equal(res[0], want_idx[j]) and np.array_equal(res[1], want_score[j]), (locked, j)
+    hi.close()
+
+
 def test_retrieval_engine_end_to_end(small_set):
     q, img, tgt = small_set["query"], small_set["image"], small_set["target"]
     gi = index.GalleryIndex(img, tgt, uuids=small_set["uuids"])
