@@ -322,10 +322,6 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
     a.out_score64[o] = sc;
     if (a.out_score32) a.out_score32[o] = (float)sc;
     a.out_idx[o] = gi;
-    for (int d = 0; d < a.n_peer; ++d) {
-      reinterpret_cast<double*>(a.peer_base[d])[peer_o + r] = sc;
-      reinterpret_cast<int64_t*>(a.peer_base[d] + a.peer_idx_region)[peer_o + r] = gi;
-    }
   };
   // rank by counting, one warp per candidate with the lanes spread over the rivals (a thread per candidate walking
   // all rivals is a chain of ~n dependent shared-memory compares: 2.7 us for 33 candidates at batch 1)
@@ -341,7 +337,22 @@ __device__ __forceinline__ void select_query(const SelectArgs& a, const int qi, 
     }
   }
   for (int r = n + tid; r < a.k; r += T) emit(r, -INFINITY, -1);
-  if (a.n_peer > 0) __threadfence_system();                  // rows before the flag, at system scope (peer GPUs)
+  if (a.n_peer > 0) {
+    // The fused all-gather: the k finished rows of this query go to this rank's slot of EVERY rank's exchange buffer.
+    // The rows were just written one at a time by whichever lane ranked them; here the whole CTA copies them out with
+    // consecutive threads on consecutive entries, so a peer receives each array as a few full NVLink write packets
+    // instead of k scattered 8-byte stores issued by one lane (top-100, 4096 queries, 2 GPUs: the selection with the
+    // push took 0.70 ms against 0.53 ms for selection + NCCL all-gather).
+    __syncthreads();                                           // the rows above are visible to the whole CTA
+    const double* ls = a.out_score64 + (size_t)qi * a.k;
+    const int64_t* li = a.out_idx + (size_t)qi * a.k;
+    for (int i = tid; i < a.k * a.n_peer; i += T) {
+      const int d = i / a.k, r = i - d * a.k;
+      reinterpret_cast<double*>(a.peer_base[d])[peer_o + r] = __ldcg(ls + r);          // L2: written by other threads of this CTA
+      reinterpret_cast<int64_t*>(a.peer_base[d] + a.peer_idx_region)[peer_o + r] = (int64_t)__ldcg(reinterpret_cast<const long long*>(li) + r);
+    }
+    __threadfence_system();                                    // rows before the flag, at system scope (peer GPUs)
+  }
   __syncthreads();
   if (a.n_peer > 0 && tid < a.n_peer) {
     unsigned int* flag = reinterpret_cast<unsigned int*>(a.peer_base[tid] + a.peer_flag_region) +
