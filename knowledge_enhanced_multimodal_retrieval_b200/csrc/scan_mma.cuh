@@ -1064,8 +1064,12 @@ inline int make_tmap_2d_uncached(CUtensorMap* map, const void* base, int64_t row
   cuuint64_t strides[1] = {(cuuint64_t)D * 2};
   cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  static const char* l2env = getenv("KEMR_TMAP_L2");                   // experiments: 0 none, 1 64 B, 2 128 B, 3 256 B (default)
+  const CUtensorMapL2promotion promo = !l2env ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+      : (l2env[0] == '0' ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (l2env[0] == '1' ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+      : (l2env[0] == '2' ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B)));
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_mma_error, sizeof g_mma_error, "cuTensorMapEncodeTiled failed (%d) rows=%lld D=%d box=%d", (int)r,
