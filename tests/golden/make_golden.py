@@ -107,6 +107,10 @@ def main():
     m["all_T2I_T2T_mrr_only"] = f64dict(rmetrics.compute_all_retrieval_metrics(
         sq.query, sq.target, sq.image, tasks=["T2I", "T2T"], compute_recall=False))
     m["training"] = f64dict(rmetrics.compute_training_metrics(sq.query, sq.target, sq.image))
+    # the three deprecated shims (metrics.py:285-352): first text variant against itself and against the images
+    m["shim_multi_mode"] = f64dict(quiet(rmetrics.compute_metrics_multi_mode, sq.image, [sq.target, sq.query]))
+    m["shim_single_4train"] = f64dict(quiet(rmetrics.compute_metrics_single_4train, sq.image, [sq.target]))
+    m["shim_multi_4train"] = f64dict(quiet(rmetrics.compute_metrics_multi_4train, sq.image, [sq.query, sq.target]))
     sim = (q @ img.T).astype(np.float32)
     m["recall_at_k_matrix"] = f64dict(rmetrics.compute_recall_at_k(sim))
     m["mrr_matrix"] = f64dict(rmetrics.compute_mrr_and_mean_rank(sim))

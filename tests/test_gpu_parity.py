@@ -228,6 +228,11 @@ def test_metrics_mirror_small_golden(golden, small_set):
     same_dict(fusion.evaluate_retrieval(sim), g["evaluate_retrieval"])
     got = metrics.compute_retrieval_metrics(q, img)
     assert all(isinstance(v, np.float64) for v in got.values())
+    # the three deprecated shims (metrics.py:285-352): first text variant against itself and against the images
+    sq_q, sq_t, sq_i = sq
+    same_dict(metrics.compute_metrics_multi_mode(sq_i, [sq_t, sq_q]), g["shim_multi_mode"])
+    same_dict(metrics.compute_metrics_single_4train(sq_i, [sq_t]), g["shim_single_4train"])
+    same_dict(metrics.compute_metrics_multi_4train(sq_i, [sq_q, sq_t]), g["shim_multi_4train"])
 
 
 def test_metrics_mirror_mid_golden(golden):

@@ -27,6 +27,11 @@ def test_ref_metrics_small(golden, small_set):
     same(O.ref_all_retrieval_metrics(*sq, tasks=["T2I", "T2T"], compute_recall=False),
          g["all_T2I_T2T_mrr_only"])
     same(O.ref_all_retrieval_metrics(*sq, compute_recall=False), g["training"])
+    # deprecated shims (metrics.py:285-352) = the dispatchers on (text, text, image) of the first variant
+    sq_q, sq_t, sq_i = sq
+    same(O.ref_all_retrieval_metrics(sq_t, sq_t, sq_i), g["shim_multi_mode"])
+    same(O.ref_all_retrieval_metrics(sq_t, sq_t, sq_i, compute_recall=False), g["shim_single_4train"])
+    same(O.ref_all_retrieval_metrics(sq_q, sq_q, sq_i, compute_recall=False), g["shim_multi_4train"])
     same(O.ref_recall_at_k(sim), g["recall_at_k_matrix"])
     same(O.ref_mrr_and_mean_rank(sim), g["mrr_matrix"])
     same(O.ref_metrics_from_matrix(sim, prefix="X"), g["metrics_fusion_matrix"])
