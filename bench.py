@@ -61,13 +61,14 @@ def peaks():
     return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def ncu_traffic(workload):
+def ncu_traffic(workload, key="scan_kernel_dram_bytes_per_launch"):
     """dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel per launch, from the committed ncu --set full
-    capture of this workload (profiles/ncu_traffic.json), or None when no capture exists for it."""
+    capture of this workload (profiles/ncu_traffic.json: a capture of an earlier run of the same command, not of this
+    run -- a number printed under ncu is never a bench value), or None when no capture exists for it."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(workload, {}).get("scan_kernel_dram_bytes_per_launch")
+            return json.load(f).get(workload, {}).get(key)
     except (OSError, ValueError):
         return None
 
@@ -697,6 +698,7 @@ def run_ours(args, cfg):
             roof = {"bound": "hbm", "achieved": bytes_ / scan_t / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["traffic"] = ncu_traffic(args.workload)
+        roof["traffic_source"] = ncu_traffic(args.workload, "source")
         roof["algorithmic_bytes"] = bytes_ + Q * D * 2.0
         roof["peak_source"] = pk["source"]
         roof["kernel"] = "scan (first kernel of kemr_scan_topk)"
