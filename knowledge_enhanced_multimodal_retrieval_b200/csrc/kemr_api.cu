@@ -444,8 +444,10 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
   // (profiles/r02_session_ab_select_warps.txt): C1 (4300 queries) 52.7 -> 40.5 us; C2 (1000 queries, under two waves)
   // 26.8 -> 33.0 us, so it stays at four.
   static const int sel_w = getenv("KEMR_SEL_W") ? atoi(getenv("KEMR_SEL_W")) : 0;               // experiments: 2 / 4 / 8
-  const int W = sel_w ? sel_w : (small ? (Q > 12 * dv.sms ? 2 : 4) : 8);
-  if (W == 2) { KEMR_SEL_NP(2) } else if (W == 4) { KEMR_SEL_NP(4) } else { KEMR_SEL_NP(8) }
+  // Up to 64 queries the GPU is nearly empty: sixteen warps per query (one pass over the lists' heads, one round of
+  // re-scoring) -- batch 4 ... 64 at 43 000 rows: 57.2-58.4 -> 52.2-54.2 us per step (profiles/r02_session_x_select16.txt)
+  const int W = sel_w ? sel_w : (small ? (Q > 12 * dv.sms ? 2 : 4) : (Q <= 64 ? 16 : 8));
+  if (W == 2) { KEMR_SEL_NP(2) } else if (W == 4) { KEMR_SEL_NP(4) } else if (W == 16) { KEMR_SEL_NP(16) } else { KEMR_SEL_NP(8) }
 #undef KEMR_SEL_NP
 #undef KEMR_SEL
   LAUNCH_CHECK("select_kernel");
