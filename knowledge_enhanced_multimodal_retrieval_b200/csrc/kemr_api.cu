@@ -418,7 +418,6 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
   if (g_scan_done_event) CUDA_TRY(cudaEventRecord(g_scan_done_event, st));
 
   // one CTA per query: 4 warps for the common small case, 8 when there are many candidates to re-score
-  const bool small = s.max_cand <= kSelSmallCand && Q > 64;   // tiny batches leave the GPU empty: 8 warps per query
   // Programmatic dependent launch: the selection's CTAs become resident while the scan drains (they block in
   // griddepcontrol.wait), so its launch latency and ramp hide behind the scan's tail.  Not when an event has to be
   // recorded between the two kernels (scan timing hook) -- anything between them in the stream makes it an ordinary launch.
@@ -444,9 +443,14 @@ static int scan_topk_impl(const uint16_t* q, int Q, const uint16_t* gal_a, const
   // (profiles/r02_session_ab_select_warps.txt): C1 (4300 queries) 52.7 -> 40.5 us; C2 (1000 queries, under two waves)
   // 26.8 -> 33.0 us, so it stays at four.
   static const int sel_w = getenv("KEMR_SEL_W") ? atoi(getenv("KEMR_SEL_W")) : 0;               // experiments: 2 / 4 / 8
-  // Up to 64 queries the GPU is nearly empty: sixteen warps per query (one pass over the lists' heads, one round of
-  // re-scoring) -- batch 4 ... 64 at 43 000 rows: 57.2-58.4 -> 52.2-54.2 us per step (profiles/r02_session_x_select16.txt)
-  const int W = sel_w ? sel_w : (small ? (Q > 12 * dv.sms ? 2 : 4) : (Q <= 64 ? 16 : 8));
+  // Few queries leave the GPU nearly empty: sixteen warps per query while every query gets an SM of its own (one pass
+  // over the lists' heads, one round of re-scoring), eight up to two per SM.  Batch 4 ... 128 at 43 000 rows: 57-65 ->
+  // 52-54 us per step (profiles/r02_session_x_select16.txt); C2's 1000 queries: 4 warps 26.6 us, 8 warps 37.3, 16 warps 53.
+  int W = 8;
+  if (Q <= dv.sms) W = 16;
+  else if (Q <= 2 * dv.sms || s.max_cand > kSelSmallCand) W = 8;
+  else W = Q > 12 * dv.sms ? 2 : 4;
+  if (sel_w) W = sel_w;
   if (W == 2) { KEMR_SEL_NP(2) } else if (W == 4) { KEMR_SEL_NP(4) } else if (W == 16) { KEMR_SEL_NP(16) } else { KEMR_SEL_NP(8) }
 #undef KEMR_SEL_NP
 #undef KEMR_SEL
