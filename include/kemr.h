@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KEMR_ABI_VERSION 3
+#define KEMR_ABI_VERSION 4
 
 enum {
   KEMR_OK = 0,

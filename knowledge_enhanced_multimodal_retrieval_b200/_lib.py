@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("KEMR_LIB") or os.path.join(_HERE, "libkemr.so")
 KEMR_OK = 0
 PATH_AUTO, PATH_WARP, PATH_MMA = 0, 1, 2
 FLAG_UNCERTIFIED, FLAG_OVERFLOW = 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = (
     "kemr_last_error", "kemr_abi_version", "kemr_device_info", "kemr_quantize_rows", "kemr_synth_rows",

@@ -21,7 +21,7 @@ def test_library_exports_header_symbols():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().kemr_abi_version() == 3
+    assert _lib.load().kemr_abi_version() == 4
 
 
 def test_no_cpu_fallback():
