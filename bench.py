@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the retrieval-scoring hot path (BASELINE.json metric: queries/sec, top-k=10).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c1|b64|b4096|c4|c5_b64|c5_b8192]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2_w19|c3|c1|b64|b4096|c4|c5_b64|c5_b8192]
 
 One "step" = one pass of the hot path over one batch of synthetic queries: similarity scan of
 both galleries + weighted T2I/T2T fusion + top-k selection + canonical re-scoring.  Default
@@ -40,6 +40,7 @@ WORKLOADS = {
     # name: Q, M, D, fused, k, kg
     "c1": dict(Q=4300, M=43000, D=512, fused=False, k=10, seed=0),
     "c2": dict(Q=1000, M=43000, D=768, fused=True, k=10, seed=1),
+    "c2_w19": dict(Q=1000, M=43000, D=768, fused=True, k=10, seed=1, weights=(0.1, 0.9)),   # evaluator.py:193-194: one accumulator per gallery
     "c3": dict(Q=1, M=43000, D=768, fused=True, k=10, seed=1, kg=True),      # + KG-hit boost: alpha 0.8 / beta 0.2, ~Poisson(20) hits
     "b64": dict(Q=64, M=2_000_000, D=768, fused=False, k=10, seed=5, device_synth=True),
     "b4096": dict(Q=4096, M=1_250_000, D=768, fused=False, k=100, seed=4, device_synth=True),
@@ -561,7 +562,7 @@ def run_ours(args, cfg):
     pk = peaks()
     Q, M, D, k = cfg["Q"], cfg["M"], cfg["D"], cfg["k"]
     G = 2 if cfg["fused"] else 1
-    wi, wt = (0.5, 0.5) if cfg["fused"] else (1.0, 0.0)
+    wi, wt = cfg.get("weights", (0.5, 0.5)) if cfg["fused"] else (1.0, 0.0)
 
     # ---- data: same gallery on every rank, per-rank query shard
     if cfg.get("device_synth"):
