@@ -168,3 +168,22 @@ def test_shared_threshold_between_lists_keeps_the_certificate_sound(arg):
         assert out == [r for _, r in truth][:len(out)], (out, truth)
         if M >= k:
             assert len(out) == k
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.sampled_from([(8, 128), (16, 128), (8, 64), (16, 64)]),
+       st.lists(st.integers(-2000, 2000), min_size=128, max_size=128), st.sampled_from([1e-4, 1e-3, 0.25]))
+def test_warm_start_floor_never_drops_a_row_of_the_lists_top_k(shape, ints, grid):
+    """scan_mma.cuh warm start: the first full tile's half of HC columns is cut into K groups and the smallest of the K
+    group maxima, v, becomes the list's first threshold (everything <= the float just below v is dropped).  At least K
+    of the tile's scores are >= v, so no dropped score can belong to the top K of the rows the list goes on to see."""
+    K, HC = shape
+    scores = (np.array(ints[:HC], dtype=np.float64) * grid).astype(np.float32)
+    g = HC // K
+    v = min(scores[j * g:(j + 1) * g].max() for j in range(K))
+    floor = np.nextafter(np.float32(v), np.float32(-np.inf))
+    kept = scores[scores > floor]                                  # the kernel's strict compare against the floor
+    assert kept.size >= K and (scores >= v).sum() >= K
+    kth = np.sort(scores)[::-1][K - 1]                             # K-th largest of the tile (with multiplicity)
+    assert floor < kth                                             # so every top-K score of the tile passes ...
+    assert np.all(scores[scores <= floor] < kth)                   # ... and every dropped one is strictly below all of them
