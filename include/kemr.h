@@ -260,7 +260,11 @@ int kemr_index_destroy(kemr_index_t* index);
  * batches with page-locked caller buffers -> the quantise kernel reads the queries in place over PCIe and the
  * selection kernel writes the caller's arrays in place; pageable caller buffers -> staged through the handle's
  * page-locked buffers, batches of 512 queries and more in chunks (memcpy, transfer and scan of consecutive chunks
- * overlap). */
+ * overlap).
+ * Selection margin: 2e-5 * max(1, |w_a| max||g_a|| + |w_b| max||g_b||), the galleries' largest row norms measured once
+ * at kemr_index_create -- un-normalised galleries or weights above one widen the margin instead of voiding the
+ * certificate.  Queries are unit rows with normalize=1; with normalize=0 they must satisfy ||q|| <= 1 up to bf16
+ * rounding (CLIP embeddings do; otherwise pass normalize=1, which leaves every query's ranking unchanged). */
 int kemr_index_search_host(kemr_index_t* index, const float* q_host, int Q, int normalize,
                            double w_a, double w_b, double alpha,
                            const int64_t* hit_rowptr_host, const int32_t* hit_col_host,

@@ -970,6 +970,7 @@ struct kemr_index {
   int p_Q = 0, p_k = 0;
   int64_t* p_idx = nullptr; double* p_score = nullptr; int32_t* p_flags = nullptr;
   uint16_t* gal[2] = {nullptr, nullptr};
+  float gal_norm[2] = {1.f, 1.f};               // largest row norm of each resident gallery (measured once at creation)
   int64_t M = 0;
   int D = 0, max_q = 0, max_k = 0;
   cudaStream_t stream = nullptr;
@@ -1050,8 +1051,19 @@ extern "C" int kemr_index_create(const uint16_t* gal_a_host, const uint16_t* gal
     IX_TRY(cudaMalloc(&ix->gal[1], gbytes));
     IX_TRY(cudaMemcpyAsync(ix->gal[1], gal_b_host, gbytes, cudaMemcpyHostToDevice, ix->stream));
   }
+  // the selection margin of every search scales with the galleries' largest row norms (index_eps)
+  float* d_norm = reinterpret_cast<float*>(ix->d_blob);
+  for (int g = 0; g < 2; ++g) {
+    if (!ix->gal[g]) continue;
+    if ((rc = kemr_row_norm_max(ix->gal[g], M, D, d_norm + g, ix->stream))) { kemr_index_destroy(ix); return rc; }
+    IX_TRY(cudaMemcpyAsync(&ix->gal_norm[g], d_norm + g, 4, cudaMemcpyDeviceToHost, ix->stream));
+  }
   IX_TRY(cudaStreamSynchronize(ix->stream));
 #undef IX_TRY
+  if (!std::isfinite(ix->gal_norm[0]) || !std::isfinite(ix->gal_norm[1])) {
+    kemr_index_destroy(ix);
+    return fail(KEMR_ERR_ARG, "index_create: the galleries contain non-finite values");
+  }
   *out = ix;
   return KEMR_OK;
 }
@@ -1065,10 +1077,21 @@ extern "C" int kemr_index_share(kemr_index_t* src, kemr_index_t** out) {
   ix->owns_gal = false;
   ix->gal[0] = src->gal[0]; ix->gal[1] = src->gal[1];
   ix->M = src->M; ix->D = src->D; ix->max_q = src->max_q; ix->max_k = src->max_k;
+  ix->gal_norm[0] = src->gal_norm[0]; ix->gal_norm[1] = src->gal_norm[1];
   int rc = index_alloc_buffers(ix);
   if (rc) { kemr_index_destroy(ix); return rc; }
   *out = ix;
   return KEMR_OK;
+}
+
+// Selection margin of a host-buffer search: the bound on |fp32 scan score - canonical score| is 2e-5 for ||q||, ||g|| <= 1
+// and |w_a| + |w_b| <= 1 and scales with max||q|| * (|w_a| max||g_a|| + |w_b| max||g_b||) (engine.eps_for does the same
+// for device-resident searches).  The galleries' norms are index state; the queries are unit rows after normalize = 1
+// and must satisfy ||q|| <= 1 (up to bf16 rounding, as CLIP embeddings do) with normalize = 0 -- kemr.h says so.
+static double index_eps(const kemr_index* ix, double w_a, double w_b) {
+  double s = std::fabs(w_a) * ix->gal_norm[0];
+  if (ix->gal[1]) s += std::fabs(w_b) * ix->gal_norm[1];
+  return 2e-5 * std::max(1.0, s * (1.0 + 1.0 / 128.0));
 }
 
 // what a submitted search still owes its caller: wait for the stream, bring the results home
@@ -1101,6 +1124,7 @@ static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const u
   if (ix->pending) return fail(KEMR_ERR_ARG, "index_search_host: a submitted search is still pending on this handle (kemr_index_wait)");
   if (Q <= 0 || Q > ix->max_q || k <= 0 || k > ix->max_k) return fail(KEMR_ERR_ARG, "index_search_host: Q or k beyond the handle's limits");
   cudaStream_t st = ix->stream;
+  const double eps = index_eps(ix, w_a, w_b);
   const size_t qbytes = (size_t)Q * ix->D * 4;
   // Page-locked caller buffers are used IN PLACE by the kernels (the quantise kernel reads the fp32 queries over
   // PCIe, the select kernel stores the results straight into the caller's arrays): no copy engine hop in either
@@ -1153,7 +1177,7 @@ static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const u
     int rc = scan_topk_impl(ix->d_q, Q, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, nullptr, nullptr, alpha,
                             hit_rowptr_host ? reinterpret_cast<const int64_t*>(ix->d_blob + o_rp) : nullptr,
                             reinterpret_cast<const int32_t*>(ix->d_blob + o_co), reinterpret_cast<const double*>(ix->d_blob + o_bo),
-                            max_hits, k, ksel, 2e-5, 0, os, nullptr, oi, of, ix->ws, ix->ws_bytes,
+                            max_hits, k, ksel, eps, 0, os, nullptr, oi, of, ix->ws, ix->ws_bytes,
                             KEMR_PATH_WARP, st, reinterpret_cast<const float*>(ix->d_blob), normalize);
     if (rc) return rc;
     ix->pending = direct ? 1 : 2;
@@ -1217,7 +1241,7 @@ static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const u
       uint16_t* qc = ix->d_q + (size_t)q0 * ix->D;
       if (!q_bf16 && (rc = kemr_quantize_rows(ix->d_qf32 + (size_t)q0 * ix->D, qc, nq, ix->D, normalize, st))) return rc;
       rc = kemr_scan_topk(qc, nq, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, alpha, d_rowptr ? d_rowptr + q0 : nullptr,
-                          ix->d_col, ix->d_bonus, max_hits, k, ksel, 2e-5, 0, os_dev + (size_t)q0 * k, nullptr,
+                          ix->d_col, ix->d_bonus, max_hits, k, ksel, eps, 0, os_dev + (size_t)q0 * k, nullptr,
                           oi_dev + (size_t)q0 * k, of_dev + q0, ix->ws, ix->ws_bytes, KEMR_PATH_AUTO, st);
       if (rc) return rc;
     }
@@ -1241,7 +1265,7 @@ static int index_search_host_impl(kemr_index_t* ix, const float* q_host, const u
     rc = q_bf16 ? KEMR_OK : kemr_quantize_rows(q_in_place ? q_dev_view : ix->d_qf32, ix->d_q, Q, ix->D, normalize, st);
     if (rc) return rc;
     rc = kemr_scan_topk(ix->d_q, Q, ix->gal[0], ix->gal[1], ix->M, ix->D, w_a, w_b, alpha, d_rowptr, ix->d_col,
-                        ix->d_bonus, max_hits, k, ksel, 2e-5, 0, os_dev, nullptr, oi_dev, of_dev,
+                        ix->d_bonus, max_hits, k, ksel, eps, 0, os_dev, nullptr, oi_dev, of_dev,
                         ix->ws, ix->ws_bytes, KEMR_PATH_AUTO, st);
   }
   if (rc) return rc;

@@ -598,6 +598,27 @@ def test_unnormalised_embeddings_scale_the_margin(path):
     assert np.array_equal(ranks.cpu().numpy(), O.canon_rank(can, np.arange(Q)))
 
 
+@pytest.mark.parametrize("Q", [2, 150])
+def test_host_index_margin_follows_gallery_norms_and_weights(Q):
+    """kemr_index_search_host scales its selection margin with the resident galleries' largest row norms (measured at
+    kemr_index_create) and the weights, like engine.eps_for: galleries of norm ~10 / ~7 and weights above one, unit
+    queries -- the small-batch and the large-batch route both return the oracle's top-k with every query certified."""
+    D, M = 256, 3000
+    rng = np.random.default_rng(10)
+    img = synth.round_to_bf16(rng.standard_normal((M, D), dtype=np.float32) * np.float32(10.0 / np.sqrt(D)))
+    tgt = synth.round_to_bf16(rng.standard_normal((M, D), dtype=np.float32) * np.float32(7.0 / np.sqrt(D)))
+    q = img[:Q] * np.float32(0.3) + rng.standard_normal((Q, D), dtype=np.float32) * np.float32(3.0 / np.sqrt(D))
+    q = synth.round_to_bf16(q / np.linalg.norm(q.astype(np.float64), axis=1, keepdims=True).astype(np.float32) * np.float32(0.995))
+    assert float(np.linalg.norm(q.astype(np.float64), axis=1).max()) <= 1.0
+    wa, wb = 1.5, 2.25
+    hi = index.HostIndex(img, tgt, max_queries=256, max_k=10)
+    idx, sc, fl = hi.search(q, k=10, t2i_weight=wa, t2t_weight=wb)
+    hi.close()
+    can = O.canon_fused64(O.canon_dot64(q, img), O.canon_dot64(q, tgt), wa, wb)
+    widx, wsc = O.canon_topk(can, 10)
+    assert np.array_equal(idx, widx) and np.array_equal(sc, wsc) and not fl.any()
+
+
 def test_sharded_index_maps_global_ids_to_its_own_uuid_slice(small_set):
     """A shard with idx_base > 0 returns GLOBAL row ids; CLIPRetriever.search must look them up in the shard's own
     uuid slice."""
