@@ -137,9 +137,11 @@ def reference_step(q, img, tgt, wi, wt, k, kg=None):
         if sim.shape[0] > sim.shape[1]:
             raise ValueError("KG workloads are square or wide")
         return np.argsort(-sim, axis=1)[:, :k]             # serving: the ranked list (retrieval.py:74)
+    # sort_kind=None: numpy's default argsort, the reference's own call (metrics.py:34,62) -- the oracle's stable kind
+    # is ~4x slower on fp32 rows and would understate the reference (profiles/r02_port_vs_reference_cpu.json)
     if tgt is not None:
-        return O.ref_retrieval_metrics_final(q, tgt, img, k_values=[1, 5, 10], t2i_weight=wi, t2t_weight=wt)
-    return O.ref_retrieval_metrics(q, img, k_values=[1, 5, 10])
+        return O.ref_retrieval_metrics_final(q, tgt, img, k_values=[1, 5, 10], t2i_weight=wi, t2t_weight=wt, sort_kind=None)
+    return O.ref_retrieval_metrics(q, img, k_values=[1, 5, 10], sort_kind=None)
 
 
 def argsort_topk_step(q, img, tgt, wi, wt, k):
