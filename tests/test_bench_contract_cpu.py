@@ -29,3 +29,24 @@ def test_reference_arm_json_line():
 
 def test_reference_arm_other_ranks_stay_silent():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}).strip() == ""
+
+
+def test_reference_step_sorts_like_the_reference_not_like_the_oracle(monkeypatch):
+    """The timing legs must call numpy's argsort the way the reference does (`np.argsort(-S, axis=1)`, default kind:
+    metrics.py:34,62) -- the oracle's stable kind is ~4x slower on fp32 rows and would understate the reference
+    (profiles/r02_port_vs_reference_cpu.json).  The parity legs keep the stable kind."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import oracle as O
+    kinds = []
+    real = np.argsort
+    monkeypatch.setattr(np, "argsort", lambda a, *args, **kw: (kinds.append(kw.get("kind")), real(a, *args, **kw))[1])
+    rng = np.random.default_rng(0)
+    q, img, tgt = (rng.standard_normal((n, 32), dtype=np.float32) for n in (6, 40, 40))
+    timed = bench.reference_step(q, img, tgt, 0.5, 0.5, 10)
+    assert kinds == [None, None]                         # two full-row argsorts, both the reference's own call
+    kinds.clear()
+    assert bench.reference_step(q, img, None, 1.0, 0.0, 10) == O.ref_retrieval_metrics(q, img, k_values=[1, 5, 10])
+    assert kinds == [None, None, "stable", "stable"]
+    assert timed == O.ref_retrieval_metrics_final(q, tgt, img, k_values=[1, 5, 10])     # tie-free data: same metrics
